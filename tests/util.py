@@ -1,0 +1,50 @@
+"""Shared helpers for the tests (fixtures loading, tolerances)."""
+import json
+import os
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load_npz(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def state_from(npz, prefix, dtype=torch.float32, device='cpu'):
+    sd = {}
+    for k in npz.files:
+        if k.startswith(prefix):
+            t = torch.from_numpy(np.array(npz[k]))
+            if t.is_floating_point():
+                t = t.to(dtype)
+            sd[k[len(prefix):]] = t.to(device)
+    return sd
+
+
+def opt_from(npz):
+    return Namespace(**json.loads(str(npz['opt'])))
+
+
+def T(a, dtype=torch.float32, device='cpu'):
+    return torch.from_numpy(np.array(a)).to(dtype).to(device)
+
+
+def rel_err(a, b):
+    """max |a-b| / (max|b| + tiny): the 'relative fp32' measure used for parity."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def grad_err(a, b, floor=1e-5):
+    """Gradient comparison: like rel_err but with an absolute floor on the scale, so
+    mathematically-zero gradients (e.g. a conv bias that feeds a BatchNorm) that
+    only carry rounding noise do not produce spurious relative errors."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    if float(a.abs().max()) < floor and float(b.abs().max()) < floor:
+        return 0.0
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor))
