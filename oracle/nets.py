@@ -340,7 +340,9 @@ def generator_losses(sdG, sdD, opt, tgt_label, tgt_image, ref_labels, ref_images
     ref_label, ref_image = ref_labels[:, 0], ref_images[:, 0]
     pred = discriminator_forward(sdD, d_input(tgt_label, fake, tgt_image, ref_label, ref_image), n_layers_D, num_D)
     pf, pr = split_pred(pred)
-    losses = {'G_GAN': ops.gan_loss(pf, True, for_discriminator=False),
+    # loss_collector.py:66 calls criterionGAN(pred_fake, True) WITHOUT for_discriminator=False, so the
+    # generator's GAN term is the discriminator-style hinge -mean(min(D(fake)-1, 0)) (loss.py:72-75).
+    losses = {'G_GAN': ops.gan_loss(pf, True, for_discriminator=True),
               'G_GAN_Feat': ops.feat_match_loss(pr, pf, opt.lambda_feat)}
     if flow[0] is not None:
         losses['F_Warp'] = (warp[0] - tgt_image).abs().mean() * opt.lambda_flow   # loss_collector.py:154-162
