@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Build libfsv_b200.so (sm_100a only) in-tree with nvcc.  Used by __graft_entry__.build()."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OUT = os.path.join(HERE, 'fsv', 'libfsv_b200.so')
+SOURCES = ['core.cu', 'layout.cu', 'norm.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_dispatch.cu', 'spade.cu', 'warp.cu', 'softmax.cu']
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math' if False else '-DFSV_NO_FAST_MATH',
+         '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default']
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'fsv_b200.h'), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    objs = []
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
+        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            print('== %s\n%s' % (src, out))
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError('nvcc failed')
+    cmd = [NVCC, '-shared', '-o', OUT] + objs  # static cudart; the driver API (TMA descriptors) is resolved at run time
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,191 @@
+// Layout plumbing kernels: NCHW<->NHWC packing at the module boundary, channel-slice
+// copies (concat), nearest x2 upsample, 3x3/s2 average pooling, activation backward.
+// All are pure streaming kernels (HBM-bound, no reuse): coalesced along the contiguous
+// dimension, grid-stride loops sized to a multiple of the SM count.
+#include "common.cuh"
+
+static inline int stream_grid(long long work_items, int threads) {
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = (long long)fsv_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// one thread per (n, hw): reads are coalesced along hw for every c, writes are C-contiguous per thread
+__global__ void k_nchw_to_nhwc(const float* __restrict__ src, float* __restrict__ dst, int N, int C, long long HW,
+                               int ld, int coff) {
+    long long total = (long long)N * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long n = i / HW, p = i - n * HW;
+        const float* s = src + n * C * HW + p;
+        float* d = dst + i * ld + coff;
+        for (int c = 0; c < C; ++c) d[c] = s[(long long)c * HW];
+    }
+}
+__global__ void k_nhwc_to_nchw(const float* __restrict__ src, float* __restrict__ dst, int N, int C, long long HW,
+                               int ld, int coff, int accumulate) {
+    long long total = (long long)N * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long n = i / HW, p = i - n * HW;
+        const float* s = src + i * ld + coff;
+        float* d = dst + n * C * HW + p;
+        for (int c = 0; c < C; ++c) {
+            float v = s[c];
+            if (accumulate) d[(long long)c * HW] += v; else d[(long long)c * HW] = v;
+        }
+    }
+}
+extern "C" int fsv_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, int dst_coff, void* stream) {
+    FSV_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && dst_ld >= dst_coff + C, "nchw_to_nhwc: bad dims");
+    long long HW = (long long)H * W;
+    k_nchw_to_nhwc<<<stream_grid(N * HW, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, N, C, HW, dst_ld, dst_coff);
+    FSV_CHECK_LAUNCH("nchw_to_nhwc");
+    return FSV_OK;
+}
+extern "C" int fsv_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int src_ld, int src_coff,
+                                int accumulate, void* stream) {
+    FSV_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && src_ld >= src_coff + C, "nhwc_to_nchw: bad dims");
+    long long HW = (long long)H * W;
+    k_nhwc_to_nchw<<<stream_grid(N * HW, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, N, C, HW, src_ld, src_coff, accumulate);
+    FSV_CHECK_LAUNCH("nhwc_to_nchw");
+    return FSV_OK;
+}
+
+__global__ void k_copy_channels(const float* __restrict__ src, int sld, int scoff, float* __restrict__ dst, int dld, int dcoff,
+                                long long rows, int C, int accumulate) {
+    long long total = rows * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / C;
+        int c = (int)(i - r * C);
+        float v = src[r * sld + scoff + c];
+        float* d = dst + r * dld + dcoff + c;
+        if (accumulate) *d += v; else *d = v;
+    }
+}
+extern "C" int fsv_copy_channels(const float* src, int src_ld, int src_coff, float* dst, int dst_ld, int dst_coff,
+                                 long long rows, int C, int accumulate, void* stream) {
+    FSV_REQUIRE(rows > 0 && C > 0 && src_ld >= src_coff + C && dst_ld >= dst_coff + C, "copy_channels: bad dims");
+    k_copy_channels<<<stream_grid(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(src, src_ld, src_coff, dst, dst_ld, dst_coff, rows, C, accumulate);
+    FSV_CHECK_LAUNCH("copy_channels");
+    return FSV_OK;
+}
+
+// y (N,2Hs,2Ws,C) <- x (N,Hs,Ws,C): one thread per output element (C contiguous => coalesced both sides)
+__global__ void k_up2_fwd(const float* __restrict__ x, float* __restrict__ y, int N, int Hs, int Ws, int C) {
+    long long total = (long long)N * Hs * 2 * Ws * 2 * C;
+    int W = Ws * 2, H = Hs * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long p = i / C;
+        int w = (int)(p % W);
+        long long q = p / W;
+        int h = (int)(q % H);
+        long long n = q / H;
+        y[i] = x[((n * Hs + (h >> 1)) * Ws + (w >> 1)) * C + c];
+    }
+}
+__global__ void k_up2_bwd(const float* __restrict__ dy, float* __restrict__ dx, int N, int Hs, int Ws, int C) {
+    long long total = (long long)N * Hs * Ws * C;
+    int W = Ws * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long p = i / C;
+        int w = (int)(p % Ws);
+        long long q = p / Ws;
+        int h = (int)(q % Hs);
+        long long n = q / Hs;
+        const float* b = dy + (((n * Hs * 2 + 2 * h) * W) + 2 * w) * C + c;
+        dx[i] = b[0] + b[C] + b[(long long)W * C] + b[(long long)W * C + C];
+    }
+}
+extern "C" int fsv_upsample2x_fwd(const float* x, float* y, int N, int Hs, int Ws, int C, void* stream) {
+    FSV_REQUIRE(N > 0 && Hs > 0 && Ws > 0 && C > 0, "upsample2x: bad dims");
+    k_up2_fwd<<<stream_grid((long long)N * Hs * Ws * 4 * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, Hs, Ws, C);
+    FSV_CHECK_LAUNCH("upsample2x_fwd");
+    return FSV_OK;
+}
+extern "C" int fsv_upsample2x_bwd(const float* dy, float* dx, int N, int Hs, int Ws, int C, void* stream) {
+    FSV_REQUIRE(N > 0 && Hs > 0 && Ws > 0 && C > 0, "upsample2x: bad dims");
+    k_up2_bwd<<<stream_grid((long long)N * Hs * Ws * C, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, Hs, Ws, C);
+    FSV_CHECK_LAUNCH("upsample2x_bwd");
+    return FSV_OK;
+}
+
+// AvgPool2d(3, s2, p1, count_include_pad=False): Ho = (H+2-3)/2+1
+__global__ void k_avgpool_fwd(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+    long long total = (long long)N * Ho * Wo * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long p = i / C;
+        int wo = (int)(p % Wo);
+        long long q = p / Wo;
+        int ho = (int)(q % Ho);
+        long long n = q / Ho;
+        float s = 0.f;
+        int cnt = 0;
+        for (int r = -1; r <= 1; ++r) {
+            int h = 2 * ho + r;
+            if (h < 0 || h >= H) continue;
+            for (int t = -1; t <= 1; ++t) {
+                int w = 2 * wo + t;
+                if (w < 0 || w >= W) continue;
+                s += x[((n * H + h) * W + w) * C + c];
+                ++cnt;
+            }
+        }
+        y[i] = s / (float)cnt;
+    }
+}
+// gather form of the adjoint: dx[h,w] = sum over outputs whose window covers (h,w) of dy/cnt(out)
+__global__ void k_avgpool_bwd(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+    long long total = (long long)N * H * W * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long p = i / C;
+        int w = (int)(p % W);
+        long long q = p / W;
+        int h = (int)(q % H);
+        long long n = q / H;
+        float s = 0.f;
+        for (int ho = (h) / 2; ho <= (h + 1) / 2; ++ho) {     // 2*ho-1 <= h <= 2*ho+1
+            if (ho < 0 || ho >= Ho) continue;
+            int ch = min(2 * ho + 1, H - 1) - max(2 * ho - 1, 0) + 1;
+            for (int wo = (w) / 2; wo <= (w + 1) / 2; ++wo) {
+                if (wo < 0 || wo >= Wo) continue;
+                int cw = min(2 * wo + 1, W - 1) - max(2 * wo - 1, 0) + 1;
+                s += dy[((n * Ho + ho) * Wo + wo) * C + c] / (float)(ch * cw);
+            }
+        }
+        dx[i] = s;
+    }
+}
+extern "C" int fsv_avgpool3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+    FSV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "avgpool: bad dims");
+    int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    k_avgpool_fwd<<<stream_grid((long long)N * Ho * Wo * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C, Ho, Wo);
+    FSV_CHECK_LAUNCH("avgpool_fwd");
+    return FSV_OK;
+}
+extern "C" int fsv_avgpool3s2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
+    FSV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "avgpool: bad dims");
+    int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    k_avgpool_bwd<<<stream_grid((long long)N * H * W * C, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C, Ho, Wo);
+    FSV_CHECK_LAUNCH("avgpool_bwd");
+    return FSV_OK;
+}
+
+__global__ void k_act_bwd(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ g, long long n,
+                          int act, float out_scale) {
+    float inv = 1.f / out_scale;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float yy = y[i] * inv;   // value before out_scale
+        g[i] = dy[i] * out_scale * fsv_act_grad(yy, act);
+    }
+}
+extern "C" int fsv_act_bwd(const float* y, const float* dy, float* g, long long n, int act, float out_scale, void* stream) {
+    FSV_REQUIRE(n > 0 && out_scale != 0.f, "act_bwd: bad args");
+    k_act_bwd<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(y, dy, g, n, act, out_scale);
+    FSV_CHECK_LAUNCH("act_bwd");
+    return FSV_OK;
+}

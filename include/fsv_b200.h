@@ -1,0 +1,175 @@
+/*
+ * fsv_b200.h -- C ABI of the B200-native (sm_100a) few-shot vid2vid hot path.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b).  The reference has no FFI
+ * of its own on this path: every hot op is an ATen/cuDNN library call made from the
+ * nn.Modules returned by models/networks/__init__.py:29-55 (define_G / define_D).
+ * Each entry point below therefore cites the reference call site(s) whose library
+ * call it replaces.  The Python host side (few-shot-vid2vid_b200/fsv) binds these
+ * with ctypes from torch.autograd.Function wrappers; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++ / torch types cross the boundary.
+ *  - every function returns 0 on success, a negative FSV_E* code on error;
+ *    fsv_last_error() returns a thread-local message for the last failure.
+ *  - all pointers are DEVICE pointers on the current CUDA device; work is enqueued
+ *    on the cudaStream_t passed last (as void*); nothing synchronises the host.
+ *  - activations are fp32 NHWC: element (n,h,w,c) of a buffer with channel stride
+ *    `ld` and channel offset `coff` lives at ((n*H + h)*W + w)*ld + coff + c.  A
+ *    consumer/producer can thus address a channel slice of a wider (concatenated)
+ *    buffer without a copy.
+ *  - conv weights are "OHWI": w[co][r][s][ci] (Cout, kh, kw, Cin) contiguous.
+ *    A per-sample weight (the hyper-network's output, base_network.py:56-71
+ *    batch_conv) is addressed as w + n*w_nstride.
+ *  - caller allocates all outputs and workspaces.
+ */
+#ifndef FSV_B200_H_
+#define FSV_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSV_OK 0
+#define FSV_EINVAL (-1)   /* bad argument / unsupported shape */
+#define FSV_ECUDA (-2)    /* CUDA runtime or launch error */
+#define FSV_ENOTSUP (-3)  /* valid request this build cannot serve (e.g. no tcgen05 path) */
+
+/* activation codes fused into producers */
+#define FSV_ACT_NONE 0
+#define FSV_ACT_LRELU 1    /* LeakyReLU(0.2): architecture.py:15-17 */
+#define FSV_ACT_TANH 2     /* generator.py:211 */
+#define FSV_ACT_SIGMOID 3  /* generator.py:487 conv_mask */
+
+/* normalisation grouping */
+#define FSV_NORM_BATCH 0     /* statistics over (N,H,W): SyncBatchNorm local stats, normalization.py:33,80 */
+#define FSV_NORM_INSTANCE 1  /* statistics over (H,W) per sample: InstanceNorm2d, normalization.py:35,82 */
+
+const char* fsv_last_error(void);
+int fsv_version(void);
+/* sm count and compute capability of the current device */
+int fsv_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ layout plumbing */
+/* NCHW (contiguous) -> NHWC slice.  Replaces the implicit layout of every reference tensor
+ * at the module boundary (generator.py:181 inputs, discriminator.py:49 input). */
+int fsv_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, int dst_coff, void* stream);
+/* NHWC slice -> NCHW (contiguous); with accumulate!=0 adds into dst (gradient of the above). */
+int fsv_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int src_ld, int src_coff,
+                     int accumulate, void* stream);
+/* copy a channel slice: dst[row, dcoff+c] = src[row, scoff+c]  (torch.cat on dim 1: generator.py:441-443,562-563) */
+int fsv_copy_channels(const float* src, int src_ld, int src_coff, float* dst, int dst_ld, int dst_coff,
+                      long long rows, int C, int accumulate, void* stream);
+/* nearest x2 upsample (generator.py:124,207; nn.Upsample(scale_factor=2) generator.py:484,537) and its adjoint */
+int fsv_upsample2x_fwd(const float* x, float* y, int N, int Hs, int Ws, int C, void* stream);
+int fsv_upsample2x_bwd(const float* dy, float* dx, int N, int Hs, int Ws, int C, void* stream);
+/* AvgPool2d(3, stride 2, pad 1, count_include_pad=False): discriminator.py:28 */
+int fsv_avgpool3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int fsv_avgpool3s2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
+/* g = dy * act'(y) given the post-activation output y (out_scale is applied after act) */
+int fsv_act_bwd(const float* y, const float* dy, float* g, long long n, int act, float out_scale, void* stream);
+
+/* ------------------------------------------------------------------ convolution / linear */
+/* One descriptor for F.conv2d (architecture.py:60,81-84; generator.py:473-489,523-537;
+ * discriminator.py:69-88), F.linear (generator.py:260-270: N=1,H=rows,W=1,k=1) and the
+ * per-sample batch_conv (base_network.py:56-71: w_nstride != 0). */
+typedef struct fsv_conv_desc {
+    int N, H, W, Cin;      /* conv input dims (H,W are AFTER the optional upsample-on-load) */
+    int x_ld, x_coff;      /* input buffer channel stride / offset */
+    int up;                /* 1, or 2 = nearest x2 upsample on load (buffer is H/2 x W/2) */
+    int Cout, kh, kw, stride, pad;
+    int Ho, Wo;            /* output dims */
+    int y_ld, y_coff;      /* output buffer channel stride / offset */
+    int act;               /* FSV_ACT_* fused after bias (+residual) */
+    float out_scale;       /* multiplies the result after act (generator.py:502 flow_multiplier) */
+    long long w_nstride;   /* 0 = shared weight; else floats between per-sample weights */
+    long long b_nstride;   /* same for the bias */
+    int res_ld, res_coff;  /* residual buffer (added before act), used when residual != NULL */
+    int use_tc;            /* 0 = SIMT path, 1 = tcgen05/TMA path (FSV_ENOTSUP if the shape is not eligible), -1 = auto */
+} fsv_conv_desc;
+
+/* y = act(conv(x, w) + bias + residual) * out_scale */
+int fsv_conv2d_fwd(const fsv_conv_desc* d, const float* x, const float* w, const float* bias,
+                   const float* residual, float* y, void* stream);
+/* dx (at conv-input resolution H x W, channel stride x_ld/x_coff) = conv_transpose(dy, w); accumulate!=0 adds */
+int fsv_conv2d_dgrad(const fsv_conv_desc* d, const float* dy, const float* w, float* dx, int accumulate, void* stream);
+/* dw[co][r][s][ci] (+= if accumulate) = sum_pixels dy * x ; per-sample when w_nstride != 0.
+ * dbias (may be NULL) = sum_pixels dy (per sample when b_nstride != 0). */
+int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                     int accumulate, void* stream);
+/* 1 if the tcgen05/TMA implicit-GEMM path can serve this descriptor (fwd) */
+int fsv_conv2d_tc_eligible(const fsv_conv_desc* d);
+
+/* ------------------------------------------------------------------ normalisation */
+/* per-(group, channel) sum and sum of squares of an NHWC slice; groups = 1 (batch) or N (instance).
+ * Outputs are DOUBLE [groups*C] (zeroed by the call). */
+int fsv_norm_stats(const float* x, int N, int HW, int C, int ld, int coff, int mode, double* sum, double* sumsq, void* stream);
+/* mean/rstd from the sums; for mode batch + training also the running-stat update of
+ * F.batch_norm (momentum, unbiased variance; count = elements per channel as seen by the reference). */
+int fsv_norm_finalize(const double* sum, const double* sumsq, int groups, int C, double count, float eps,
+                      float momentum, float* running_mean, float* running_var, int update_running,
+                      float* mean, float* rstd, void* stream);
+/* eval-mode stats from running buffers: mean = running_mean, rstd = 1/sqrt(running_var+eps) */
+int fsv_norm_from_running(const float* running_mean, const float* running_var, int C, float eps,
+                          float* mean, float* rstd, void* stream);
+/* y = act((x-mean)*rstd*weight + bias); weight/bias may be NULL.
+ * Replaces BatchNorm/InstanceNorm + LeakyReLU pairs (architecture.py:65-68; generator.py:473-486; discriminator.py:76-85). */
+int fsv_norm_apply_fwd(const float* x, const float* mean, const float* rstd, const float* weight, const float* bias,
+                       float* y, int N, int HW, int C, int mode, int act, void* stream);
+/* backward of the above given y (for the activation mask) and dy:
+ *   g = dy*act'(y)*weight;  dx = rstd*(g - S1/cnt - xhat*S2/cnt)  (batch_stats!=0)  or  rstd*g  (eval)
+ *   dweight += sum dy'*xhat, dbias += sum dy'  (when weight != NULL; buffers are zeroed by the call)
+ * scratch: double[2*groups*C]. */
+int fsv_norm_apply_bwd(const float* x, const float* y, const float* dy, const float* mean, const float* rstd,
+                       const float* weight, float* dx, float* dweight, float* dbias, double* scratch,
+                       int N, int HW, int C, int mode, int act, int batch_stats, void* stream);
+
+/* ------------------------------------------------------------------ fused SPADE (normalization.py:37-52 + architecture.py:96-97) */
+#define FSV_SPADE_MAX_MAPS 3
+typedef struct fsv_spade_desc {
+    int N, H, W, C;            /* output dims; x buffer is (N, H/up, W/up, C) contiguous */
+    int up;                    /* 1 or 2: nearest x2 upsample of x on load (generator.py:207 feeding bn_0/bn_s) */
+    int mode;                  /* FSV_NORM_BATCH / FSV_NORM_INSTANCE: layout of mean/rstd ([C] or [N*C]) */
+    int act;                   /* FSV_ACT_NONE (shortcut, architecture.py:103) or FSV_ACT_LRELU */
+    int nmaps;                 /* 1..3 label maps (None maps are dropped by the caller) */
+    int K[FSV_SPADE_MAX_MAPS];         /* hidden channels of map i */
+    int m_ld[FSV_SPADE_MAX_MAPS];      /* channel stride of map i's buffer (map is N,H,W,K at offset m_coff) */
+    int m_coff[FSV_SPADE_MAX_MAPS];
+    long long w_nstride[FSV_SPADE_MAX_MAPS];  /* 0 = fixed mlp_gamma/mlp_beta weights; else per-sample stride (hyper-weights) */
+} fsv_spade_desc;
+/* out = act( (((x-mean)*rstd) * (1+g_0) + b_0) * (1+g_1) + b_1 ... ),  g_i = Wg_i . map_i + bg_i  (1x1) */
+int fsv_spade_fwd(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
+                  const float* const* maps, const float* const* wg, const float* const* bg,
+                  const float* const* wb, const float* const* bb, float* out, void* stream);
+/* Backward.  Recomputes gamma/beta and the pre-activation value (so `out` is not needed), walks the modulation chain backwards and emits
+ *   dxhat  (N,H,W,C): gradient w.r.t. the normalised activation (feed to fsv_spade_norm_bwd)
+ *   dgamma[i], dbeta[i] (N,H,W,C each): gradients of the 1x1 conv outputs (feed to fsv_conv2d_dgrad/wgrad) */
+int fsv_spade_bwd(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
+                  const float* const* maps, const float* const* wg, const float* const* bg,
+                  const float* const* wb, const float* const* bb, const float* dout,
+                  float* dxhat, float* const* dgamma, float* const* dbeta, void* stream);
+/* dx (N,H/up,W/up,C) from dxhat: batch_stats!=0: rstd*(sum_children(g) - k*S1/cnt - k*xhat*S2/cnt), else rstd*sum(g).
+ * scratch: double[2*groups*C]. */
+int fsv_spade_norm_bwd(const float* x, const float* dxhat, const float* mean, const float* rstd, float* dx,
+                       double* scratch, int N, int H, int W, int C, int up, int mode, int batch_stats, void* stream);
+
+/* ------------------------------------------------------------------ warp + composite (base_network.py:13-37; generator.py:431-443,214-224) */
+/* img (N,H,W,Ci) NHWC, flow (N,H,W,2) in pixels (x,y), mask (N,H,W,1) or NULL, raw (N,H,W,Ci) or NULL.
+ * out (N,H,W,out_ld) at out_coff:  blend==0: out[..,0:Ci] = warp, out[..,Ci] = mask (the [warp,mask] concat, when mask!=NULL)
+ *                                   blend==1: out[..,0:Ci] = raw*mask + warp*(1-mask)  (generator.py:217,224) */
+int fsv_warp_fwd(const float* img, const float* flow, const float* mask, const float* raw, float* out,
+                 int N, int H, int W, int Ci, int out_ld, int out_coff, int blend, void* stream);
+/* gradients: dflow (N,H,W,2), dmask (N,H,W,1) (may be NULL), draw (may be NULL), dimg (may be NULL; atomically accumulated, caller zeroes) */
+int fsv_warp_bwd(const float* img, const float* flow, const float* mask, const float* raw, const float* dout,
+                 float* dflow, float* dmask, float* draw, float* dimg,
+                 int N, int H, int W, int Ci, int out_ld, int out_coff, int blend, void* stream);
+
+/* ------------------------------------------------------------------ reference-feature softmax (generator.py:385) */
+/* row-wise softmax over C for rows x C contiguous; and its backward dx = y*(dy - sum(dy*y)) */
+int fsv_softmax_rows_fwd(const float* x, float* y, long long rows, int C, void* stream);
+int fsv_softmax_rows_bwd(const float* y, const float* dy, float* dx, long long rows, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSV_B200_H_ */
