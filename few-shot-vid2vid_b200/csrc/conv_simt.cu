@@ -27,6 +27,7 @@ struct ConvP {
     float out_scale;
     long long w_nstride, b_nstride;
     int res_ld, res_coff;
+    int in_act;
     int accumulate;
 };
 
@@ -35,7 +36,7 @@ static ConvP make_p(const fsv_conv_desc* d, int accumulate) {
     p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.x_ld = d->x_ld; p.x_coff = d->x_coff; p.up = d->up;
     p.Cout = d->Cout; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.Ho = d->Ho; p.Wo = d->Wo;
     p.y_ld = d->y_ld; p.y_coff = d->y_coff; p.act = d->act; p.out_scale = d->out_scale;
-    p.w_nstride = d->w_nstride; p.b_nstride = d->b_nstride; p.res_ld = d->res_ld; p.res_coff = d->res_coff;
+    p.w_nstride = d->w_nstride; p.b_nstride = d->b_nstride; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.in_act = d->in_act;
     p.accumulate = accumulate;
     return p;
 }
@@ -50,6 +51,7 @@ int fsv_conv_validate(const fsv_conv_desc* d, const char* who) {
                 "%s: Ho/Wo inconsistent with H,W,k,stride,pad", who);
     FSV_REQUIRE(d->x_ld >= d->x_coff + d->Cin && d->y_ld >= d->y_coff + d->Cout, "%s: ld/coff inconsistent", who);
     FSV_REQUIRE(d->out_scale != 0.f, "%s: out_scale must be non-zero", who);
+    FSV_REQUIRE(d->in_act == FSV_ACT_NONE || d->in_act == FSV_ACT_LRELU, "%s: in_act must be none or lrelu", who);
     return FSV_OK;
 }
 
@@ -128,6 +130,10 @@ __global__ void __launch_bounds__(256) k_conv_simt(ConvP p, const float* __restr
                         if (k + 2 < KC) v2 = ptr[2];
                         if (k + 3 < KC) v3 = ptr[3];
                     }
+                }
+                if (MODE == 0 && p.in_act == FSV_ACT_LRELU) {
+                    v0 = fsv_act(v0, FSV_ACT_LRELU); v1 = fsv_act(v1, FSV_ACT_LRELU);
+                    v2 = fsv_act(v2, FSV_ACT_LRELU); v3 = fsv_act(v3, FSV_ACT_LRELU);
                 }
                 As[akq + 0][ap] = v0; As[akq + 1][ap] = v1; As[akq + 2][ap] = v2; As[akq + 3][ap] = v3;
             }
@@ -283,6 +289,10 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(ConvP p, const float* __rest
                 if (b_vec) { float4 t = *reinterpret_cast<const float4*>(ptr); b0 = t.x; b1 = t.y; b2 = t.z; b3 = t.w; }
                 else { b0 = ptr[0]; if (ci + 1 < p.Cin) b1 = ptr[1]; if (ci + 2 < p.Cin) b2 = ptr[2]; if (ci + 3 < p.Cin) b3 = ptr[3]; }
             }
+        }
+        if (p.in_act == FSV_ACT_LRELU) {
+            b0 = fsv_act(b0, FSV_ACT_LRELU); b1 = fsv_act(b1, FSV_ACT_LRELU);
+            b2 = fsv_act(b2, FSV_ACT_LRELU); b3 = fsv_act(b3, FSV_ACT_LRELU);
         }
         *reinterpret_cast<float4*>(&As[kk][cq]) = make_float4(a0, a1, a2, a3);
         *reinterpret_cast<float4*>(&Bs[kk][cq]) = make_float4(b0, b1, b2, b3);

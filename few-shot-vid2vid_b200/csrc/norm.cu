@@ -76,7 +76,7 @@ extern "C" int fsv_norm_stats(const float* x, int N, int HW, int C, int ld, int 
 }
 
 __global__ void k_norm_finalize(const double* __restrict__ sum, const double* __restrict__ sumsq, int total, int C, double count,
-                                float eps, float momentum, float* running_mean, float* running_var, int update_running,
+                                double ucount, float eps, float momentum, float* running_mean, float* running_var, int update_running,
                                 float* __restrict__ mean, float* __restrict__ rstd) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -86,18 +86,18 @@ __global__ void k_norm_finalize(const double* __restrict__ sum, const double* __
     mean[i] = (float)m;
     rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
     if (update_running && i < C) {   // batch mode: one group
-        double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+        double unbiased = ucount > 1.0 ? var * (ucount / (ucount - 1.0)) : var;
         running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)m;
         running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
     }
 }
-extern "C" int fsv_norm_finalize(const double* sum, const double* sumsq, int groups, int C, double count, float eps,
-                                 float momentum, float* running_mean, float* running_var, int update_running,
+extern "C" int fsv_norm_finalize(const double* sum, const double* sumsq, int groups, int C, double count, double unbias_count,
+                                 float eps, float momentum, float* running_mean, float* running_var, int update_running,
                                  float* mean, float* rstd, void* stream) {
     FSV_REQUIRE(groups > 0 && C > 0 && count > 0, "norm_finalize: bad dims");
     FSV_REQUIRE(!update_running || (groups == 1 && running_mean && running_var), "norm_finalize: running update needs batch mode");
     int total = groups * C;
-    k_norm_finalize<<<fsv_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(sum, sumsq, total, C, count, eps, momentum,
+    k_norm_finalize<<<fsv_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(sum, sumsq, total, C, count, unbias_count, eps, momentum,
                                                                             running_mean, running_var, update_running, mean, rstd);
     FSV_CHECK_LAUNCH("norm_finalize");
     return FSV_OK;

@@ -1,0 +1,216 @@
+"""Parameter-holding layers of the B200 hot path.
+
+Every class keeps the attribute names (hence ``state_dict`` keys) of the reference module it
+stands in for, so reference checkpoints load unchanged; the forward bodies
+call the fsv C ABI through ``fsv.ops`` on NHWC activations.  Spectral normalisation stays the
+parameter-side ``torch.nn.utils.spectral_norm`` hook (buffers ``weight_orig/_u/_v``, one power
+iteration per training forward) exactly as the reference applies it.
+"""
+import torch
+import torch.nn as nn
+from torch.nn.utils import spectral_norm as _sn
+
+from .. import ops
+from ..ops import ACT_NONE, ACT_LRELU, NORM_BATCH, NORM_INSTANCE
+
+
+class Conv2d(nn.Module):
+    """nn.Conv2d stand-in (weight (Cout,Cin,kh,kw), optional bias) running fsv conv kernels."""
+
+    def __init__(self, cin, cout, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = cin, cout
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        self.weight = nn.Parameter(torch.empty(cout, cin, kernel_size, kernel_size))
+        self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+
+    def ohwi(self):
+        return self.weight.permute(0, 2, 3, 1).contiguous()
+
+    def forward(self, x, up=1, act=ACT_NONE, residual=None, out_scale=1.0, in_act=ACT_NONE):
+        return ops.conv2d(x, self.ohwi(), self.bias, stride=self.stride, pad=self.padding, up=up, act=act,
+                          out_scale=out_scale, residual=residual, in_act=in_act)
+
+
+class Linear(nn.Module):
+    """nn.Linear stand-in for the hyper-network MLPs (generator.py:103-110)."""
+
+    def __init__(self, fin, fout):
+        super().__init__()
+        self.in_features, self.out_features = fin, fout
+        self.weight = nn.Parameter(torch.empty(fout, fin))
+        self.bias = nn.Parameter(torch.zeros(fout))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+
+    def forward(self, x, act=ACT_NONE):
+        return ops.linear(x, self.weight, self.bias, act=act)
+
+
+def spectral(module):
+    return _sn(module)
+
+
+class BatchNorm(nn.Module):
+    """(Sync)BatchNorm2d stand-in: local batch statistics, eps 1e-5, momentum 0.1."""
+
+    def __init__(self, c, affine=True, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum, self.affine = c, eps, momentum, affine
+        if affine:
+            self.weight = nn.Parameter(torch.ones(c))
+            self.bias = nn.Parameter(torch.zeros(c))
+        else:
+            self.register_parameter('weight', None)
+            self.register_parameter('bias', None)
+        self.register_buffer('running_mean', torch.zeros(c))
+        self.register_buffer('running_var', torch.ones(c))
+        self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+
+    def tick(self):
+        if self.training:
+            self.num_batches_tracked += 1
+
+    def forward(self, x, act=ACT_NONE):
+        self.tick()
+        return ops.norm_act(x, self.weight, self.bias, self.running_mean, self.running_var, NORM_BATCH, self.training,
+                            self.eps, self.momentum, act)
+
+
+class InstanceNorm(nn.Module):
+    """nn.InstanceNorm2d(affine, eps=0.1) stand-in (normalization.py:35,82); no running statistics."""
+
+    def __init__(self, c, affine=True, eps=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.affine = c, eps, affine
+        if affine:
+            self.weight = nn.Parameter(torch.ones(c))
+            self.bias = nn.Parameter(torch.zeros(c))
+        else:
+            self.register_parameter('weight', None)
+            self.register_parameter('bias', None)
+
+    def forward(self, x, act=ACT_NONE):
+        return ops.norm_act(x, self.weight, self.bias, None, None, NORM_INSTANCE, self.training, self.eps, 0.1, act)
+
+
+class SPADE(nn.Module):
+    """normalization.py:18-52.  ``norm`` holds the BatchNorm buffers (or nothing for instance norm),
+    ``mlp_gamma{s}/mlp_beta{s}`` the fixed 1x1 weights (absent for map 0 when ``params_free``)."""
+
+    def __init__(self, norm_nc, hidden_nc, norm='batch', ks=1, params_free=False):
+        super().__init__()
+        if ks != 1:
+            raise NotImplementedError('SPADE with spade_ks != 1 is outside the hot-path scope (default spade_ks=1)')
+        if not isinstance(hidden_nc, list):
+            hidden_nc = [hidden_nc]
+        self.norm_nc, self.hidden_nc, self.params_free = norm_nc, list(hidden_nc), params_free
+        for i, nh in enumerate(hidden_nc):
+            if not params_free or i != 0:
+                s = str(i + 1) if i > 0 else ''
+                setattr(self, 'mlp_gamma%s' % s, Conv2d(nh, norm_nc, 1))
+                setattr(self, 'mlp_beta%s' % s, Conv2d(nh, norm_nc, 1))
+        self.batch = 'batch' in norm
+        self.norm = BatchNorm(norm_nc, affine=False) if self.batch else InstanceNorm(norm_nc, affine=False)
+
+    def forward(self, x, maps, weights=None, up=1, act=ACT_NONE):
+        """x: (N, H/up, W/up, C) NHWC; maps: list of NHWC label maps at (H, W) or None;
+        weights: None or (flat, wg_off, bg_off, wb_off, bb_off) locating the hyper-weights of map 0."""
+        if not isinstance(maps, (list, tuple)):
+            maps = [maps]
+        C = self.norm_nc
+        tensors, mcfg = [], []
+        for i, m in enumerate(maps):
+            if m is None:
+                continue
+            K = m.shape[3]
+            if weights is None or i != 0:
+                s = str(i + 1) if i > 0 else ''
+                g, b = getattr(self, 'mlp_gamma%s' % s), getattr(self, 'mlp_beta%s' % s)
+                tensors += [m, g.weight.reshape(C, K), g.bias, b.weight.reshape(C, K), b.bias]
+                mcfg.append(dict(K=K))
+            else:
+                flat, wg_off, bg_off, wb_off, bb_off = weights
+                tensors += [m, flat, flat, flat, flat]
+                mcfg.append(dict(K=K, wg_off=wg_off, bg_off=bg_off, wb_off=wb_off, bb_off=bb_off, nstride=flat.shape[1]))
+        if self.batch:
+            self.norm.tick()
+        cfg = dict(up=up, mode=NORM_BATCH if self.batch else NORM_INSTANCE, training=self.training,
+                   eps=self.norm.eps, momentum=0.1, act=act, maps=mcfg)
+        rm = self.norm.running_mean if self.batch else None
+        rv = self.norm.running_var if self.batch else None
+        return ops.SpadeFn.apply(x, rm, rv, cfg, *tensors)
+
+
+class ConvNormAct(nn.Module):
+    """architecture.py:57-69 SPADEConv2d with a plain norm: ``conv`` (spectral, bias) -> ``bn`` -> LeakyReLU."""
+
+    def __init__(self, fin, fout, stride=1):
+        super().__init__()
+        self.conv = spectral(Conv2d(fin, fout, 3, stride=stride, padding=1))
+        self.bn = BatchNorm(fout, affine=True)
+
+    def forward(self, x):
+        return self.bn(self.conv(x), act=ACT_LRELU)
+
+
+class SPADEResnetBlock(nn.Module):
+    """architecture.py:71-108.  With a 'spade' norm this is the generator main-branch block; with a plain
+    batch norm (flow network, generator.py:477-480) ``bn_*`` are BatchNorm layers."""
+
+    def __init__(self, fin, fout, norm='batch', hidden_nc=0, norm_params_free=False):
+        super().__init__()
+        fhidden = min(fin, fout)
+        self.learned_shortcut = fin != fout
+        self.spade = 'spade' in norm
+        self.conv_0 = spectral(Conv2d(fin, fhidden, 3, padding=1))
+        self.conv_1 = spectral(Conv2d(fhidden, fout, 3, padding=1))
+        if self.learned_shortcut:
+            self.conv_s = spectral(Conv2d(fin, fout, 1, bias=False))
+        if self.spade:
+            mk = lambda c: SPADE(c, hidden_nc, norm=norm, ks=1, params_free=norm_params_free)  # noqa: E731
+        else:
+            mk = lambda c: BatchNorm(c, affine=True)  # noqa: E731
+        self.bn_0 = mk(fin)
+        self.bn_1 = mk(fhidden)
+        if self.learned_shortcut:
+            self.bn_s = mk(fin)
+
+    def forward(self, x, maps=None, norm_weights=None, up=1):
+        """x: NHWC at 1/up of the block's resolution (the reference's nearest upsample, generator.py:207,
+        is folded into the SPADE loads)."""
+        if not self.spade:
+            dx = self.conv_0(self.bn_0(x, act=ACT_LRELU))
+            return self.conv_1(self.bn_1(dx, act=ACT_LRELU), residual=x)
+        nw = norm_weights if norm_weights is not None else [None] * 3
+        if self.learned_shortcut:
+            xs = self.conv_s(self.bn_s(x, maps, nw[2], up=up, act=ACT_NONE))
+        else:
+            xs = x if up == 1 else ops.upsample2x(x)
+        dx = self.conv_0(self.bn_0(x, maps, nw[0], up=up, act=ACT_LRELU))
+        return self.conv_1(self.bn_1(dx, maps, nw[1], up=1, act=ACT_LRELU), residual=xs)
+
+
+def init_weights(net, init_type='xavier', gain=0.02):
+    """base_network.py:86-115: xavier-normal (gain) on every conv / linear weight (reaching ``weight_orig``
+    under spectral norm), zero biases; norm-layer affine parameters are left at (1, 0) -- the reference's
+    'BatchNorm2d' name test does not match its SyncBatchNorm / InstanceNorm classes."""
+    for m in net.modules():
+        if isinstance(m, (Conv2d, Linear)):
+            w = m.weight_orig if hasattr(m, 'weight_orig') else m.weight
+            if init_type == 'normal':
+                nn.init.normal_(w.data, 0.0, gain)
+            elif init_type == 'xavier':
+                nn.init.xavier_normal_(w.data, gain=gain)
+            elif init_type == 'xavier_uniform':
+                nn.init.xavier_uniform_(w.data, gain=1.0)
+            elif init_type == 'kaiming':
+                nn.init.kaiming_normal_(w.data, a=0, mode='fan_in')
+            elif init_type == 'orthogonal':
+                nn.init.orthogonal_(w.data, gain=gain)
+            elif init_type == 'none':
+                pass
+            else:
+                raise NotImplementedError('initialization method [%s] is not implemented' % init_type)
+            if m.bias is not None:
+                nn.init.constant_(m.bias.data, 0.0)

@@ -1,0 +1,572 @@
+"""torch.autograd.Function wrappers over the fsv_b200 C ABI.
+
+Activations are fp32 NHWC tensors of shape (N, H, W, C), contiguous.  PyTorch is used for
+device memory, streams and autograd bookkeeping only; every forward/backward body is one
+or more calls into libfsv_b200.so on the current CUDA stream.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream, ConvDesc, SpadeDesc, PtrArray, c_vp
+
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID = _lib.ACT_NONE, _lib.ACT_LRELU, _lib.ACT_TANH, _lib.ACT_SIGMOID
+NORM_BATCH, NORM_INSTANCE = _lib.NORM_BATCH, _lib.NORM_INSTANCE
+
+# global switch for the conv path: -1 auto (tcgen05 when eligible), 0 force SIMT, 1 force tcgen05
+CONV_USE_TC = -1
+# launch counter (bench.py reports it as gpu_launches): number of C-ABI compute calls issued
+LAUNCHES = [0]
+
+
+def _c(t):
+    if t is None:
+        return None
+    _lib.require_cuda(t)
+    if t.dtype != torch.float32:
+        raise _lib.FsvError('fsv ops take float32 tensors, got %s' % t.dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _off(t, off_floats):
+    return c_vp(t.data_ptr() + 4 * int(off_floats))
+
+
+def _call(fn, *args):
+    LAUNCHES[0] += 1
+    check(fn(*args), fn.__name__)
+
+
+# --------------------------------------------------------------------------- layout
+
+class ToNHWC(torch.autograd.Function):
+    """NCHW (reference boundary layout) -> NHWC."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, c, h, w = x.shape
+        y = torch.empty((n, h, w, c), device=x.device, dtype=torch.float32)
+        _call(lib.fsv_nchw_to_nhwc, ptr(x), ptr(y), n, c, h, w, c, 0, stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        n, h, w, c = dy.shape
+        dx = torch.empty((n, c, h, w), device=dy.device, dtype=torch.float32)
+        _call(lib.fsv_nhwc_to_nchw, ptr(dy), ptr(dx), n, c, h, w, c, 0, 0, stream())
+        return dx
+
+
+class ToNCHW(torch.autograd.Function):
+    """NHWC -> contiguous NCHW (for callers that need contiguous reference-layout outputs)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+        _call(lib.fsv_nhwc_to_nchw, ptr(x), ptr(y), n, c, h, w, c, 0, 0, stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        n, c, h, w = dy.shape
+        dx = torch.empty((n, h, w, c), device=dy.device, dtype=torch.float32)
+        _call(lib.fsv_nchw_to_nhwc, ptr(dy), ptr(dx), n, c, h, w, c, 0, stream())
+        return dx
+
+
+class PackNHWC(torch.autograd.Function):
+    """Several NCHW tensors (same N,H,W) -> one channel-concatenated NHWC tensor, in one pass per input.
+    Fuses the reference's torch.cat(dim=1) at the network inputs (generator.py:499; loss_collector.py:47-58)
+    with the boundary layout change."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [_c(x) for x in xs]
+        n, _, h, w = xs[0].shape
+        cs = [x.shape[1] for x in xs]
+        ct = sum(cs)
+        y = torch.empty((n, h, w, ct), device=xs[0].device, dtype=torch.float32)
+        off = 0
+        for x, c in zip(xs, cs):
+            if tuple(x.shape) != (n, c, h, w):
+                raise _lib.FsvError('pack_nhwc: inconsistent input shapes')
+            _call(lib.fsv_nchw_to_nhwc, ptr(x), ptr(y), n, c, h, w, ct, off, stream())
+            off += c
+        ctx.cs = cs
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        n, h, w, ct = dy.shape
+        outs, off = [], 0
+        for i, c in enumerate(ctx.cs):
+            if ctx.needs_input_grad[i]:
+                dx = torch.empty((n, c, h, w), device=dy.device, dtype=torch.float32)
+                _call(lib.fsv_nhwc_to_nchw, ptr(dy), ptr(dx), n, c, h, w, ct, off, 0, stream())
+                outs.append(dx)
+            else:
+                outs.append(None)
+            off += c
+        return tuple(outs)
+
+
+def pack_nhwc(*xs):
+    return PackNHWC.apply(*xs)
+
+
+def to_nhwc(x):
+    return ToNHWC.apply(x)
+
+
+def to_nchw(x):
+    return ToNCHW.apply(x)
+
+
+def nchw_view(x_nhwc):
+    """Zero-copy NCHW-shaped (channels_last strided) view of an NHWC tensor."""
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+class CatC(torch.autograd.Function):
+    """Channel concat of NHWC tensors (torch.cat(dim=1) of the reference: generator.py:499,562-563)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [_c(x) for x in xs]
+        n, h, w = xs[0].shape[:3]
+        cs = [x.shape[3] for x in xs]
+        ctx.cs = cs
+        y = torch.empty((n, h, w, sum(cs)), device=xs[0].device, dtype=torch.float32)
+        off = 0
+        for x, c in zip(xs, cs):
+            _call(lib.fsv_copy_channels, ptr(x), c, 0, ptr(y), sum(cs), off, n * h * w, c, 0, stream())
+            off += c
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        n, h, w, ct = dy.shape
+        outs, off = [], 0
+        for i, c in enumerate(ctx.cs):
+            if ctx.needs_input_grad[i]:
+                dx = torch.empty((n, h, w, c), device=dy.device, dtype=torch.float32)
+                _call(lib.fsv_copy_channels, ptr(dy), ct, off, ptr(dx), c, 0, n * h * w, c, 0, stream())
+                outs.append(dx)
+            else:
+                outs.append(None)
+            off += c
+        return tuple(outs)
+
+
+def cat_channels(*xs):
+    return CatC.apply(*xs)
+
+
+class Up2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.float32)
+        _call(lib.fsv_upsample2x_fwd, ptr(x), ptr(y), n, h, w, c, stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        n, h2, w2, c = dy.shape
+        dx = torch.empty((n, h2 // 2, w2 // 2, c), device=dy.device, dtype=torch.float32)
+        _call(lib.fsv_upsample2x_bwd, ptr(dy), ptr(dx), n, h2 // 2, w2 // 2, c, stream())
+        return dx
+
+
+def upsample2x(x):
+    return Up2.apply(x)
+
+
+class AvgPool3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, h, w, c = x.shape
+        ctx.shape = (n, h, w, c)
+        y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), device=x.device, dtype=torch.float32)
+        _call(lib.fsv_avgpool3s2_fwd, ptr(x), ptr(y), n, h, w, c, stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        n, h, w, c = ctx.shape
+        dx = torch.empty((n, h, w, c), device=dy.device, dtype=torch.float32)
+        _call(lib.fsv_avgpool3s2_bwd, ptr(dy), ptr(dx), n, h, w, c, stream())
+        return dx
+
+
+def avgpool3s2(x):
+    return AvgPool3s2.apply(x)
+
+
+# --------------------------------------------------------------------------- convolution
+
+def _conv_desc(n, h, w, cin, cout, kh, kw, stride, pad, up=1, act=ACT_NONE, out_scale=1.0, w_nstride=0, b_nstride=0,
+               use_tc=None, in_act=ACT_NONE):
+    d = ConvDesc()
+    d.N, d.H, d.W, d.Cin, d.x_ld, d.x_coff, d.up = n, h, w, cin, cin, 0, up
+    d.Cout, d.kh, d.kw, d.stride, d.pad = cout, kh, kw, stride, pad
+    d.Ho = (h + 2 * pad - kh) // stride + 1
+    d.Wo = (w + 2 * pad - kw) // stride + 1
+    d.y_ld, d.y_coff, d.act, d.out_scale = cout, 0, act, out_scale
+    d.w_nstride, d.b_nstride, d.res_ld, d.res_coff = w_nstride, b_nstride, cout, 0
+    d.in_act = in_act
+    d.use_tc = CONV_USE_TC if use_tc is None else use_tc
+    return d
+
+
+class Conv2dFn(torch.autograd.Function):
+    """y = act(conv(x, w) + b + residual) * out_scale on NHWC.
+
+    ``wbase`` holds OHWI weights starting ``w_off`` floats in; with ``w_nstride`` != 0 sample n
+    uses wbase.flat[w_off + n*w_nstride : ...] (the hyper-network's flat output, zero-copy).
+    Same for ``bbase`` / ``b_off`` / ``b_nstride``.  cfg: dict(cout, kh, kw, stride, pad, up,
+    act, out_scale, w_off, b_off, w_nstride, b_nstride).
+    """
+
+    @staticmethod
+    def forward(ctx, x, wbase, bbase, residual, cfg):
+        x, wbase, bbase, residual = _c(x), _c(wbase), _c(bbase), _c(residual)
+        n, hs, ws, cin = x.shape
+        up = cfg.get('up', 1)
+        d = _conv_desc(n, hs * up, ws * up, cin, cfg['cout'], cfg['kh'], cfg['kw'], cfg.get('stride', 1), cfg.get('pad', 0),
+                       up, cfg.get('act', ACT_NONE), cfg.get('out_scale', 1.0), cfg.get('w_nstride', 0), cfg.get('b_nstride', 0),
+                       cfg.get('use_tc'), cfg.get('in_act', ACT_NONE))
+        y = torch.empty((n, d.Ho, d.Wo, d.Cout), device=x.device, dtype=torch.float32)
+        _call(lib.fsv_conv2d_fwd, ctypes.byref(d), ptr(x), _off(wbase, cfg.get('w_off', 0)),
+              None if bbase is None else _off(bbase, cfg.get('b_off', 0)), ptr(residual), ptr(y), stream())
+        ctx.cfg, ctx.d = cfg, d
+        ctx.has_b, ctx.has_r = bbase is not None, residual is not None
+        ctx.same_base = bbase is not None and bbase.data_ptr() == wbase.data_ptr() and bbase.numel() == wbase.numel()
+        need_y = d.act != ACT_NONE
+        ctx.save_for_backward(x, wbase, y if need_y else None)
+        ctx.bshape = None if bbase is None else tuple(bbase.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wbase, y = ctx.saved_tensors
+        cfg, d = ctx.cfg, ctx.d
+        dy = _c(dy)
+        st = stream()
+        if d.act != ACT_NONE or d.out_scale != 1.0:
+            g = torch.empty_like(dy)
+            _call(lib.fsv_act_bwd, ptr(y if y is not None else dy), ptr(dy), ptr(g), dy.numel(), d.act, d.out_scale, st)
+        else:
+            g = dy
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dd = ConvDesc.from_buffer_copy(d)
+            dd.up = 1
+            dfull = torch.empty((d.N, d.H, d.W, d.Cin), device=dy.device, dtype=torch.float32)
+            _call(lib.fsv_conv2d_dgrad, ctypes.byref(dd), ptr(g), _off(wbase, cfg.get('w_off', 0)), ptr(dfull), 0, st)
+            if d.up == 2:
+                dx = torch.empty_like(x)
+                _call(lib.fsv_upsample2x_bwd, ptr(dfull), ptr(dx), d.N, d.H // 2, d.W // 2, d.Cin, st)
+            else:
+                dx = dfull
+            if d.in_act != ACT_NONE:   # lrelu on load: sign(lrelu(x)) == sign(x), so x serves as the 'post-activation' value
+                _call(lib.fsv_act_bwd, ptr(x), ptr(dx), ptr(dx), dx.numel(), d.in_act, 1.0, st)
+        need_w = ctx.needs_input_grad[1]
+        need_b = ctx.has_b and ctx.needs_input_grad[2]
+        if need_w or need_b:
+            shared = d.w_nstride == 0 and cfg.get('w_off', 0) == 0
+            dw = torch.empty_like(wbase) if shared else torch.zeros_like(wbase)
+            if need_b:
+                db = dw if ctx.same_base else torch.zeros(ctx.bshape, device=dy.device, dtype=torch.float32)
+            _call(lib.fsv_conv2d_wgrad, ctypes.byref(d), ptr(x), ptr(g), _off(dw, cfg.get('w_off', 0)) if need_w else None,
+                  _off(db, cfg.get('b_off', 0)) if need_b else None, 0 if shared else 1, st)
+            if ctx.same_base:
+                db = None          # the single flat gradient is returned through wbase
+            if not need_w:
+                dw = None
+        if ctx.has_r and ctx.needs_input_grad[3]:
+            dres = g
+        return dx, dw, db, dres, None
+
+
+def conv2d(x, w_ohwi, bias=None, stride=1, pad=0, up=1, act=ACT_NONE, out_scale=1.0, residual=None, use_tc=None,
+           in_act=ACT_NONE):
+    cout, kh, kw, _ = w_ohwi.shape
+    cfg = dict(cout=cout, kh=kh, kw=kw, stride=stride, pad=pad, up=up, act=act, out_scale=out_scale, use_tc=use_tc,
+               in_act=in_act)
+    return Conv2dFn.apply(x, w_ohwi, bias, residual, cfg)
+
+
+def batch_conv1x1(x, flat, cout, cin, w_off, b_off, act=ACT_NONE):
+    """Per-sample 1x1 conv with weights living inside ``flat`` (B, L): base_network.py:56-71."""
+    L = flat.shape[1]
+    cfg = dict(cout=cout, kh=1, kw=1, stride=1, pad=0, up=1, act=act, w_off=w_off, b_off=b_off, w_nstride=L, b_nstride=L, use_tc=0)
+    assert x.shape[3] == cin
+    return Conv2dFn.apply(x, flat, flat, None, cfg)
+
+
+def linear(x2d, w, bias, act=ACT_NONE):
+    """F.linear on (rows, K) with w (out, K): a 1x1 conv over a rows x 1 'image'."""
+    rows, k = x2d.shape
+    y = conv2d(x2d.reshape(1, rows, 1, k), w.reshape(w.shape[0], 1, 1, k), bias, act=act)
+    return y.reshape(rows, w.shape[0])
+
+
+# --------------------------------------------------------------------------- normalisation (+ activation)
+
+def _stats(x, n, hw, c, mode, training, running_mean, running_var, eps, momentum, unbias_mul=1):
+    dev = x.device
+    groups = n if mode == NORM_INSTANCE else 1
+    mean = torch.empty(groups * c, device=dev, dtype=torch.float32)
+    rstd = torch.empty(groups * c, device=dev, dtype=torch.float32)
+    st = stream()
+    if training or mode == NORM_INSTANCE:
+        sums = torch.empty(2 * groups * c, device=dev, dtype=torch.float64)
+        _call(lib.fsv_norm_stats, ptr(x), n, hw, c, c, 0, mode, ptr(sums), _off(sums, 2 * groups * c), st)
+        count = float(hw if mode == NORM_INSTANCE else n * hw)
+        upd = 1 if (mode == NORM_BATCH and running_mean is not None) else 0
+        _call(lib.fsv_norm_finalize, ptr(sums), _off(sums, 2 * groups * c), groups, c, count, count * unbias_mul, eps, momentum,
+              ptr(running_mean) if upd else None, ptr(running_var) if upd else None, upd, ptr(mean), ptr(rstd), st)
+    else:
+        _call(lib.fsv_norm_from_running, ptr(running_mean), ptr(running_var), c, eps, ptr(mean), ptr(rstd), st)
+    return mean, rstd
+
+
+class NormActFn(torch.autograd.Function):
+    """y = act(norm(x) * weight + bias): BatchNorm (local statistics) or InstanceNorm, + activation."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, cfg):
+        x, weight, bias = _c(x), _c(weight), _c(bias)
+        n, h, w, c = x.shape
+        mode, training = cfg['mode'], cfg['training']
+        mean, rstd = _stats(x, n, h * w, c, mode, training, running_mean, running_var, cfg['eps'], cfg.get('momentum', 0.1))
+        y = torch.empty_like(x)
+        _call(lib.fsv_norm_apply_fwd, ptr(x), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), ptr(y), n, h * w, c, mode,
+              cfg.get('act', ACT_NONE), stream())
+        ctx.cfg = cfg
+        ctx.save_for_backward(x, y, mean, rstd, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd, weight = ctx.saved_tensors
+        cfg = ctx.cfg
+        dy = _c(dy)
+        n, h, w, c = x.shape
+        mode = cfg['mode']
+        groups = n if mode == NORM_INSTANCE else 1
+        batch_stats = 1 if (cfg['training'] or mode == NORM_INSTANCE) else 0
+        dx = torch.empty_like(x)
+        dwt = torch.empty(c, device=x.device, dtype=torch.float32) if weight is not None else None
+        dbs = torch.empty(c, device=x.device, dtype=torch.float32) if weight is not None else None
+        scratch = torch.empty(2 * groups * c, device=x.device, dtype=torch.float64)
+        _call(lib.fsv_norm_apply_bwd, ptr(x), ptr(y), ptr(dy), ptr(mean), ptr(rstd), ptr(weight), ptr(dx), ptr(dwt), ptr(dbs),
+              ptr(scratch), n, h * w, c, mode, cfg.get('act', ACT_NONE), batch_stats, stream())
+        return dx, dwt, dbs, None, None, None
+
+
+def norm_act(x, weight, bias, running_mean, running_var, mode, training, eps, momentum=0.1, act=ACT_NONE):
+    cfg = dict(mode=mode, training=training, eps=eps, momentum=momentum, act=act)
+    return NormActFn.apply(x, weight, bias, running_mean, running_var, cfg)
+
+
+# --------------------------------------------------------------------------- fused SPADE
+
+class SpadeFn(torch.autograd.Function):
+    """Fused SPADE: normalise (+ upsample-on-load) -> per-map 1x1 gamma/beta -> modulate -> activation.
+
+    forward(ctx, x, running_mean, running_var, cfg, *tensors) with, per map i,
+    tensors[5i:5i+5] = (map_i, wg_base, bg_base, wb_base, bb_base) and
+    cfg['maps'][i] = dict(K, wg_off, bg_off, wb_off, bb_off, nstride).
+    cfg: dict(up, mode, training, eps, momentum, act, maps=[...]).
+    """
+
+    @staticmethod
+    def forward(ctx, x, running_mean, running_var, cfg, *tensors):
+        x = _c(x)
+        tensors = [_c(t) for t in tensors]
+        n, hs, ws, c = x.shape
+        up, mode = cfg['up'], cfg['mode']
+        h, w = hs * up, ws * up
+        mean, rstd = _stats(x, n, hs * ws, c, mode, cfg['training'], running_mean, running_var, cfg['eps'],
+                            cfg.get('momentum', 0.1), unbias_mul=up * up)
+        d, arrays = SpadeFn._desc(cfg, n, h, w, c, tensors)
+        out = torch.empty((n, h, w, c), device=x.device, dtype=torch.float32)
+        _call(lib.fsv_spade_fwd, ctypes.byref(d), ptr(x), ptr(mean), ptr(rstd), *arrays, ptr(out), stream())
+        ctx.cfg = cfg
+        ctx.dims = (n, h, w, c)
+        ctx.save_for_backward(x, mean, rstd, *tensors)
+        return out
+
+    @staticmethod
+    def _desc(cfg, n, h, w, c, tensors):
+        d = SpadeDesc()
+        d.N, d.H, d.W, d.C, d.up, d.mode, d.act = n, h, w, c, cfg['up'], cfg['mode'], cfg.get('act', ACT_NONE)
+        nm = len(cfg['maps'])
+        d.nmaps = nm
+        maps, wg, bg, wb, bb = PtrArray(), PtrArray(), PtrArray(), PtrArray(), PtrArray()
+        for i, mc in enumerate(cfg['maps']):
+            m, g0, g1, b0, b1 = tensors[5 * i:5 * i + 5]
+            if tuple(m.shape[:3]) != (n, h, w):
+                raise _lib.FsvError('SPADE label map %d has spatial size %s, expected %s (non-identity nearest resize is not '
+                                    'supported)' % (i, tuple(m.shape[1:3]), (h, w)))
+            d.K[i], d.m_ld[i], d.m_coff[i], d.w_nstride[i] = mc['K'], m.shape[3], 0, mc.get('nstride', 0)
+            maps[i] = m.data_ptr()
+            wg[i] = g0.data_ptr() + 4 * mc.get('wg_off', 0)
+            bg[i] = g1.data_ptr() + 4 * mc.get('bg_off', 0)
+            wb[i] = b0.data_ptr() + 4 * mc.get('wb_off', 0)
+            bb[i] = b1.data_ptr() + 4 * mc.get('bb_off', 0)
+        return d, (maps, wg, bg, wb, bb)
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved = ctx.saved_tensors
+        x, mean, rstd = saved[:3]
+        tensors = list(saved[3:])
+        cfg = ctx.cfg
+        n, h, w, c = ctx.dims
+        dout = _c(dout)
+        dev = dout.device
+        st = stream()
+        nm = len(cfg['maps'])
+        d, arrays = SpadeFn._desc(cfg, n, h, w, c, tensors)
+        dxhat = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+        dgs = [torch.empty((n, h, w, c), device=dev, dtype=torch.float32) for _ in range(nm)]
+        dbs = [torch.empty((n, h, w, c), device=dev, dtype=torch.float32) for _ in range(nm)]
+        pg, pb = PtrArray(), PtrArray()
+        for i in range(nm):
+            pg[i], pb[i] = dgs[i].data_ptr(), dbs[i].data_ptr()
+        _call(lib.fsv_spade_bwd, ctypes.byref(d), ptr(x), ptr(mean), ptr(rstd), *arrays, ptr(dout), ptr(dxhat), pg, pb, st)
+        mode = cfg['mode']
+        groups = n if mode == NORM_INSTANCE else 1
+        batch_stats = 1 if (cfg['training'] or mode == NORM_INSTANCE) else 0
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            scratch = torch.empty(2 * groups * c, device=dev, dtype=torch.float64)
+            _call(lib.fsv_spade_norm_bwd, ptr(x), ptr(dxhat), ptr(mean), ptr(rstd), ptr(dx), ptr(scratch), n, h, w, c,
+                  cfg['up'], mode, batch_stats, st)
+        grads = [None] * len(tensors)
+        gbuf = {}   # data_ptr -> gradient buffer, so that views of one flat hyper-output share one gradient
+
+        def buf_for(idx):
+            t = tensors[idx]
+            key = (t.data_ptr(), t.numel())
+            if key not in gbuf:
+                gbuf[key] = torch.zeros_like(t)
+                grads[idx] = gbuf[key]
+            return gbuf[key]
+
+        for i, mc in enumerate(cfg['maps']):
+            m = tensors[5 * i]
+            K = mc['K']
+            ns = mc.get('nstride', 0)
+            cd = _conv_desc(n, h, w, K, c, 1, 1, 1, 0, 1, ACT_NONE, 1.0, ns, ns, 0)
+            cd.x_ld = m.shape[3]
+            need_m = ctx.needs_input_grad[4 + 5 * i]
+            if need_m:
+                dm = torch.empty_like(m) if m.shape[3] == K else torch.zeros_like(m)
+                _call(lib.fsv_conv2d_dgrad, ctypes.byref(cd), ptr(dgs[i]), _off(tensors[5 * i + 1], mc.get('wg_off', 0)), ptr(dm), 0, st)
+                _call(lib.fsv_conv2d_dgrad, ctypes.byref(cd), ptr(dbs[i]), _off(tensors[5 * i + 3], mc.get('wb_off', 0)), ptr(dm), 1, st)
+                grads[5 * i] = dm
+            if ctx.needs_input_grad[4 + 5 * i + 1]:
+                gw, gb = buf_for(5 * i + 1), buf_for(5 * i + 2)
+                _call(lib.fsv_conv2d_wgrad, ctypes.byref(cd), ptr(m), ptr(dgs[i]), _off(gw, mc.get('wg_off', 0)),
+                      _off(gb, mc.get('bg_off', 0)), 1, st)
+            if ctx.needs_input_grad[4 + 5 * i + 3]:
+                gw, gb = buf_for(5 * i + 3), buf_for(5 * i + 4)
+                _call(lib.fsv_conv2d_wgrad, ctypes.byref(cd), ptr(m), ptr(dbs[i]), _off(gw, mc.get('wb_off', 0)),
+                      _off(gb, mc.get('bb_off', 0)), 1, st)
+        return (dx, None, None, None) + tuple(grads)
+
+
+# --------------------------------------------------------------------------- warp + composite
+
+class WarpFn(torch.autograd.Function):
+    """blend=False: out = [bilinear_warp(img, flow), mask] (N,H,W,Ci+1);  blend=True: raw*mask + warp*(1-mask)."""
+
+    @staticmethod
+    def forward(ctx, img, flow, mask, raw, blend):
+        img, flow, mask, raw = _c(img), _c(flow), _c(mask), _c(raw)
+        n, h, w, ci = img.shape
+        co = ci if (blend or mask is None) else ci + 1
+        out = torch.empty((n, h, w, co), device=img.device, dtype=torch.float32)
+        _call(lib.fsv_warp_fwd, ptr(img), ptr(flow), ptr(mask), ptr(raw), ptr(out), n, h, w, ci, co, 0, 1 if blend else 0, stream())
+        ctx.blend, ctx.co = blend, co
+        ctx.save_for_backward(img, flow, mask, raw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, flow, mask, raw = ctx.saved_tensors
+        dout = _c(dout)
+        n, h, w, ci = img.shape
+        dflow = torch.empty_like(flow)
+        dmask = torch.empty_like(mask) if (mask is not None and ctx.needs_input_grad[2]) else None
+        draw = torch.empty_like(raw) if (raw is not None and ctx.needs_input_grad[3]) else None
+        dimg = torch.zeros_like(img) if ctx.needs_input_grad[0] else None
+        _call(lib.fsv_warp_bwd, ptr(img), ptr(flow), ptr(mask), ptr(raw), ptr(dout), ptr(dflow), ptr(dmask), ptr(draw), ptr(dimg),
+              n, h, w, ci, ctx.co, 0, 1 if ctx.blend else 0, stream())
+        return dimg, dflow, dmask, draw, None
+
+
+def warp_concat(img, flow, mask):
+    return WarpFn.apply(img, flow, mask, None, False)
+
+
+def warp_blend(img, flow, mask, raw):
+    return WarpFn.apply(img, flow, mask, raw, True)
+
+
+# --------------------------------------------------------------------------- reference-feature outer product
+
+class SoftmaxOuterFn(torch.autograd.Function):
+    """out[b,c1,c2] = sum_hw img[b,hw,c1] * softmax_c(lab)[b,hw,c2]   (generator.py:381-388)."""
+
+    @staticmethod
+    def forward(ctx, img, lab):
+        img, lab = _c(img), _c(lab)
+        b, h, w, c = img.shape
+        soft = torch.empty_like(lab)
+        st = stream()
+        _call(lib.fsv_softmax_rows_fwd, ptr(lab), ptr(soft), b * h * w, c, st)
+        out = torch.empty((b, c, c), device=img.device, dtype=torch.float32)
+        d = _conv_desc(b, h, w, c, c, 1, 1, 1, 0, 1, ACT_NONE, 1.0, c * c, 0, 0)
+        _call(lib.fsv_conv2d_wgrad, ctypes.byref(d), ptr(soft), ptr(img), ptr(out), None, 0, st)
+        ctx.save_for_backward(img, soft)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, soft = ctx.saved_tensors
+        dout = _c(dout)
+        b, h, w, c = img.shape
+        st = stream()
+        d = _conv_desc(b, h, w, c, c, 1, 1, 1, 0, 1, ACT_NONE, 1.0, c * c, 0, 0)
+        dimg = dlab = None
+        if ctx.needs_input_grad[0]:
+            dimg = torch.empty_like(img)
+            _call(lib.fsv_conv2d_fwd, ctypes.byref(d), ptr(soft), ptr(dout), None, None, ptr(dimg), st)
+        if ctx.needs_input_grad[1]:
+            dsoft = torch.empty_like(soft)
+            _call(lib.fsv_conv2d_dgrad, ctypes.byref(d), ptr(img), ptr(dout), ptr(dsoft), 0, st)
+            dlab = torch.empty_like(soft)
+            _call(lib.fsv_softmax_rows_bwd, ptr(soft), ptr(dsoft), ptr(dlab), b * h * w, c, st)
+        return dimg, dlab
+
+
+def softmax_outer(img_feat, lab_feat):
+    return SoftmaxOuterFn.apply(img_feat, lab_feat)

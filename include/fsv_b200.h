@@ -85,6 +85,7 @@ typedef struct fsv_conv_desc {
     long long w_nstride;   /* 0 = shared weight; else floats between per-sample weights */
     long long b_nstride;   /* same for the bias */
     int res_ld, res_coff;  /* residual buffer (added before act), used when residual != NULL */
+    int in_act;            /* FSV_ACT_NONE or FSV_ACT_LRELU applied to x on load (generator.py:210 conv_img(actvn(x))) */
     int use_tc;            /* 0 = SIMT path, 1 = tcgen05/TMA path (FSV_ENOTSUP if the shape is not eligible), -1 = auto */
 } fsv_conv_desc;
 
@@ -105,9 +106,11 @@ int fsv_conv2d_tc_eligible(const fsv_conv_desc* d);
  * Outputs are DOUBLE [groups*C] (zeroed by the call). */
 int fsv_norm_stats(const float* x, int N, int HW, int C, int ld, int coff, int mode, double* sum, double* sumsq, void* stream);
 /* mean/rstd from the sums; for mode batch + training also the running-stat update of
- * F.batch_norm (momentum, unbiased variance; count = elements per channel as seen by the reference). */
-int fsv_norm_finalize(const double* sum, const double* sumsq, int groups, int C, double count, float eps,
-                      float momentum, float* running_mean, float* running_var, int update_running,
+ * F.batch_norm (momentum, unbiased variance).  count = elements per channel that were summed;
+ * unbias_count = elements per channel as seen by the reference (4x count when the reference
+ * normalises a nearest-x2-upsampled copy of the tensor the sums were taken over). */
+int fsv_norm_finalize(const double* sum, const double* sumsq, int groups, int C, double count, double unbias_count,
+                      float eps, float momentum, float* running_mean, float* running_var, int update_running,
                       float* mean, float* rstd, void* stream);
 /* eval-mode stats from running buffers: mean = running_mean, rstd = 1/sqrt(running_var+eps) */
 int fsv_norm_from_running(const float* running_mean, const float* running_var, int C, float eps,
