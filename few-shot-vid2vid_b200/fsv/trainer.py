@@ -1,0 +1,118 @@
+"""One training iteration of the hot path: the mirror of the reference's inner loop
+(train.py:55-62 -> vid2vid_model.py:62-128 -> loss_collector.py:47-228) for the single-frame
+phase with ``--no_flow_gt --no_vgg_loss`` on datasets without a foreground mask (face / street):
+
+    D-step: G forward under no_grad -> D on [fake ; real] -> hinge real/fake -> backward -> Adam
+    G-step: G forward -> D on [fake ; real] -> GAN + feature matching + warp L1 + mask losses -> backward -> Adam
+
+The loss arithmetic is the reference's own torch code path (it sits ABOVE the define_G/define_D
+boundary and is kept); the networks are the fsv drop-in modules.
+"""
+import torch
+
+from . import ops
+
+
+def _d_input(tgt_label, fake, real, ref_label, ref_image):
+    """loss_collector.py:47-58,104-110 with concat_ref_for_D: batch [fake ; real], channels
+    [ref_label, ref_image, tgt_label, image]."""
+    tgt = torch.cat([fake, real], dim=0)
+    tgt = torch.cat([tgt_label.repeat(2, 1, 1, 1), tgt], dim=1)
+    ref = torch.cat([ref_label, ref_image], dim=1).repeat(2, 1, 1, 1)
+    return torch.cat([ref, tgt], dim=1)
+
+
+def _split(pred):
+    """base_model.py:141-147 divide_pred."""
+    fake = [[t[:t.size(0) // 2] for t in p] for p in pred]
+    real = [[t[t.size(0) // 2:] for t in p] for p in pred]
+    return fake, real
+
+
+def _hinge(pred, target_is_real):
+    """loss.py:69-78 (for_discriminator=True branch -- also what the reference uses for the generator's GAN
+    term, because loss_collector.py:66 omits for_discriminator=False)."""
+    z = pred * 0
+    return -torch.mean(torch.min(pred - 1, z)) if target_is_real else -torch.mean(torch.min(-pred - 1, z))
+
+
+def _gan_loss(preds, target_is_real):
+    """loss.py:92-104."""
+    loss = 0
+    for p in preds:
+        loss = loss + _hinge(p[-1], target_is_real).view(1)
+    return loss / len(preds)
+
+
+def _feat_match(pred_real, pred_fake, lambda_feat):
+    """loss_collector.py:206-215."""
+    num_d = len(pred_fake)
+    loss = 0
+    for i in range(num_d):
+        for j in range(len(pred_fake[i]) - 1):
+            loss = loss + torch.nn.functional.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) / num_d
+    return loss * lambda_feat
+
+
+def _masked_l1(a, b, m):
+    m = m.expand_as(a)
+    return torch.nn.functional.l1_loss(a * m, b * m)
+
+
+def _mask_loss(flow_mask, warped, tgt, lambda_mask):
+    """loss_collector.py:191-204."""
+    conf = torch.clamp(1 - torch.sum(abs(warped - tgt), dim=1, keepdim=True), 0, 1)
+    zero, one = torch.zeros_like(flow_mask), torch.ones_like(flow_mask)
+    return (_masked_l1(flow_mask, zero, conf) + _masked_l1(flow_mask, one, 1 - conf)) * lambda_mask
+
+
+def discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images):
+    """vid2vid_model.py:106-128."""
+    with torch.no_grad():
+        fake = netG(tgt_label, ref_labels, ref_images)[0]
+    pred = netD(_d_input(tgt_label, fake.detach(), tgt_image, ref_labels[:, 0], ref_images[:, 0]))
+    pf, pr = _split(pred)
+    return {'D_real': _gan_loss(pr, True), 'D_fake': _gan_loss(pf, False)}
+
+
+def generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images):
+    """vid2vid_model.py:62-104 (non-zero terms under --no_flow_gt --no_vgg_loss, no foreground mask)."""
+    out = netG(tgt_label, ref_labels, ref_images)
+    fake, flow, fmask, warp = out[0], out[1], out[2], out[4]
+    pred = netD(_d_input(tgt_label, fake, tgt_image, ref_labels[:, 0], ref_images[:, 0]))
+    pf, pr = _split(pred)
+    losses = {'G_GAN': _gan_loss(pf, True), 'G_GAN_Feat': _feat_match(pr, pf, opt.lambda_feat)}
+    if flow[0] is not None:
+        losses['F_Warp'] = torch.nn.functional.l1_loss(warp[0], tgt_image) * opt.lambda_flow
+        losses['F_Mask'] = _mask_loss(fmask[0], warp[0], tgt_image, opt.lambda_mask)
+    return losses, fake
+
+
+def make_optimizers(opt, netG, netD):
+    """base_model.py:39-48 Adam with TTUR."""
+    if opt.no_TTUR:
+        beta1, beta2, g_lr, d_lr = opt.beta1, 0.999, opt.lr, opt.lr
+    else:
+        beta1, beta2, g_lr, d_lr = 0, opt.beta2, opt.lr / 2, opt.lr * 2
+    return (torch.optim.Adam(netG.parameters(), lr=g_lr, betas=(beta1, beta2)),
+            torch.optim.Adam(netD.parameters(), lr=d_lr, betas=(beta1, beta2)))
+
+
+def loss_backward(losses, optimizer, grad_sync=None):
+    """loss_collector.py:217-228: mean -> sum -> zero_grad -> backward -> [allreduce] -> step."""
+    loss = sum(torch.mean(v) for v in losses.values())
+    optimizer.zero_grad()
+    loss.backward()
+    if grad_sync is not None:
+        grad_sync()
+    optimizer.step()
+    return loss
+
+
+def train_step(opt, netG, netD, optG, optD, tgt_label, tgt_image, ref_labels, ref_images, sync_G=None, sync_D=None):
+    """train.py:58-62: discriminator update, then generator update, for one frame."""
+    d_losses = discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images)
+    ld = loss_backward(d_losses, optD, sync_D)
+    g_losses, fake = generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images)
+    lg = loss_backward(g_losses, optG, sync_G)
+    return ld, lg, fake

@@ -1,0 +1,89 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/fsv_b200.h declares; the drop-in modules expose exactly the reference's state_dict; the
+product refuses to run without CUDA (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from util import load_npz, state_from, opt_from
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, 'include', 'fsv_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(fsv_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from fsv import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), 'libfsv_b200.so does not export %s' % n
+    # and the ctypes table binds each of them (except the error string getter bound separately)
+    for n in names:
+        assert n in _lib.SIGNATURES or n == 'fsv_last_error', n
+    assert lib.fsv_version() >= 100
+
+
+def test_state_dict_names_match_reference():
+    from fsv import networks
+    z = load_npz('g_face_tiny.npz')
+    opt = opt_from(z)
+    G = networks.define_G(opt)
+    ref = state_from(z, 'sd.')
+    mine = G.state_dict()
+    assert list(mine.keys()) == list(ref.keys())
+    assert all(tuple(mine[k].shape) == tuple(ref[k].shape) for k in ref)
+    G.load_state_dict(ref)
+    G.init_temporal_network()
+    zt = load_npz('g_face_tiny_temporal.npz')
+    assert set(G.state_dict().keys()) == set(state_from(zt, 'sd.').keys())
+    zd = load_npz('d_tiny.npz')
+    D = networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, 2, True, gpu_ids=[])
+    assert list(D.state_dict().keys()) == list(state_from(zd, 'sd.').keys())
+    # finetune's name filter (vid2vid_model.py:208-209) still finds its parameter groups
+    keys = list(mine.keys())
+    assert any('fc' in k for k in keys) and any('conv_img' in k for k in keys) and any(k.startswith('up_') for k in keys)
+
+
+def test_init_matches_reference_statistics():
+    from fsv import networks
+    z = load_npz('g_face_tiny.npz')
+    opt = opt_from(z)
+    torch.manual_seed(0)
+    G = networks.define_G(opt)
+    ref = state_from(z, 'sd.')
+    mine = G.state_dict()
+    for k in ('up_2.conv_0.weight_orig', 'fc_spade_0_1.0.weight_orig', 'label_embedding.down_1.0.weight'):
+        assert abs(mine[k].std().item() / ref[k].std().item() - 1) < 0.25, k
+    for k in mine:
+        if k.endswith('.bias'):
+            assert float(mine[k].abs().max()) == 0.0, k
+        if k.endswith('bn.weight'):
+            assert float((mine[k] - 1).abs().max()) == 0.0, k
+
+
+def test_product_has_no_cpu_fallback():
+    from fsv import networks
+    z = load_npz('g_face_tiny.npz')
+    opt = opt_from(z)
+    G = networks.define_G(opt)
+    with pytest.raises(Exception) as e:
+        G(torch.zeros(1, 1, 64, 64), torch.zeros(1, 1, 1, 64, 64), torch.zeros(1, 1, 3, 64, 64))
+    assert 'CUDA' in str(e.value) or 'cuda' in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'few-shot-vid2vid_b200')
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(d, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, os.path.join(d, f)

@@ -1,0 +1,183 @@
+"""GPU parity tests, network level: the drop-in FewShotGenerator / MultiscaleDiscriminator (fsv kernels, called
+through the C ABI) against (a) the golden fixtures produced by the REFERENCE code itself and (b) the CPU oracle,
+with the reference state_dict loaded into the new modules.  Tolerance 1e-3 relative fp32 (BASELINE.json)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nets as ON     # noqa: E402  (checker only)
+from util import load_npz, state_from, opt_from, T, rel_err, grad_err   # noqa: E402
+
+TOL = 1e-3
+GTOL = 2e-3
+
+
+def _nets():
+    from fsv import networks, ops
+    ops.CONV_USE_TC = 0
+    return networks
+
+
+def C(a):
+    return T(a).cuda()
+
+
+def _make_G(z, temporal=False, train=True):
+    networks = _nets()
+    opt = opt_from(z)
+    opt.gpu_ids = [0]
+    G = networks.define_G(opt)
+    if temporal:
+        G.init_temporal_network()
+    missing = G.load_state_dict(state_from(z, 'sd.'))
+    G.train(train)
+    return G, opt
+
+
+def test_generator_train_forward_backward_vs_reference_golden():
+    z = load_npz('g_face_tiny.npz')
+    G, opt = _make_G(z)
+    label = C(z['label']).requires_grad_(True)
+    iref = C(z['iref']).requires_grad_(True)
+    out = G(label, C(z['lref']), iref)
+    assert out[3] is None and out[1][1] is None and out[5] is None
+    assert rel_err(out[0], T(z['out_img'])) < TOL
+    assert rel_err(out[1][0], T(z['out_flow'])) < TOL
+    assert rel_err(out[2][0], T(z['out_mask'])) < TOL
+    assert rel_err(out[4][0], T(z['out_warp'])) < TOL
+    loss = ((out[0] * C(z['r1'])).sum() + 0.05 * (out[1][0] * C(z['r2'])).sum() + (out[2][0] * C(z['r3'])).sum() +
+            (out[4][0] * C(z['r4'])).sum())
+    assert abs(loss.item() - float(z['loss'])) < 2e-3 * abs(float(z['loss'])) + 2e-3
+    loss.backward()
+    params = dict(G.named_parameters())
+    for k in z.files:
+        if k.startswith('grad.'):
+            assert grad_err(params[k[5:]].grad, T(z[k])) < GTOL, k
+    assert grad_err(label.grad, T(z['grad_label'])) < GTOL
+    assert grad_err(iref.grad, T(z['grad_iref'])) < GTOL
+    sd1 = G.state_dict()
+    for k in z.files:
+        if k.startswith('post.'):
+            assert rel_err(sd1[k[5:]].float(), T(z[k])) < TOL, k
+
+
+def test_generator_eval_weight_cache_vs_reference_golden():
+    z = load_npz('g_face_tiny_eval.npz')
+    G, opt = _make_G(z, train=False)
+    with torch.no_grad():
+        o0 = G(C(z['label0']), C(z['lref']), C(z['iref']), t=0)
+        o1 = G(C(z['label1']), C(z['lref']), C(z['iref']), t=1)
+    assert rel_err(o0[0], T(z['out_img0'])) < TOL
+    assert rel_err(o1[0], T(z['out_img1'])) < TOL
+    assert rel_err(o1[1][0], T(z['out_flow1'])) < TOL
+    assert rel_err(o1[2][0], T(z['out_mask1'])) < TOL
+
+
+def test_generator_temporal_vs_reference_golden():
+    z = load_npz('g_face_tiny_temporal.npz')
+    G, opt = _make_G(z, temporal=True)
+    out = G(C(z['label']), C(z['lref']), C(z['iref']), prev=[C(z['prev_label']), C(z['prev_img'])])
+    assert rel_err(out[0], T(z['out_img'])) < TOL
+    assert rel_err(out[1][1], T(z['out_flow_prev'])) < TOL
+    assert rel_err(out[2][1], T(z['out_mask_prev'])) < TOL
+    assert rel_err(out[4][1], T(z['out_warp_prev'])) < TOL
+    loss = (out[0] * C(z['r1'])).sum() + (out[4][1] * C(z['r4'])).sum() + (out[2][1] * C(z['r3'])).sum()
+    loss.backward()
+    params = dict(G.named_parameters())
+    for k in z.files:
+        if k.startswith('grad.'):
+            assert grad_err(params[k[5:]].grad, T(z[k])) < GTOL, k
+
+
+def test_discriminator_vs_reference_golden():
+    networks = _nets()
+    z = load_npz('d_tiny.npz')
+    zg = load_npz('g_face_tiny.npz')
+    opt = opt_from(zg)
+    opt.gpu_ids = [0]
+    D = networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, 2, True, gpu_ids=[0])
+    D.load_state_dict(state_from(z, 'sd.'))
+    D.train()
+    x = C(z['x']).requires_grad_(True)
+    pred = D(x)
+    loss = 0
+    assert len(pred) == 2
+    for i, p in enumerate(pred):
+        assert len(p) == 6
+        for j, t in enumerate(p):
+            assert tuple(t.shape) == tuple(z['out.%d.%d' % (i, j)].shape)
+            assert rel_err(t, T(z['out.%d.%d' % (i, j)])) < TOL, (i, j)
+            loss = loss + (t * C(z['r.%d.%d' % (i, j)])).sum()
+    loss.backward()
+    assert grad_err(x.grad, T(z['grad_x'])) < GTOL
+    params = dict(D.named_parameters())
+    for k in z.files:
+        if k.startswith('grad.'):
+            assert grad_err(params[k[5:]].grad, T(z[k])) < GTOL, k
+    sd1 = D.state_dict()
+    for k in z.files:
+        if k.startswith('post.'):
+            assert rel_err(sd1[k[5:]], T(z[k])) < TOL, k
+
+
+def test_train_step_losses_vs_reference_golden():
+    """one D-step + G-step through fsv.trainer (the mirror of vid2vid_model.py:62-128 + loss_collector.py)"""
+    from fsv import trainer
+    networks = _nets()
+    z = load_npz('step_face_tiny.npz')
+    zg = load_npz('g_face_tiny.npz')
+    opt = opt_from(zg)
+    opt.gpu_ids = [0]
+    G = networks.define_G(opt)
+    G.load_state_dict(state_from(zg, 'sd.'))
+    D = networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, 1, True, gpu_ids=[0])
+    D.load_state_dict(state_from(z, 'sdD.'))
+    G.train(), D.train()
+    label, lref, iref, tgt = C(z['label']), C(z['lref']), C(z['iref']), C(z['tgt'])
+    dl = trainer.discriminator_losses(opt, G, D, label, tgt, lref, iref)
+    assert rel_err(dl['D_real'].reshape(-1), T(z['D_real']).reshape(-1)) < TOL
+    assert rel_err(dl['D_fake'].reshape(-1), T(z['D_fake']).reshape(-1)) < TOL
+    sum(v.mean() for v in dl.values()).backward()
+    pd = dict(D.named_parameters())
+    for k in z.files:
+        if k.startswith('gradD.'):
+            assert grad_err(pd[k[6:]].grad, T(z[k])) < GTOL, k
+    D.zero_grad()
+    gl, fake = trainer.generator_losses(opt, G, D, label, tgt, lref, iref)
+    assert rel_err(fake, T(z['fake'])) < TOL
+    for n in ('G_GAN', 'G_GAN_Feat', 'F_Warp', 'F_Mask'):
+        assert rel_err(gl[n].reshape(-1), T(z[n]).reshape(-1)) < TOL, n
+    sum(v.mean() for v in gl.values()).backward()
+    pg = dict(G.named_parameters())
+    for k in z.files:
+        if k.startswith('gradG.'):
+            assert grad_err(pg[k[6:]].grad, T(z[k])) < GTOL, k
+
+
+def test_generator_matches_oracle_on_fresh_seeded_inputs():
+    """same seeded inputs through the CUDA path and the CPU oracle (not a stored fixture): pose-like 6-channel
+    labels, rectangular frames, batch 3."""
+    networks = _nets()
+    zg = load_npz('g_face_tiny.npz')
+    opt = opt_from(zg)
+    opt.gpu_ids = [0]
+    opt.input_nc = 6
+    opt.aspect_ratio = 0.5
+    torch.manual_seed(5)
+    G = networks.define_G(opt)
+    G.train()
+    sd = {k: v.detach().cpu().clone() for k, v in G.state_dict().items()}
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 3, 64, 32
+    label = torch.rand(B, 6, H, W, generator=g) * 2 - 1
+    lref = torch.rand(B, 1, 6, H, W, generator=g) * 2 - 1
+    iref = torch.rand(B, 1, 3, H, W, generator=g) * 2 - 1
+    out = G(label.cuda(), lref.cuda(), iref.cuda())
+    opt_cpu = opt_from(zg)
+    opt_cpu.input_nc, opt_cpu.aspect_ratio = 6, 0.5
+    ref = ON.generator_forward(sd, opt_cpu, label, lref, iref, training=True)
+    assert rel_err(out[0], ref[0]) < TOL
+    assert rel_err(out[1][0], ref[1][0]) < TOL
+    assert rel_err(out[2][0], ref[2][0]) < TOL
+    assert rel_err(out[4][0], ref[4][0]) < TOL

@@ -1,0 +1,295 @@
+"""GPU parity tests, op level: every fsv C-ABI kernel family (through the autograd wrappers) against the
+CPU oracle / plain torch-CPU float64 math on the same seeded inputs.  Tolerance: 1e-3 relative fp32
+(BASELINE.json north_star); the SIMT fp32 kernels are expected to sit around 1e-6."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ops as O          # noqa: E402  (checker only)
+from util import rel_err, grad_err   # noqa: E402
+
+TOL = 1e-4
+
+
+def _fsv():
+    import fsv
+    from fsv import ops
+    ops.CONV_USE_TC = 0          # op tests pin the exact-fp32 SIMT path; the tcgen05 path has its own tests
+    return ops
+
+
+def dev(t):
+    return t.detach().float().cuda()
+
+
+def to_nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def to_nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+G = torch.Generator().manual_seed(7)
+
+
+def rnd(*shape, scale=1.0):
+    return torch.randn(*shape, generator=G, dtype=torch.float64) * scale
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, up, act, bias, residual
+    (2, 9, 11, 1, 4, 3, 1, 1, 1, 1, True, False),
+    (2, 12, 10, 5, 8, 3, 2, 1, 1, 1, True, False),
+    (1, 6, 8, 8, 16, 3, 1, 1, 2, 1, True, False),
+    (2, 17, 13, 8, 4, 4, 2, 2, 1, 1, True, False),
+    (2, 9, 9, 16, 1, 4, 1, 2, 1, 0, True, False),
+    (2, 8, 8, 64, 32, 1, 1, 0, 1, 0, False, False),
+    (1, 8, 8, 32, 72, 3, 1, 1, 1, 0, True, True),
+    (2, 10, 6, 12, 3, 3, 1, 1, 1, 2, True, False),
+    (2, 10, 6, 12, 1, 3, 1, 1, 1, 3, True, False),
+    (1, 33, 31, 20, 24, 3, 2, 1, 1, 1, True, False),
+    (3, 5, 7, 130, 70, 3, 1, 1, 1, 0, True, False),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_fwd_bwd(case):
+    ops = _fsv()
+    N, H, W, Cin, Cout, k, stride, pad, up, act, has_b, has_r = case
+    x = rnd(N, Cin, H, W).requires_grad_(True)
+    w = rnd(Cout, Cin, k, k, scale=0.2).requires_grad_(True)
+    b = rnd(Cout).requires_grad_(True) if has_b else None
+    xin = O.up2(x) if up == 2 else x
+    y = F.conv2d(xin, w, b, stride=stride, padding=pad)
+    r = rnd(*y.shape).requires_grad_(True) if has_r else None
+    if has_r:
+        y = y + r
+    y = [lambda v: v, O.lrelu, torch.tanh, torch.sigmoid][act](y)
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+
+    xg = to_nhwc(dev(x)).requires_grad_(True)
+    wg = dev(w).requires_grad_(True)
+    bg = dev(b).requires_grad_(True) if has_b else None
+    rg = to_nhwc(dev(r)).requires_grad_(True) if has_r else None
+    yg = ops.conv2d(xg, wg.permute(0, 2, 3, 1).contiguous(), bg, stride=stride, pad=pad, up=up, act=act, residual=rg)
+    assert rel_err(to_nchw(yg), y) < TOL
+    (yg * to_nhwc(dev(go))).sum().backward()
+    assert grad_err(to_nchw(xg.grad), x.grad) < TOL
+    assert grad_err(wg.grad, w.grad) < TOL
+    if has_b:
+        assert grad_err(bg.grad, b.grad) < TOL
+    if has_r:
+        assert grad_err(to_nchw(rg.grad), r.grad) < TOL
+
+
+def test_conv_in_act_and_scale():
+    ops = _fsv()
+    x = rnd(2, 8, 7, 9).requires_grad_(True)
+    w = rnd(3, 8, 3, 3, scale=0.2).requires_grad_(True)
+    b = rnd(3).requires_grad_(True)
+    y = torch.tanh(F.conv2d(O.lrelu(x), w, b, padding=1))
+    y2 = F.conv2d(x, w, b, padding=1) * 20.0
+    go = rnd(*y.shape)
+    ((y + y2) * go).sum().backward()
+    xg, wg, bg = to_nhwc(dev(x)).requires_grad_(True), dev(w).requires_grad_(True), dev(b).requires_grad_(True)
+    wo = wg.permute(0, 2, 3, 1).contiguous()
+    yg = ops.conv2d(xg, wo, bg, pad=1, act=ops.ACT_TANH, in_act=ops.ACT_LRELU)
+    yg2 = ops.conv2d(xg, wo, bg, pad=1, out_scale=20.0)
+    assert rel_err(to_nchw(yg), y) < TOL and rel_err(to_nchw(yg2), y2) < TOL
+    ((yg + yg2) * to_nhwc(dev(go))).sum().backward()
+    assert grad_err(to_nchw(xg.grad), x.grad) < TOL and grad_err(wg.grad, w.grad) < TOL and grad_err(bg.grad, b.grad) < TOL
+
+
+@pytest.mark.parametrize('rows,k,out', [(64, 16, 34), (200, 64, 66), (37, 8, 9)])
+def test_linear(rows, k, out):
+    ops = _fsv()
+    x = rnd(rows, k).requires_grad_(True)
+    w = rnd(out, k, scale=0.3).requires_grad_(True)
+    b = rnd(out).requires_grad_(True)
+    y = O.lrelu(F.linear(x, w, b))
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    xg, wg, bg = dev(x).requires_grad_(True), dev(w).requires_grad_(True), dev(b).requires_grad_(True)
+    yg = ops.linear(xg, wg, bg, act=ops.ACT_LRELU)
+    assert rel_err(yg, y) < TOL
+    (yg * dev(go)).sum().backward()
+    assert grad_err(xg.grad, x.grad) < TOL and grad_err(wg.grad, w.grad) < TOL and grad_err(bg.grad, b.grad) < TOL
+
+
+def test_batch_conv1x1_inside_flat():
+    """per-sample weights addressed inside the hyper-network's flat output (base_network.py:56-71,154-167)."""
+    ops = _fsv()
+    B, cin, cout, H, W = 3, 8, 4, 6, 5
+    L = cout * cin + cout + 7                       # trailing junk like the embedding weights' dropped tail
+    flat = rnd(B, L, scale=0.3).requires_grad_(True)
+    x = rnd(B, cin, H, W).requires_grad_(True)
+    wt = flat[:, :cout * cin].reshape(B, cout, cin, 1, 1)
+    bs = flat[:, cout * cin:cout * cin + cout]
+    y = O.lrelu(O.batch_conv(x, wt, bs))
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    fg = dev(flat).requires_grad_(True)
+    xg = to_nhwc(dev(x)).requires_grad_(True)
+    yg = ops.batch_conv1x1(xg, fg, cout, cin, 0, cout * cin, act=ops.ACT_LRELU)
+    assert rel_err(to_nchw(yg), y) < TOL
+    (yg * to_nhwc(dev(go))).sum().backward()
+    assert grad_err(to_nchw(xg.grad), x.grad) < TOL
+    assert grad_err(fg.grad, flat.grad) < TOL
+
+
+@pytest.mark.parametrize('mode,training,affine', [('batch', True, True), ('batch', False, True), ('instance', True, True),
+                                                  ('batch', True, False)])
+def test_norm_act(mode, training, affine):
+    ops = _fsv()
+    N, C, H, W = 3, 12, 9, 7
+    x = (rnd(N, C, H, W) * 2 + 0.7).requires_grad_(True)
+    wt = (rnd(C) * 0.3 + 1).requires_grad_(True) if affine else None
+    bs = rnd(C).requires_grad_(True) if affine else None
+    rm, rv = rnd(C, scale=0.2).float(), (torch.rand(C, generator=G) + 0.5)
+    sd = {'n.running_mean': rm.clone().double(), 'n.running_var': rv.clone().double(),
+          'n.num_batches_tracked': torch.tensor(0)}
+    if affine:
+        sd['n.weight'], sd['n.bias'] = wt, bs
+    y = O.lrelu(O.batch_norm(x, sd, 'n', training) if mode == 'batch' else O.instance_norm(x, wt, bs, eps=0.1))
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    xg = to_nhwc(dev(x)).requires_grad_(True)
+    wg = dev(wt).requires_grad_(True) if affine else None
+    bg = dev(bs).requires_grad_(True) if affine else None
+    rmg, rvg = rm.cuda(), rv.float().cuda()
+    m = ops.NORM_BATCH if mode == 'batch' else ops.NORM_INSTANCE
+    yg = ops.norm_act(xg, wg, bg, rmg if mode == 'batch' else None, rvg if mode == 'batch' else None, m, training,
+                      1e-5 if mode == 'batch' else 0.1, 0.1, ops.ACT_LRELU)
+    assert rel_err(to_nchw(yg), y) < TOL
+    (yg * to_nhwc(dev(go))).sum().backward()
+    assert grad_err(to_nchw(xg.grad), x.grad) < TOL
+    if affine:
+        assert grad_err(wg.grad, wt.grad) < TOL and grad_err(bg.grad, bs.grad) < TOL
+    if mode == 'batch' and training:
+        assert rel_err(rmg, sd['n.running_mean']) < TOL and rel_err(rvg, sd['n.running_var']) < TOL
+
+
+@pytest.mark.parametrize('kind,up,nmaps,adaptive,training', [
+    ('batch', 1, 1, False, True), ('batch', 2, 3, True, True), ('instance', 1, 2, True, True),
+    ('batch', 1, 2, True, False), ('batch', 2, 1, True, True), ('batch', 1, 3, False, True)])
+def test_spade(kind, up, nmaps, adaptive, training):
+    """fused SPADE (+LeakyReLU, + x2 upsample-on-load) vs normalization.py:37-52 restated in oracle.ops.spade."""
+    ops = _fsv()
+    from fsv.networks.layers import SPADE
+    N, C, Hs, Ws = 2, 12, 6, 5
+    Ks = [8, 4, 16][:nmaps]
+    H, W = Hs * up, Ws * up
+    x = (rnd(N, C, Hs, Ws) * 1.5 + 0.3).requires_grad_(True)
+    maps = [rnd(N, K, H, W).requires_grad_(True) for K in Ks]
+    mod = SPADE(C, Ks, norm='spectralspadesync' + kind, ks=1, params_free=adaptive).cuda()
+    mod.train(training)
+    sd = {}
+    for n_, p_ in mod.named_parameters():
+        p_.data.normal_(0, 0.3)
+        sd['s.' + n_] = p_.detach().cpu().double().requires_grad_(True)
+    if kind == 'batch':
+        mod.norm.running_mean.normal_(0, 0.2)
+        mod.norm.running_var.uniform_(0.5, 1.5)
+        sd['s.norm.running_mean'] = mod.norm.running_mean.cpu().double().clone()
+        sd['s.norm.running_var'] = mod.norm.running_var.cpu().double().clone()
+        sd['s.norm.num_batches_tracked'] = torch.tensor(0)
+    flat = wts = None
+    if adaptive:
+        K0 = Ks[0]
+        n_gb = C * K0 + C
+        flat = rnd(N, 2 * n_gb, scale=0.3).requires_grad_(True)
+        wts = O.slice_gamma_beta(flat, [C, K0, 1, 1])
+        wts = [[wts[0]], [wts[1]]]
+    xin = O.up2(x) if up == 2 else x
+    y = O.lrelu(O.spade(xin, maps, sd, 's', kind, training, wts))
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+
+    xg = to_nhwc(dev(x)).requires_grad_(True)
+    mg = [to_nhwc(dev(m)).requires_grad_(True) for m in maps]
+    fg = dev(flat).requires_grad_(True) if adaptive else None
+    wloc = (fg, 0, C * Ks[0], C * Ks[0] + C, 2 * C * Ks[0] + C) if adaptive else None
+    yg = mod(xg, mg, wloc, up=up, act=ops.ACT_LRELU)
+    assert rel_err(to_nchw(yg), y) < TOL
+    (yg * to_nhwc(dev(go))).sum().backward()
+    assert grad_err(to_nchw(xg.grad), x.grad) < TOL
+    for a, b in zip(mg, maps):
+        assert grad_err(to_nchw(a.grad), b.grad) < TOL
+    for n_, p_ in mod.named_parameters():
+        assert grad_err(p_.grad, sd['s.' + n_].grad) < TOL, n_
+    if adaptive:
+        assert grad_err(fg.grad, flat.grad) < TOL
+    if kind == 'batch' and training:
+        assert rel_err(mod.norm.running_mean, sd['s.norm.running_mean']) < TOL
+        assert rel_err(mod.norm.running_var, sd['s.norm.running_var']) < TOL
+        assert int(mod.norm.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize('blend', [False, True])
+def test_warp(blend):
+    ops = _fsv()
+    N, H, W = 2, 11, 14
+    img = rnd(N, 3, H, W).requires_grad_(True)
+    flow = (rnd(N, 2, H, W) * 3).requires_grad_(True)
+    mask = torch.sigmoid(rnd(N, 1, H, W)).requires_grad_(True)
+    raw = rnd(N, 3, H, W).requires_grad_(True)
+    wr = O.resample(img, flow)
+    y = raw * mask + wr * (1 - mask) if blend else torch.cat([wr, mask], 1)
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    ig, fg = to_nhwc(dev(img)).requires_grad_(True), to_nhwc(dev(flow)).requires_grad_(True)
+    mg, rg = to_nhwc(dev(mask)).requires_grad_(True), to_nhwc(dev(raw)).requires_grad_(True)
+    yg = ops.warp_blend(ig, fg, mg, rg) if blend else ops.warp_concat(ig, fg, mg)
+    assert rel_err(to_nchw(yg), y) < TOL
+    (yg * to_nhwc(dev(go))).sum().backward()
+    assert grad_err(to_nchw(fg.grad), flow.grad) < 5e-4
+    assert grad_err(to_nchw(mg.grad), mask.grad) < TOL
+    assert grad_err(to_nchw(ig.grad), img.grad) < TOL
+    if blend:
+        assert grad_err(to_nchw(rg.grad), raw.grad) < TOL
+
+
+def test_softmax_outer():
+    ops = _fsv()
+    B, C, H, W = 2, 24, 4, 3
+    a = rnd(B, C, H, W).requires_grad_(True)
+    l = (rnd(B, C, H, W) * 2).requires_grad_(True)
+    y = O.ref_outer_product(a, l)[..., 0]
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    ag, lg = to_nhwc(dev(a)).requires_grad_(True), to_nhwc(dev(l)).requires_grad_(True)
+    yg = ops.softmax_outer(ag, lg)
+    assert rel_err(yg, y) < TOL
+    (yg * dev(go)).sum().backward()
+    assert grad_err(to_nchw(ag.grad), a.grad) < TOL and grad_err(to_nchw(lg.grad), l.grad) < TOL
+
+
+def test_layout_ops():
+    ops = _fsv()
+    x = rnd(2, 5, 7, 9).requires_grad_(True)
+    z = rnd(2, 3, 7, 9).requires_grad_(True)
+    xg, zg = dev(x).requires_grad_(True), dev(z).requires_grad_(True)
+    p = ops.pack_nhwc(xg, zg)
+    assert torch.equal(to_nchw(p).cpu().double(), torch.cat([x, z], 1).float().double())
+    u = ops.upsample2x(p)
+    a = ops.avgpool3s2(u)
+    c = ops.cat_channels(a, a * 2)
+    back = ops.to_nchw(c)
+    ref = torch.cat([x, z], 1)
+    ref = O.avgpool3s2(O.up2(ref))
+    ref = torch.cat([ref, ref * 2], 1)
+    assert rel_err(back, ref) < 1e-6
+    go = rnd(*ref.shape)
+    (ref * go).sum().backward()
+    (back * dev(go)).sum().backward()
+    assert grad_err(xg.grad, x.grad) < 1e-5 and grad_err(zg.grad, z.grad) < 1e-5
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    ops = _fsv()
+    with pytest.raises(Exception):
+        ops.to_nhwc(torch.zeros(1, 1, 2, 2))
