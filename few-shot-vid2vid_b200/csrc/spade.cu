@@ -97,12 +97,14 @@ __device__ __forceinline__ void spade_gemm(const SpadeP& p, int i, int n, int m0
         }
         __syncthreads();
     }
-    const float* bgp = p.bg[i] + (long long)n * p.w_nstride[i];
-    const float* bbp = p.bb[i] + (long long)n * p.w_nstride[i];
+    // biases may be absent: the reference's adaptive path calls batch_conv(m, weights[0][j]) with the weight
+    // tensor only (normalization.py:48-50), i.e. the hyper-network's bias slots are never applied.
+    const float* bgp = p.bg[i] ? p.bg[i] + (long long)n * p.w_nstride[i] : nullptr;
+    const float* bbp = p.bb[i] ? p.bb[i] + (long long)n * p.w_nstride[i] : nullptr;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         int c = c0 + tx * 4 + s;
-        float g0 = c < p.C ? bgp[c] : 0.f, b0 = c < p.C ? bbp[c] : 0.f;
+        float g0 = (bgp && c < p.C) ? bgp[c] : 0.f, b0 = (bbp && c < p.C) ? bbp[c] : 0.f;
 #pragma unroll
         for (int r = 0; r < 4; ++r) { gam[r][s] += g0; bet[r][s] += b0; }
     }
@@ -249,7 +251,7 @@ static int fill_p(SpadeP& p, const fsv_spade_desc* d, const float* const* maps, 
         p.dgamma[i] = nullptr; p.dbeta[i] = nullptr;
         if (on) {
             FSV_REQUIRE(p.K[i] > 0 && p.m_ld[i] >= p.m_coff[i] + p.K[i], "%s: map %d ld/coff/K inconsistent", who, i);
-            FSV_REQUIRE(maps[i] && wg[i] && bg[i] && wb[i] && bb[i], "%s: map %d has null pointers", who, i);
+            FSV_REQUIRE(maps[i] && wg[i] && wb[i], "%s: map %d has null map/weight pointers", who, i);
         }
     }
     return FSV_OK;

@@ -130,9 +130,11 @@ class SPADE(nn.Module):
                 tensors += [m, g.weight.reshape(C, K), g.bias, b.weight.reshape(C, K), b.bias]
                 mcfg.append(dict(K=K))
             else:
-                flat, wg_off, bg_off, wb_off, bb_off = weights
-                tensors += [m, flat, flat, flat, flat]
-                mcfg.append(dict(K=K, wg_off=wg_off, bg_off=bg_off, wb_off=wb_off, bb_off=bb_off, nstride=flat.shape[1]))
+                # normalization.py:48-50 calls batch_conv(m, weights[0][j]) with j = min(i, 1) = 0, i.e. with the
+                # weight tensor of the [weight, bias] pair only: the generated bias slots are never applied.
+                flat, wg_off, _bg_off, wb_off, _bb_off = weights
+                tensors += [m, flat, None, flat, None]
+                mcfg.append(dict(K=K, wg_off=wg_off, wb_off=wb_off, nstride=flat.shape[1]))
         if self.batch:
             self.norm.tick()
         cfg = dict(up=up, mode=NORM_BATCH if self.batch else NORM_INSTANCE, training=self.training,

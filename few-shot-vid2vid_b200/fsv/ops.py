@@ -426,9 +426,9 @@ class SpadeFn(torch.autograd.Function):
             d.K[i], d.m_ld[i], d.m_coff[i], d.w_nstride[i] = mc['K'], m.shape[3], 0, mc.get('nstride', 0)
             maps[i] = m.data_ptr()
             wg[i] = g0.data_ptr() + 4 * mc.get('wg_off', 0)
-            bg[i] = g1.data_ptr() + 4 * mc.get('bg_off', 0)
+            bg[i] = None if g1 is None else g1.data_ptr() + 4 * mc.get('bg_off', 0)
             wb[i] = b0.data_ptr() + 4 * mc.get('wb_off', 0)
-            bb[i] = b1.data_ptr() + 4 * mc.get('bb_off', 0)
+            bb[i] = None if b1 is None else b1.data_ptr() + 4 * mc.get('bb_off', 0)
         return d, (maps, wg, bg, wb, bb)
 
     @staticmethod
@@ -483,13 +483,15 @@ class SpadeFn(torch.autograd.Function):
                 _call(lib.fsv_conv2d_dgrad, ctypes.byref(cd), ptr(dbs[i]), _off(tensors[5 * i + 3], mc.get('wb_off', 0)), ptr(dm), 1, st)
                 grads[5 * i] = dm
             if ctx.needs_input_grad[4 + 5 * i + 1]:
-                gw, gb = buf_for(5 * i + 1), buf_for(5 * i + 2)
+                gw = buf_for(5 * i + 1)
+                gb = buf_for(5 * i + 2) if tensors[5 * i + 2] is not None else None
                 _call(lib.fsv_conv2d_wgrad, ctypes.byref(cd), ptr(m), ptr(dgs[i]), _off(gw, mc.get('wg_off', 0)),
-                      _off(gb, mc.get('bg_off', 0)), 1, st)
+                      None if gb is None else _off(gb, mc.get('bg_off', 0)), 1, st)
             if ctx.needs_input_grad[4 + 5 * i + 3]:
-                gw, gb = buf_for(5 * i + 3), buf_for(5 * i + 4)
+                gw = buf_for(5 * i + 3)
+                gb = buf_for(5 * i + 4) if tensors[5 * i + 4] is not None else None
                 _call(lib.fsv_conv2d_wgrad, ctypes.byref(cd), ptr(m), ptr(dbs[i]), _off(gw, mc.get('wb_off', 0)),
-                      _off(gb, mc.get('bb_off', 0)), 1, st)
+                      None if gb is None else _off(gb, mc.get('bb_off', 0)), 1, st)
         return (dx, None, None, None) + tuple(grads)
 
 

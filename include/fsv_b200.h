@@ -140,7 +140,9 @@ typedef struct fsv_spade_desc {
     int m_coff[FSV_SPADE_MAX_MAPS];
     long long w_nstride[FSV_SPADE_MAX_MAPS];  /* 0 = fixed mlp_gamma/mlp_beta weights; else per-sample stride (hyper-weights) */
 } fsv_spade_desc;
-/* out = act( (((x-mean)*rstd) * (1+g_0) + b_0) * (1+g_1) + b_1 ... ),  g_i = Wg_i . map_i + bg_i  (1x1) */
+/* out = act( (((x-mean)*rstd) * (1+g_0) + b_0) * (1+g_1) + b_1 ... ),  g_i = Wg_i . map_i + bg_i  (1x1).
+ * bg[i] / bb[i] may be NULL (no bias): the reference's adaptive path applies the hyper-weights without their
+ * bias slots (normalization.py:48-50 indexes weights[0][j] -> the weight tensor only). */
 int fsv_spade_fwd(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
                   const float* const* maps, const float* const* wg, const float* const* bg,
                   const float* const* wb, const float* const* bb, float* out, void* stream);

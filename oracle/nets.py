@@ -48,7 +48,7 @@ def sn_conv_bn_lrelu(sd, prefix, x, stride, training):
     return lrelu(batch_norm(y, sd, prefix + '.bn', training))
 
 
-def spade_resblock(sd, prefix, x, maps, norm_kind, training, norm_weights=None):
+def spade_resblock(sd, prefix, x, maps, norm_kind, training, norm_weights=None, taps=None):
     """architecture.py:92-108 SPADEResnetBlock.forward with SPADE norms
     (generator main branch).  Learned 1x1 shortcut has NO activation (:103)."""
     if norm_weights is None:
@@ -59,10 +59,12 @@ def spade_resblock(sd, prefix, x, maps, norm_kind, training, norm_weights=None):
         xs = F.conv2d(xs, get_weight(sd, prefix + '.conv_s', training), None)
     else:
         xs = x
-    dx = lrelu(spade(x, maps, sd, prefix + '.bn_0', norm_kind, training, norm_weights[0]))
-    dx = F.conv2d(dx, get_weight(sd, prefix + '.conv_0', training), sd[prefix + '.conv_0.bias'], padding=1)
-    dx = lrelu(spade(dx, maps, sd, prefix + '.bn_1', norm_kind, training, norm_weights[1]))
-    dx = F.conv2d(dx, get_weight(sd, prefix + '.conv_1', training), sd[prefix + '.conv_1.bias'], padding=1)
+    t0 = lrelu(spade(x, maps, sd, prefix + '.bn_0', norm_kind, training, norm_weights[0]))
+    t1 = F.conv2d(t0, get_weight(sd, prefix + '.conv_0', training), sd[prefix + '.conv_0.bias'], padding=1)
+    t2 = lrelu(spade(t1, maps, sd, prefix + '.bn_1', norm_kind, training, norm_weights[1]))
+    dx = F.conv2d(t2, get_weight(sd, prefix + '.conv_1', training), sd[prefix + '.conv_1.bias'], padding=1)
+    if taps is not None:     # debugging aid for the tests: expose the intermediates
+        taps.update({prefix + '.bn_0': t0, prefix + '.conv_0': t1, prefix + '.bn_1': t2, prefix + '.conv_s': xs})
     return xs + dx
 
 
@@ -239,7 +241,7 @@ def generator_forward(sd, opt, label, label_refs, img_refs, prev=(None, None), t
     internals = {}
     for i in range(nd, -1, -1):
         nw = norm_w[i] if (opt.adaptive_spade and i < opt.n_adaptive_layers) else None
-        x = spade_resblock(sd, 'up_%d' % i, x, enc_label[i], kind, training, nw)
+        x = spade_resblock(sd, 'up_%d' % i, x, enc_label[i], kind, training, nw, taps=internals if return_internals else None)
         if return_internals:
             internals['up_%d' % i] = x
         if i != 0:

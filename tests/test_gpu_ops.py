@@ -52,6 +52,9 @@ CONV_CASES = [
     (2, 10, 6, 12, 1, 3, 1, 1, 1, 3, True, False),
     (1, 33, 31, 20, 24, 3, 2, 1, 1, 1, True, False),
     (3, 5, 7, 130, 70, 3, 1, 1, 1, 0, True, False),
+    (2, 32, 32, 8, 8, 3, 1, 1, 1, 0, True, True),      # up_1.conv_1 of the tiny golden generator
+    (2, 16, 16, 16, 16, 3, 1, 1, 1, 0, True, True),
+    (2, 64, 64, 4, 4, 3, 1, 1, 1, 0, True, True),
 ]
 
 
@@ -177,11 +180,18 @@ def test_norm_act(mode, training, affine):
     ('batch', 1, 1, False, True), ('batch', 2, 3, True, True), ('instance', 1, 2, True, True),
     ('batch', 1, 2, True, False), ('batch', 2, 1, True, True), ('batch', 1, 3, False, True)])
 def test_spade(kind, up, nmaps, adaptive, training):
+    _run_spade(kind, up, nmaps, adaptive, training, 2, 12, 6, 5, [8, 4, 16][:nmaps])
+
+
+@pytest.mark.parametrize('C,Hs,up,Ks', [(8, 32, 1, [8, 8]), (16, 16, 2, [8, 8]), (4, 64, 1, [4, 4]), (64, 4, 1, [64])])
+def test_spade_generator_shapes(C, Hs, up, Ks):
+    _run_spade('batch', up, len(Ks), True, True, 2, C, Hs, Hs, Ks)
+
+
+def _run_spade(kind, up, nmaps, adaptive, training, N, C, Hs, Ws, Ks):
     """fused SPADE (+LeakyReLU, + x2 upsample-on-load) vs normalization.py:37-52 restated in oracle.ops.spade."""
     ops = _fsv()
     from fsv.networks.layers import SPADE
-    N, C, Hs, Ws = 2, 12, 6, 5
-    Ks = [8, 4, 16][:nmaps]
     H, W = Hs * up, Ws * up
     x = (rnd(N, C, Hs, Ws) * 1.5 + 0.3).requires_grad_(True)
     maps = [rnd(N, K, H, W).requires_grad_(True) for K in Ks]
@@ -202,8 +212,9 @@ def test_spade(kind, up, nmaps, adaptive, training):
         K0 = Ks[0]
         n_gb = C * K0 + C
         flat = rnd(N, 2 * n_gb, scale=0.3).requires_grad_(True)
+        # same structure the generator passes: [[Wg, bg], [Wb, bb]]; the reference (and the oracle) then index
+        # weights[0][0] -> Wg only, so the bias slots are dead (normalization.py:48-50)
         wts = O.slice_gamma_beta(flat, [C, K0, 1, 1])
-        wts = [[wts[0]], [wts[1]]]
     xin = O.up2(x) if up == 2 else x
     y = O.lrelu(O.spade(xin, maps, sd, 's', kind, training, wts))
     go = rnd(*y.shape)
@@ -293,3 +304,59 @@ def test_cpu_tensor_is_rejected_loudly():
     ops = _fsv()
     with pytest.raises(Exception):
         ops.to_nhwc(torch.zeros(1, 1, 2, 2))
+
+
+@pytest.mark.parametrize('fin,fout,Hs,up', [(16, 8, 16, 2), (8, 4, 8, 2), (12, 12, 6, 1)])
+def test_spade_resblock(fin, fout, Hs, up):
+    """whole SPADEResnetBlock (architecture.py:92-108) incl. spectral norm, learned shortcut, hyper-weights, fused
+    upsample: module vs oracle.nets.spade_resblock, gradients w.r.t. input, maps, hyper-weights and parameters."""
+    ops = _fsv()
+    from oracle import nets as ON
+    from fsv.networks.layers import SPADEResnetBlock
+    N, K = 2, 8
+    H = Hs * up
+    torch.manual_seed(3)
+    blk = SPADEResnetBlock(fin, fout, norm='spectralspadesyncbatch', hidden_nc=[K, K, K], norm_params_free=True).cuda()
+    blk.train()
+    for n_, p_ in blk.named_parameters():
+        p_.data.normal_(0, 0.3)
+    sd = {'b.' + k: v.detach().cpu().double().clone() for k, v in blk.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(('running_mean', 'running_var', 'weight_u', 'weight_v')):
+            v.requires_grad_(True)
+    x = rnd(N, fin, Hs, Hs).requires_grad_(True)
+    maps = [rnd(N, K, H, H).requires_grad_(True), rnd(N, K, H, H).requires_grad_(True), None]
+    fh = min(fin, fout)
+    flats, wlocs, wts = [], [], []
+    for co in (fin, fh, fin):
+        n_gb = co * K + co
+        f = rnd(N, 2 * n_gb, scale=0.3).requires_grad_(True)
+        flats.append(f)
+        wts.append(O.slice_gamma_beta(f, [co, K, 1, 1]))
+        wlocs.append((0, co * K, n_gb, n_gb + co * K))
+    xin = O.up2(x) if up == 2 else x
+    y = ON.spade_resblock(sd, 'b', xin, maps, 'batch', True, wts)
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+
+    xg = to_nhwc(dev(x)).requires_grad_(True)
+    mg = [to_nhwc(dev(m)).requires_grad_(True) for m in maps[:2]] + [None]
+    fg = [dev(f).requires_grad_(True) for f in flats]
+    yg = blk(xg, mg, norm_weights=[(f,) + loc for f, loc in zip(fg, wlocs)], up=up)
+    assert rel_err(to_nchw(yg), y) < TOL
+    (yg * to_nhwc(dev(go))).sum().backward()
+    assert grad_err(to_nchw(xg.grad), x.grad) < TOL
+    for a, b in zip(mg[:2], maps[:2]):
+        assert grad_err(to_nchw(a.grad), b.grad) < TOL
+    for a, b in zip(fg, flats):
+        if fin == fout and a is fg[2]:
+            continue                      # no learned shortcut: the shortcut's hyper-weights are unused
+        assert grad_err(a.grad, b.grad) < TOL
+    for n_, p_ in blk.named_parameters():
+        r = sd['b.' + n_].grad
+        if n_ == 'conv_0.bias':
+            continue        # feeds a BatchNorm: mathematically zero gradient, only rounding noise on both sides
+        if r is None:
+            assert p_.grad is None or float(p_.grad.abs().max()) == 0.0, n_
+        else:
+            assert grad_err(p_.grad, r) < TOL, n_

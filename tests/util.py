@@ -48,3 +48,17 @@ def grad_err(a, b, floor=1e-5):
     if float(a.abs().max()) < floor and float(b.abs().max()) < floor:
         return 0.0
     return float((a - b).abs().max() / max(float(b.abs().max()), floor))
+
+
+def l2_err(a, b, floor=1e-5):
+    """Relative L2 error ||a-b|| / ||b||.  Used for NETWORK-level gradient parity: a deep LeakyReLU network is not
+    differentiable where a pre-activation is ~0, and with ~1e6 activations one of them always sits within fp32
+    rounding (|v| ~ 1e-6) of the kink; any change of summation order (GPU vs CPU) can flip that element's slope
+    (1 vs 0.2), which perturbs a handful of gradient entries by percents while leaving the L2 error ~1e-3
+    (measured: up_1.bn_1 of the tiny golden generator has one pre-activation of 1.4e-6).  Op- and
+    block-level tests use the tight max-norm criterion on continuous random inputs."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    if float(a.abs().max()) < floor and float(b.abs().max()) < floor:
+        return 0.0
+    return float((a - b).norm() / max(float(b.norm()), floor))
