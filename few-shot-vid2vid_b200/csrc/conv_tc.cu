@@ -1,9 +1,378 @@
-// tcgen05/TMA implicit-GEMM convolution (placeholder until the kernel lands: reports "not eligible").
+// tcgen05 / TMA implicit-GEMM convolution (forward) for NHWC fp32 activations, TF32 tensor cores,
+// fp32 accumulation in TMEM.  sm_100a only.
+//
+// Replaces cuDNN's conv2d for the FLOP-carrying layers of the hot path (architecture.py:60,81-84;
+// generator.py:473-489,523-537; discriminator.py:69-88): 3x3 stride-1/2 (pad 1) and 4x4 stride-1/2
+// (pad 2) with Cin % 32 == 0 and Cout % 16 == 0.  The data gradient of a stride-1 conv is the same
+// kernel run on dy with spatially flipped, channel-transposed weights (host side, ops.py).
+//
+// GEMM view:  D[pixel, cout] = sum_{tap} sum_{ci}  X[pixel shifted by tap, ci] * W[cout, tap, ci]
+//   M tile  = 128 output pixels = TN images x TH rows x TW cols (one TMA box of the NHWC input per tap,
+//             out-of-bounds rows/cols zero-filled by TMA == the conv's zero padding; no im2col buffer)
+//   N tile  = BN output channels (<= 128), accumulator = 128 lanes x BN fp32 columns of TMEM
+//   K block = 32 input channels of one tap = 128-byte rows, SWIZZLE_128B, K-major for both operands
+//   stride 2: the input is addressed through four "parity" tensor maps (even/odd rows x even/odd
+//             cols), so every tap is again a dense box load.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane issues tcgen05.mma.kind::tf32, 4 per K block), warps 2..5 = epilogue (tcgen05.ld 32x32b, bias +
+// residual + activation + scale, 16-byte global stores).  smem ring of STAGES x (16 KB A + BN*128 B B)
+// guarded by full/empty mbarriers; tcgen05.commit releases ring slots and signals the epilogue.
+//
+// Roofline: tensor-bound in the limit; with 4-byte operands a 128x128x32 tile moves 32 KB per
+// 1.05 MFLOP (32 FLOP/B) through L2, so this first version is L2-bandwidth bound below the TF32 peak
+// (DESIGN.md section 5).
 #include "common.cuh"
-extern "C" int fsv_conv2d_tc_eligible(const fsv_conv_desc* d) { (void)d; return 0; }
+#include <cuda.h>
+#include <string.h>
+
+#define TC_BM 128
+#define TC_BK 32           // fp32 elements per K block = 128 bytes
+#define TC_MAX_TAPS 16
+#define TC_STAGES 4
+#define TC_A_BYTES (TC_BM * TC_BK * 4)   // 16 KB
+
+struct TcTap { int map, dh, dw, wk; };
+
+struct __align__(64) TcParams {
+    CUtensorMap amap[4];
+    CUtensorMap bmap;
+    TcTap taps[TC_MAX_TAPS];
+    int ntaps, Cin, Cout, N, Ho, Wo;
+    int TW, TH, TN, tiles_w, tiles_h;
+    int y_ld, y_coff, res_ld, res_coff, act;
+    float out_scale;
+    int BN;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64), [46,48) version = 1 (Blackwell),
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @ [4,6), a/b format TF32 (2) @ [7,10)/[10,13),
+// K-major A and B (bits 15,16 = 0), N>>3 @ [17,23), M>>4 @ [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcParams p, const float* __restrict__ bias,
+                                                    const float* __restrict__ residual, float* __restrict__ y) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for SWIZZLE_128B
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BN = p.BN;
+    const int b_bytes = BN * TC_BK * 4;
+    const int stage_bytes = TC_A_BYTES + b_bytes;
+    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * stage_bytes);   // full[STAGES], empty[STAGES], tmem_full
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int mt = blockIdx.x;
+    const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+    const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
+    const int n0 = mt * p.TN;
+    const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+    const int co0 = blockIdx.y * BN;
+    const int kblocks = p.Cin / TC_BK;
+    const int num_k = p.ntaps * kblocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[TC_STAGES + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * TC_STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t ph = (kb / TC_STAGES) & 1;
+                mbar_wait(smem_u32(&bars[TC_STAGES + s]), ph ^ 1);          // slot free
+                const int t = kb / kblocks, cb = kb - t * kblocks;
+                const TcTap tap = p.taps[t];
+                const uint32_t full = smem_u32(&bars[s]);
+                const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
+                mbar_expect_tx(full, (uint32_t)stage_bytes);
+                tma_load_4d(a_dst, &p.amap[tap.map], full, cb * TC_BK, w0 + tap.dw, h0 + tap.dh, n0);
+                tma_load_2d(a_dst + TC_A_BYTES, &p.bmap, full, tap.wk * p.Cin + cb * TC_BK, co0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer
+            const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t ph = (kb / TC_STAGES) & 1;
+                mbar_wait(smem_u32(&bars[s]), ph);                           // operands landed
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
+                    tc_mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                }
+                tc_commit(smem_u32(&bars[TC_STAGES + s]));                   // frees the smem slot when the MMAs retire
+            }
+            tc_commit(smem_u32(&bars[2 * TC_STAGES]));                       // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 -> TMEM lane quadrant (warp % 4)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                // GEMM row = pixel inside the tile
+        mbar_wait(smem_u32(&bars[2 * TC_STAGES]), 0);
+        tc_fence_after();
+        const int tw = row % p.TW;
+        const int r2 = row / p.TW;
+        const int th = r2 % p.TH;
+        const int tn = r2 / p.TH;
+        const int n = n0 + tn, ho = h0 + th, wo = w0 + tw;
+        const bool valid = (n < p.N) && (ho < p.Ho) && (wo < p.Wo);
+        const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
+        float* yrow = y + pix * p.y_ld + p.y_coff + co0;
+        const float* rrow = residual ? residual + pix * p.res_ld + p.res_coff + co0 : nullptr;
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (valid) {
+                const int ncol = min(32, BN - c);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncol) {
+                        float4 o;
+                        o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
+                        o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+                        if (bias) {
+                            float4 b = *reinterpret_cast<const float4*>(bias + co0 + c + j);
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        if (rrow) {
+                            float4 r = *reinterpret_cast<const float4*>(rrow + c + j);
+                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                        }
+                        o.x = fsv_act(o.x, p.act) * p.out_scale; o.y = fsv_act(o.y, p.act) * p.out_scale;
+                        o.z = fsv_act(o.z, p.act) * p.out_scale; o.w = fsv_act(o.w, p.act) * p.out_scale;
+                        *reinterpret_cast<float4*>(yrow + c + j) = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)f;
+    }
+    return fn;
+}
+
+static int pick_bn(int cout) {
+    if (cout % 128 == 0) return 128;
+    if (cout <= 128 && cout % 16 == 0) return cout;
+    if (cout % 64 == 0) return 64;
+    if (cout % 32 == 0) return 32;
+    return 0;
+}
+
+extern "C" int fsv_conv2d_tc_eligible(const fsv_conv_desc* d) {
+    if (!d) return 0;
+    if (d->up != 1 || d->in_act != FSV_ACT_NONE) return 0;
+    if (d->w_nstride != 0 || d->b_nstride != 0) return 0;
+    if (d->Cin % TC_BK != 0 || d->x_coff % 4 != 0 || d->x_ld % 4 != 0) return 0;
+    if (pick_bn(d->Cout) == 0) return 0;
+    if (d->y_ld % 4 != 0 || d->y_coff % 4 != 0 || d->res_ld % 4 != 0 || d->res_coff % 4 != 0) return 0;
+    if (d->kh * d->kw > TC_MAX_TAPS) return 0;
+    if (d->stride != 1 && d->stride != 2) return 0;
+    if ((long long)d->Ho * d->Wo * d->N < 64) return 0;          // tiny problems: the SIMT kernel is as good
+    return get_encode() != nullptr ? 1 : 0;
+}
+
+static int encode_act_map(CUtensorMap* m, const float* base, int C, int ld, int Wd, int Hd, int N, long long sw, long long sh,
+                          long long sn, int TW, int TH, int TN) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4};
+    cuuint32_t box[4] = {TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    (void)ld;
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 extern "C" int fsv_conv2d_fwd_tc(const fsv_conv_desc* d, const float* x, const float* w, const float* bias,
                                  const float* residual, float* y, void* stream) {
-    (void)d; (void)x; (void)w; (void)bias; (void)residual; (void)y; (void)stream;
-    fsv_set_error("conv2d_fwd_tc: tcgen05 path not built");
-    return FSV_ENOTSUP;
+    FSV_REQUIRE(d != nullptr, "conv2d_fwd_tc: null descriptor");
+    if (!fsv_conv2d_tc_eligible(d)) {
+        fsv_set_error("conv2d_fwd_tc: shape not eligible for the tcgen05 path (need Cin%%32==0, Cout%%16==0, up==1, shared weights)");
+        return FSV_ENOTSUP;
+    }
+    FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w) & 15) == 0 && (((uintptr_t)y) & 15) == 0, "conv2d_fwd_tc: pointers must be 16-byte aligned");
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = pick_bn(d->Cout);
+    // M-tile shape: 128 = TN * TH * TW
+    int TW = 16, TH = 8, TN = 1;
+    if (d->Wo < 16) {
+        TW = 1; while (TW * 2 <= d->Wo && TW < 16) TW *= 2;
+        int rem = 128 / TW;
+        TH = 1; while (TH * 2 <= d->Ho && TH * 2 <= rem) TH *= 2;
+        TN = rem / TH;
+    }
+    p.TW = TW; p.TH = TH; p.TN = TN;
+    p.tiles_w = fsv_cdiv(d->Wo, TW); p.tiles_h = fsv_cdiv(d->Ho, TH);
+    const int tiles_n = fsv_cdiv(d->N, TN);
+    p.ntaps = d->kh * d->kw; p.Cin = d->Cin; p.Cout = d->Cout; p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
+    p.y_ld = d->y_ld; p.y_coff = d->y_coff; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.act = d->act; p.out_scale = d->out_scale;
+    p.BN = BN;
+    const long long ld = d->x_ld;
+    const float* xb = x + d->x_coff;
+    int rc = 0;
+    if (d->stride == 1) {
+        rc = encode_act_map(&p.amap[0], xb, d->Cin, d->x_ld, d->W, d->H, d->N, ld, ld * d->W, ld * d->W * d->H, TW, TH, TN);
+        FSV_REQUIRE(rc == 0, "conv2d_fwd_tc: cuTensorMapEncodeTiled(A) failed with %d", rc);
+        for (int r = 0; r < d->kh; ++r)
+            for (int s = 0; s < d->kw; ++s) {
+                TcTap& t = p.taps[r * d->kw + s];
+                t.map = 0; t.dh = r - d->pad; t.dw = s - d->pad; t.wk = r * d->kw + s;
+            }
+    } else {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                int Hd = (d->H - ph + 1) / 2, Wd = (d->W - pw + 1) / 2;
+                if (Hd <= 0 || Wd <= 0) { Hd = Hd > 0 ? Hd : 1; Wd = Wd > 0 ? Wd : 1; }
+                rc = encode_act_map(&p.amap[ph * 2 + pw], xb + ((long long)ph * d->W + pw) * ld, d->Cin, d->x_ld, Wd, Hd, d->N,
+                                    2 * ld, 2 * ld * d->W, ld * d->W * d->H, TW, TH, TN);
+                FSV_REQUIRE(rc == 0, "conv2d_fwd_tc: cuTensorMapEncodeTiled(A parity %d%d) failed with %d", ph, pw, rc);
+            }
+        for (int r = 0; r < d->kh; ++r)
+            for (int s = 0; s < d->kw; ++s) {
+                TcTap& t = p.taps[r * d->kw + s];
+                int qh = r - d->pad, qw = s - d->pad;
+                int ph = ((qh % 2) + 2) % 2, pw = ((qw % 2) + 2) % 2;
+                t.map = ph * 2 + pw; t.dh = (qh - ph) / 2; t.dw = (qw - pw) / 2; t.wk = r * d->kw + s;
+            }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)p.ntaps * d->Cin, (cuuint64_t)d->Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)p.ntaps * d->Cin * 4};
+        cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = get_encode()(&p.bmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        FSV_REQUIRE(r == CUDA_SUCCESS, "conv2d_fwd_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+    const int smem_bytes = TC_STAGES * (TC_A_BYTES + BN * TC_BK * 4) + (2 * TC_STAGES + 1) * 8 + 16 + 1024;
+    static int configured = 0;
+    if (configured < smem_bytes) {
+        FSV_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->Cout / BN);
+    k_conv_tc<<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(p, bias, residual, y);
+    FSV_CHECK_LAUNCH("conv2d_fwd_tc");
+    return FSV_OK;
 }

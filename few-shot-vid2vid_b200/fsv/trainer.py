@@ -93,7 +93,7 @@ def make_optimizers(opt, netG, netD):
     if opt.no_TTUR:
         beta1, beta2, g_lr, d_lr = opt.beta1, 0.999, opt.lr, opt.lr
     else:
-        beta1, beta2, g_lr, d_lr = 0, opt.beta2, opt.lr / 2, opt.lr * 2
+        beta1, beta2, g_lr, d_lr = 0.0, opt.beta2, opt.lr / 2, opt.lr * 2
     return (torch.optim.Adam(netG.parameters(), lr=g_lr, betas=(beta1, beta2)),
             torch.optim.Adam(netD.parameters(), lr=d_lr, betas=(beta1, beta2)))
 

@@ -1,0 +1,89 @@
+"""GPU parity tests of the tcgen05/TMA implicit-GEMM convolution (TF32 operands, fp32 accumulation) against
+float64 CPU math.  Stated tolerance for the TF32 path: 3e-3 relative (10-bit mantissa operands, K up to 4608);
+the exact-fp32 SIMT path (test_gpu_ops.py) is the 1e-4 one."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ops as O           # noqa: E402
+from util import rel_err, grad_err    # noqa: E402
+
+TOL_TF32 = 3e-3
+G = torch.Generator().manual_seed(21)
+
+
+def rnd(*shape, scale=1.0):
+    return torch.randn(*shape, generator=G, dtype=torch.float64) * scale
+
+
+def to_nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+TC_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, act, bias, residual
+    (2, 16, 16, 32, 32, 3, 1, 1, 0, False, False),
+    (1, 32, 32, 64, 128, 3, 1, 1, 1, True, False),
+    (2, 8, 8, 128, 256, 3, 1, 1, 0, True, True),
+    (2, 17, 17, 32, 64, 4, 2, 2, 1, True, False),
+    (2, 18, 18, 64, 32, 4, 1, 2, 0, True, False),
+    (2, 32, 32, 32, 64, 3, 2, 1, 1, True, False),
+    (4, 4, 4, 64, 64, 3, 1, 1, 0, True, False),
+    (1, 16, 16, 32, 48, 3, 1, 1, 0, True, False),
+    (3, 33, 29, 32, 32, 3, 1, 1, 0, True, False),
+    (2, 16, 16, 64, 64, 1, 1, 0, 0, False, False),
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_conv_tc_forward(case):
+    from fsv import ops, _lib
+    N, H, W, Cin, Cout, k, stride, pad, act, has_b, has_r = case
+    x = rnd(N, Cin, H, W)
+    w = rnd(Cout, Cin, k, k, scale=0.1)
+    b = rnd(Cout) if has_b else None
+    y = F.conv2d(x, w, b, stride=stride, padding=pad)
+    r = rnd(*y.shape) if has_r else None
+    if has_r:
+        y = y + r
+    y = [lambda v: v, O.lrelu][act](y)
+    xg = to_nhwc(x.float().cuda())
+    wg = w.float().cuda().permute(0, 2, 3, 1).contiguous()
+    bg = b.float().cuda() if has_b else None
+    rg = to_nhwc(r.float().cuda()) if has_r else None
+    d = ops._conv_desc(N, H, W, Cin, Cout, k, k, stride, pad)
+    assert _lib.lib.fsv_conv2d_tc_eligible(d) == 1
+    yg = ops.conv2d(xg, wg, bg, stride=stride, pad=pad, act=act, residual=rg, use_tc=1)
+    torch.cuda.synchronize()
+    assert rel_err(yg.permute(0, 3, 1, 2), y) < TOL_TF32
+    ys = ops.conv2d(xg, wg, bg, stride=stride, pad=pad, act=act, residual=rg, use_tc=0)
+    assert rel_err(yg, ys) < TOL_TF32
+
+
+def test_conv_tc_autograd_matches_simt():
+    """forward on tcgen05, data gradient on tcgen05 (flipped weights), weight gradient SIMT: vs the all-SIMT path"""
+    from fsv import ops
+    x = rnd(2, 64, 24, 24).float().cuda()
+    w = (rnd(96, 64, 3, 3) * 0.1).float().cuda()
+    b = rnd(96).float().cuda()
+    go = to_nhwc(rnd(2, 96, 24, 24).float().cuda())
+    res = {}
+    for tc in (0, 1):
+        xg = to_nhwc(x).requires_grad_(True)
+        wg = w.clone().requires_grad_(True)
+        bg = b.clone().requires_grad_(True)
+        y = ops.conv2d(xg, wg.permute(0, 2, 3, 1).contiguous(), bg, pad=1, use_tc=(-1 if tc else 0))   # no activation: a TF32-vs-fp32 sign flip at the LeakyReLU kink would dominate the comparison
+        (y * go).sum().backward()
+        res[tc] = (y.detach(), xg.grad, wg.grad, bg.grad)
+    for a, bb in zip(res[1], res[0]):
+        assert grad_err(a, bb) < TOL_TF32
+
+
+def test_not_eligible_is_reported():
+    from fsv import ops, _lib
+    d = ops._conv_desc(1, 8, 8, 3, 32, 3, 3, 1, 1)
+    assert _lib.lib.fsv_conv2d_tc_eligible(d) == 0
+    with pytest.raises(Exception):
+        ops.conv2d(torch.zeros(1, 8, 8, 3, device='cuda'), torch.zeros(32, 3, 3, 3, device='cuda'), None, pad=1, use_tc=1)
