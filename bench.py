@@ -172,7 +172,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 32)   # more threads than this slows the small per-layer CPU convs down
     sample_batch = 1
     t = cpu_step_time(args.workload, sample_batch, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     v = sample_batch / t
@@ -262,13 +262,21 @@ def run_fsv(args):
     if rank == 0:
         real_call = ops._call
         pending = []
+        detail = {}
+        from fsv._lib import lib
 
         def prof_call(fn, *a):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             real_call(fn, *a)
             e.record()
-            pending.append((fn.__name__, a, s, e))
+            key = fn.__name__
+            if key.startswith('fsv_conv2d') and key != 'fsv_conv2d_tc_eligible':
+                cd = a[0]._obj
+                key += ' %dx%d %d->%d k%d s%d up%d%s%s' % (cd.H, cd.W, cd.Cin, cd.Cout, cd.kh, cd.stride, cd.up,
+                                                          ' persample' if cd.w_nstride else '', ' TC' if (cd.use_tc != 0 and lib.fsv_conv2d_tc_eligible(a[0])) else '')
+            detail.setdefault(key, [0.0, 0])
+            pending.append((fn.__name__, a, s, e, key))
         ops._call = prof_call
         psteps = 2
         for _ in range(psteps):
@@ -276,10 +284,12 @@ def run_fsv(args):
         torch.cuda.synchronize()
         ops._call = real_call
         spade_bytes = 0.0
-        for name, a, s, e in pending:
+        for name, a, s, e, key in pending:
             d = prof.setdefault(name, [0.0, 0])
             d[0] += s.elapsed_time(e) / psteps
             d[1] += 1.0 / psteps
+            detail[key][0] += s.elapsed_time(e) / psteps
+            detail[key][1] += 1.0 / psteps
             if name == 'fsv_spade_fwd':
                 sd = a[0]._obj
                 px = sd.N * sd.H * sd.W
@@ -289,6 +299,10 @@ def run_fsv(args):
 
     if rank != 0:
         return
+    if args.breakdown:
+        with open(args.breakdown, 'w') as f:
+            for k, v in sorted(detail.items(), key=lambda kv: -kv[1][0]):
+                f.write('%9.3f ms  x%-5.1f %s\n' % (v[0], v[1], k))
     peaks = load_peaks()
     t_step = ms / args.steps / 1e3
     gbatch = batch * world
@@ -320,7 +334,7 @@ def run_fsv(args):
             'roofline': roof, 'roofline_spade': roof_spade,
             'kernel_ms_per_step': {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = min(os.cpu_count() or 1, 32)
         t_cpu = cpu_step_time(args.workload, 1, threads)
         line['cpu_baseline'] = {'value': 1.0 / t_cpu, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                                 'sample': 'CPU oracle (torch-CPU port of the reference), one D-step+G-step fwd/bwd at batch 1, no optimiser'}
@@ -337,6 +351,7 @@ def main():
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the workload\'s)')
     ap.add_argument('--simt', action='store_true', help='force the exact-fp32 SIMT conv path')
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    ap.add_argument('--breakdown', default=None, help='write a per-kernel/per-shape time breakdown of one step to this file')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

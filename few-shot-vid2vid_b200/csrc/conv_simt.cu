@@ -364,7 +364,7 @@ extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const fl
         }
         int co_tiles = fsv_cdiv(d->Cout, BM), ci_tiles = fsv_cdiv(d->Cin, BN);
         long long base = (long long)co_tiles * ci_tiles * taps;
-        long long want = ((long long)fsv_sm_count() * 4 + base - 1) / base;       // ~4 CTAs per SM
+        long long want = ((long long)fsv_sm_count() * 16 + base - 1) / base;      // ~16 CTAs per SM (short K loops: latency-bound otherwise)
         long long per_sample = (want + d->N - 1) / d->N;
         if (per_sample < 1) per_sample = 1;
         long long max_per_sample = (MP + 63) / 64;

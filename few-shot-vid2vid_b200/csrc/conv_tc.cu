@@ -42,6 +42,7 @@ struct __align__(64) TcParams {
     int y_ld, y_coff, res_ld, res_coff, act;
     float out_scale;
     int BN;
+    int OH, OW, os, oph, opw;   // output buffer dims and pixel stride/offset: pixel (ho,wo) of the GEMM lands at (ho*os+oph, wo*os+opw)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
         const int tn = r2 / p.TH;
         const int n = n0 + tn, ho = h0 + th, wo = w0 + tw;
         const bool valid = (n < p.N) && (ho < p.Ho) && (wo < p.Wo);
-        const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
+        const long long pix = ((long long)n * p.OH + (ho * p.os + p.oph)) * p.OW + (wo * p.os + p.opw);
         float* yrow = y + pix * p.y_ld + p.y_coff + co0;
         const float* rrow = residual ? residual + pix * p.res_ld + p.res_coff + co0 : nullptr;
         for (int c = 0; c < BN; c += 32) {
@@ -302,6 +303,40 @@ static int encode_act_map(CUtensorMap* m, const float* base, int C, int ld, int 
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+static void pick_tile(int Ho, int Wo, int& TW, int& TH, int& TN) {
+    TW = 16; TH = 8; TN = 1;
+    if (Wo < 16) {
+        TW = 1; while (TW * 2 <= Wo && TW < 16) TW *= 2;
+        int rem = 128 / TW;
+        TH = 1; while (TH * 2 <= Ho && TH * 2 <= rem) TH *= 2;
+        TN = rem / TH;
+    }
+}
+
+static int encode_weight_map(CUtensorMap* m, const float* w, long long kdim, int rows, int BN) {
+    cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kdim * 4};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int launch_tc(TcParams& p, int tiles_n, const float* bias, const float* residual, float* y, cudaStream_t st, const char* who) {
+    const int smem_bytes = TC_STAGES * (TC_A_BYTES + p.BN * TC_BK * 4) + (2 * TC_STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        FSV_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, p.Cout / p.BN);
+    k_conv_tc<<<grid, 192, smem_bytes, st>>>(p, bias, residual, y);
+    FSV_CHECK_LAUNCH(who);
+    return FSV_OK;
+}
+
 extern "C" int fsv_conv2d_fwd_tc(const fsv_conv_desc* d, const float* x, const float* w, const float* bias,
                                  const float* residual, float* y, void* stream) {
     FSV_REQUIRE(d != nullptr, "conv2d_fwd_tc: null descriptor");
@@ -313,18 +348,13 @@ extern "C" int fsv_conv2d_fwd_tc(const fsv_conv_desc* d, const float* x, const f
     TcParams p;
     memset(&p, 0, sizeof(p));
     const int BN = pick_bn(d->Cout);
-    // M-tile shape: 128 = TN * TH * TW
-    int TW = 16, TH = 8, TN = 1;
-    if (d->Wo < 16) {
-        TW = 1; while (TW * 2 <= d->Wo && TW < 16) TW *= 2;
-        int rem = 128 / TW;
-        TH = 1; while (TH * 2 <= d->Ho && TH * 2 <= rem) TH *= 2;
-        TN = rem / TH;
-    }
+    int TW, TH, TN;
+    pick_tile(d->Ho, d->Wo, TW, TH, TN);
     p.TW = TW; p.TH = TH; p.TN = TN;
     p.tiles_w = fsv_cdiv(d->Wo, TW); p.tiles_h = fsv_cdiv(d->Ho, TH);
     const int tiles_n = fsv_cdiv(d->N, TN);
     p.ntaps = d->kh * d->kw; p.Cin = d->Cin; p.Cout = d->Cout; p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
+    p.OH = d->Ho; p.OW = d->Wo; p.os = 1; p.oph = 0; p.opw = 0;
     p.y_ld = d->y_ld; p.y_coff = d->y_coff; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.act = d->act; p.out_scale = d->out_scale;
     p.BN = BN;
     const long long ld = d->x_ld;
@@ -355,24 +385,76 @@ extern "C" int fsv_conv2d_fwd_tc(const fsv_conv_desc* d, const float* x, const f
                 t.map = ph * 2 + pw; t.dh = (qh - ph) / 2; t.dw = (qw - pw) / 2; t.wk = r * d->kw + s;
             }
     }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)p.ntaps * d->Cin, (cuuint64_t)d->Cout};
-        cuuint64_t strides[1] = {(cuuint64_t)p.ntaps * d->Cin * 4};
-        cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = get_encode()(&p.bmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        FSV_REQUIRE(r == CUDA_SUCCESS, "conv2d_fwd_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    rc = encode_weight_map(&p.bmap, w, (long long)p.ntaps * d->Cin, d->Cout, BN);
+    FSV_REQUIRE(rc == 0, "conv2d_fwd_tc: cuTensorMapEncodeTiled(B) failed with %d", rc);
+    return launch_tc(p, tiles_n, bias, residual, y, (cudaStream_t)stream, "conv2d_fwd_tc");
+}
+
+// ------------------------------------------------------------------ data gradient on the same kernel
+// dx[n,h,w,ci] = sum_{r,s,co} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,co] * w[co][r][s][ci]  (where divisible and in range).
+// GEMM operands: A = dy (NHWC, K = Cout), B = wt[ci][r][s][co] (the OHWI weight with its channel axes swapped).
+//   stride 1: one launch, tap (r,s) reads dy at (+pad-r, +pad-s).
+//   stride 2: four launches, one per output parity (h%2, w%2); each uses the taps with r = (h+pad) mod 2 (same for s)
+//             and writes its quarter of dx through the strided-output epilogue.
+extern "C" int fsv_conv2d_dgrad_tc_eligible(const fsv_conv_desc* d) {
+    if (!d) return 0;
+    if (d->up != 1 || d->w_nstride != 0) return 0;
+    if (d->Cout % TC_BK != 0 || d->y_coff % 4 != 0 || d->y_ld % 4 != 0) return 0;
+    if (pick_bn(d->Cin) == 0 || d->x_ld % 4 != 0 || d->x_coff % 4 != 0) return 0;
+    if (d->kh * d->kw > TC_MAX_TAPS) return 0;
+    if (d->stride != 1 && d->stride != 2) return 0;
+    if ((long long)d->H * d->W * d->N < 256) return 0;
+    return get_encode() != nullptr ? 1 : 0;
+}
+
+extern "C" int fsv_conv2d_dgrad_tc(const fsv_conv_desc* d, const float* dy, const float* wt, float* dx, void* stream) {
+    FSV_REQUIRE(d != nullptr, "conv2d_dgrad_tc: null descriptor");
+    if (!fsv_conv2d_dgrad_tc_eligible(d)) {
+        fsv_set_error("conv2d_dgrad_tc: shape not eligible for the tcgen05 path");
+        return FSV_ENOTSUP;
     }
-    const int smem_bytes = TC_STAGES * (TC_A_BYTES + BN * TC_BK * 4) + (2 * TC_STAGES + 1) * 8 + 16 + 1024;
-    static int configured = 0;
-    if (configured < smem_bytes) {
-        FSV_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
+    FSV_REQUIRE((((uintptr_t)dy) & 15) == 0 && (((uintptr_t)wt) & 15) == 0 && (((uintptr_t)dx) & 15) == 0, "conv2d_dgrad_tc: pointers must be 16-byte aligned");
+    const int BN = pick_bn(d->Cin);
+    const int taps_all = d->kh * d->kw;
+    const long long ld = d->y_ld;
+    const float* dyb = dy + d->y_coff;
+    const int nclass = d->stride == 1 ? 1 : 4;
+    for (int cls = 0; cls < nclass; ++cls) {
+        const int ph = d->stride == 1 ? 0 : cls / 2, pw = d->stride == 1 ? 0 : cls % 2;
+        const int OHc = d->stride == 1 ? d->H : (d->H - ph + 1) / 2;     // output rows of this parity class
+        const int OWc = d->stride == 1 ? d->W : (d->W - pw + 1) / 2;
+        if (OHc <= 0 || OWc <= 0) continue;
+        TcParams p;
+        memset(&p, 0, sizeof(p));
+        int TW, TH, TN;
+        pick_tile(OHc, OWc, TW, TH, TN);
+        p.TW = TW; p.TH = TH; p.TN = TN;
+        p.tiles_w = fsv_cdiv(OWc, TW); p.tiles_h = fsv_cdiv(OHc, TH);
+        const int tiles_n = fsv_cdiv(d->N, TN);
+        p.Cin = d->Cout; p.Cout = d->Cin; p.N = d->N; p.Ho = OHc; p.Wo = OWc;
+        p.OH = d->H; p.OW = d->W; p.os = d->stride; p.oph = ph; p.opw = pw;
+        p.y_ld = d->x_ld; p.y_coff = d->x_coff; p.res_ld = d->x_ld; p.res_coff = 0; p.act = FSV_ACT_NONE; p.out_scale = 1.f;
+        p.BN = BN;
+        int nt = 0;
+        for (int r = 0; r < d->kh; ++r)
+            for (int s = 0; s < d->kw; ++s) {
+                int th = ph + d->pad - r, tw = pw + d->pad - s;
+                if (d->stride == 2 && ((th & 1) || (tw & 1))) continue;
+                TcTap& t = p.taps[nt++];
+                t.map = 0; t.wk = r * d->kw + s;
+                t.dh = d->stride == 1 ? th : th / 2;       // th is even here for stride 2 (may be negative: exact division)
+                t.dw = d->stride == 1 ? tw : tw / 2;
+            }
+        p.ntaps = nt;
+        if (nt == 0) {   // no tap reaches this parity class (e.g. 1x1 stride-2): its outputs are zero
+            FSV_REQUIRE(false, "conv2d_dgrad_tc: kernel %dx%d stride %d leaves a parity class without taps", d->kh, d->kw, d->stride);
+        }
+        int rc = encode_act_map(&p.amap[0], dyb, d->Cout, d->y_ld, d->Wo, d->Ho, d->N, ld, ld * d->Wo, ld * d->Wo * d->Ho, TW, TH, TN);
+        FSV_REQUIRE(rc == 0, "conv2d_dgrad_tc: cuTensorMapEncodeTiled(A) failed with %d", rc);
+        rc = encode_weight_map(&p.bmap, wt, (long long)taps_all * d->Cout, d->Cin, BN);
+        FSV_REQUIRE(rc == 0, "conv2d_dgrad_tc: cuTensorMapEncodeTiled(B) failed with %d", rc);
+        rc = launch_tc(p, tiles_n, nullptr, nullptr, dx, (cudaStream_t)stream, "conv2d_dgrad_tc");
+        if (rc) return rc;
     }
-    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->Cout / BN);
-    k_conv_tc<<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(p, bias, residual, y);
-    FSV_CHECK_LAUNCH("conv2d_fwd_tc");
     return FSV_OK;
 }

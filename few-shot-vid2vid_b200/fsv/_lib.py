@@ -50,6 +50,8 @@ SIGNATURES = {
     'fsv_conv2d_dgrad': [_CD, c_vp, c_vp, c_vp, c_int, c_vp],
     'fsv_conv2d_wgrad': [_CD, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
     'fsv_conv2d_tc_eligible': [_CD],
+    'fsv_conv2d_dgrad_tc_eligible': [_CD],
+    'fsv_conv2d_dgrad_tc': [_CD, c_vp, c_vp, c_vp, c_vp],
     'fsv_norm_stats': [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'fsv_norm_finalize': [c_vp, c_vp, c_int, c_int, c_double, c_double, c_float, c_float, c_vp, c_vp, c_int, c_vp, c_vp, c_vp],
     'fsv_norm_from_running': [c_vp, c_vp, c_int, c_float, c_vp, c_vp, c_vp],

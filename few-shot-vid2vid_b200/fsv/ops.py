@@ -249,7 +249,18 @@ class Conv2dFn(torch.autograd.Function):
                        up, cfg.get('act', ACT_NONE), cfg.get('out_scale', 1.0), cfg.get('w_nstride', 0), cfg.get('b_nstride', 0),
                        cfg.get('use_tc'), cfg.get('in_act', ACT_NONE))
         y = torch.empty((n, d.Ho, d.Wo, d.Cout), device=x.device, dtype=torch.float32)
-        _call(lib.fsv_conv2d_fwd, ctypes.byref(d), ptr(x), _off(wbase, cfg.get('w_off', 0)),
+        xin, dcall = x, d
+        if up == 2 and d.use_tc != 0:
+            # the tcgen05 path reads dense TMA boxes: materialise the nearest upsample once (HBM-cheap next to the
+            # 9-tap conv it feeds) when that makes the layer tensor-core eligible; the weight gradient still reads x
+            # through the fused upsample-on-load, so only x (not its 4x copy) is kept for backward.
+            du = ConvDesc.from_buffer_copy(d)
+            du.up = 1
+            if lib.fsv_conv2d_tc_eligible(ctypes.byref(du)):
+                xin = torch.empty((n, d.H, d.W, cin), device=x.device, dtype=torch.float32)
+                _call(lib.fsv_upsample2x_fwd, ptr(x), ptr(xin), n, hs, ws, cin, stream())
+                dcall = du
+        _call(lib.fsv_conv2d_fwd, ctypes.byref(dcall), ptr(xin), _off(wbase, cfg.get('w_off', 0)),
               None if bbase is None else _off(bbase, cfg.get('b_off', 0)), ptr(residual), ptr(y), stream())
         ctx.cfg, ctx.d = cfg, d
         ctx.has_b, ctx.has_r = bbase is not None, residual is not None
@@ -272,10 +283,20 @@ class Conv2dFn(torch.autograd.Function):
             g = dy
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
-            dd = ConvDesc.from_buffer_copy(d)
-            dd.up = 1
             dfull = torch.empty((d.N, d.H, d.W, d.Cin), device=dy.device, dtype=torch.float32)
-            _call(lib.fsv_conv2d_dgrad, ctypes.byref(dd), ptr(g), _off(wbase, cfg.get('w_off', 0)), ptr(dfull), 0, st)
+            done = False
+            if d.use_tc != 0 and cfg.get('w_off', 0) == 0:
+                dd = ConvDesc.from_buffer_copy(d)
+                dd.up = 1
+                if lib.fsv_conv2d_dgrad_tc_eligible(ctypes.byref(dd)):
+                    # tcgen05 data gradient: the kernel wants the weight with its channel axes swapped, wt[ci][r][s][co]
+                    wt = wbase.reshape(d.Cout, d.kh, d.kw, d.Cin).permute(3, 1, 2, 0).contiguous()
+                    _call(lib.fsv_conv2d_dgrad_tc, ctypes.byref(dd), ptr(g), ptr(wt), ptr(dfull), st)
+                    done = True
+            if not done:
+                dd = ConvDesc.from_buffer_copy(d)
+                dd.up = 1
+                _call(lib.fsv_conv2d_dgrad, ctypes.byref(dd), ptr(g), _off(wbase, cfg.get('w_off', 0)), ptr(dfull), 0, st)
             if d.up == 2:
                 dx = torch.empty_like(x)
                 _call(lib.fsv_upsample2x_bwd, ptr(dfull), ptr(dx), d.N, d.H // 2, d.W // 2, d.Cin, st)

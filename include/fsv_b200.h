@@ -100,6 +100,11 @@ int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const float* dy, fl
                      int accumulate, void* stream);
 /* 1 if the tcgen05/TMA implicit-GEMM path can serve this descriptor (fwd) */
 int fsv_conv2d_tc_eligible(const fsv_conv_desc* d);
+/* Data gradient on the tcgen05/TMA kernel.  wt is the weight with its channel axes swapped: wt[ci][r][s][co]
+ * (Cin, kh, kw, Cout).  Stride 1: one launch; stride 2: one launch per output parity class with a strided-output
+ * epilogue.  dx is fully overwritten.  FSV_ENOTSUP when fsv_conv2d_dgrad_tc_eligible() is 0. */
+int fsv_conv2d_dgrad_tc_eligible(const fsv_conv_desc* d);
+int fsv_conv2d_dgrad_tc(const fsv_conv_desc* d, const float* dy, const float* wt, float* dx, void* stream);
 
 /* ------------------------------------------------------------------ normalisation */
 /* per-(group, channel) sum and sum of squares of an NHWC slice; groups = 1 (batch) or N (instance).

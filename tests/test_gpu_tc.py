@@ -87,3 +87,34 @@ def test_not_eligible_is_reported():
     assert _lib.lib.fsv_conv2d_tc_eligible(d) == 0
     with pytest.raises(Exception):
         ops.conv2d(torch.zeros(1, 8, 8, 3, device='cuda'), torch.zeros(32, 3, 3, 3, device='cuda'), None, pad=1, use_tc=1)
+
+
+DGRAD_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad
+    (2, 32, 32, 32, 64, 3, 2, 1),
+    (2, 17, 17, 32, 64, 4, 2, 2),
+    (1, 33, 29, 64, 32, 3, 1, 1),
+    (2, 18, 18, 64, 32, 4, 1, 2),
+    (2, 31, 31, 32, 32, 4, 2, 2),
+    (2, 16, 16, 128, 256, 3, 2, 1),
+    (2, 16, 16, 64, 64, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize('case', DGRAD_CASES)
+def test_conv_tc_dgrad(case):
+    """tcgen05 data gradient (stride 1: one launch; stride 2: four parity launches with strided output) vs float64."""
+    from fsv import ops, _lib
+    N, H, W, Cin, Cout, k, stride, pad = case
+    x = rnd(N, Cin, H, W).requires_grad_(True)
+    w = rnd(Cout, Cin, k, k, scale=0.1)
+    y = F.conv2d(x, w, None, stride=stride, padding=pad)
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    d = ops._conv_desc(N, H, W, Cin, Cout, k, k, stride, pad)
+    assert _lib.lib.fsv_conv2d_dgrad_tc_eligible(d) == 1
+    xg = to_nhwc(x.detach().float().cuda()).requires_grad_(True)
+    wg = w.float().cuda().permute(0, 2, 3, 1).contiguous()
+    yg = ops.conv2d(xg, wg, None, stride=stride, pad=pad, use_tc=-1)
+    (yg * to_nhwc(go.float().cuda())).sum().backward()
+    assert grad_err(xg.grad.permute(0, 3, 1, 2), x.grad) < TOL_TF32
