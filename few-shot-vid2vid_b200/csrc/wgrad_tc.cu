@@ -1,0 +1,308 @@
+// tcgen05 / TMA weight gradient of the convolutions (TF32 operands, fp32 accumulation in TMEM, split-K with
+// fp32 reductions into dW).  sm_100a only.
+//
+//   dW[co][r][s][ci] = sum over pixels  dy[px][co] * x[px shifted by (r,s)][ci]
+//
+// is, per tap, a GEMM whose reduction dimension is the PIXEL index.  tcgen05.mma wants both operands K-major
+// in shared memory (K = pixels contiguous), while the activations live in HBM as NHWC (channels contiguous).
+// So the operands are first re-laid out by a tiled transpose kernel into planar "channel-major" buffers
+//   T[plane][n][c][h][w]   (row pitch padded to 16 bytes)
+// -- dy as one plane; x as one plane PER KERNEL COLUMN s (and per row parity for stride 2):
+//   X[s][ph][n][c][hq][wo] = x[n][hq*stride+ph][wo*stride + s - pad][c]   (0 outside the image; optionally read
+//   through the nearest x2 upsample the conv reads x with)
+// The column shift has to be baked into the copy because a TMA box must start on a 16-byte boundary of the
+// innermost dimension -- a one-pixel (4-byte) shift along W is not addressable -- while row shifts are free (outer
+// coordinate, out-of-bounds rows zero-filled by TMA == the conv's zero padding).  With that, x and dy share the
+// same (wo) column grid and every tap is a dense, aligned box.  The copies are pure HBM streaming.
+//
+// GEMM tile: M = 128 channels of the wider operand, N = up to 128 channels of the narrower one, K block = 32
+// pixels (a PW x PH x PN box, PW*PH*PN = 32, 128-byte K rows, SWIZZLE_128B).  grid = (split-K chunks, taps,
+// M-tiles x N-tiles).  Warp roles and the smem ring are those of conv_tc.cu; the epilogue adds the tile into
+// dW with fp32 atomics (red.global.add.f32).
+#include "tc_common.cuh"
+
+#define WG_STAGES 4
+#define WG_MAX_TAPS 16
+
+struct WgTap { int plane, dh, dw; };
+
+struct __align__(64) WgParams {
+    CUtensorMap dymap;          // planar dy: dims (Wo, Ho, Cout, N)
+    CUtensorMap xmap[8];        // planar x planes (kernel column s, row parity ph): dims (Wo, Hq, Cin, N)
+    WgTap taps[WG_MAX_TAPS];
+    int ntaps, Cin, Cout, N, Ho, Wo;
+    int PW, PH, PN, nWB, nHB, nNB;     // K-block pixel box and block counts
+    int role;                   // 0: M = Cout (A from dy, B from x)   1: M = Cin (A from x, B from dy)
+    int BN, mtiles, ntiles;
+    int kb_per_split;
+};
+
+__global__ void __launch_bounds__(192, 1) k_wgrad_tc(const __grid_constant__ WgParams p, float* __restrict__ dw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BN = p.BN;
+    const int stage_bytes = TC_A_BYTES + BN * TC_BK * 4;
+    uint64_t* bars = (uint64_t*)(smem + WG_STAGES * stage_bytes);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WG_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int tap_i = blockIdx.y;
+    const WgTap tap = p.taps[tap_i];
+    const int mt = blockIdx.z / p.ntiles, nt = blockIdx.z - mt * p.ntiles;
+    const int m0 = mt * TC_BM, n0 = nt * BN;
+    const int KB = p.nWB * p.nHB * p.nNB;
+    const int kb0 = blockIdx.x * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, KB);
+    const int num_k = kb1 - kb0;
+    if (num_k <= 0) return;        // uniform for the whole CTA
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[WG_STAGES + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * WG_STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const CUtensorMap* amap = p.role == 0 ? &p.dymap : &p.xmap[tap.plane];
+            const CUtensorMap* bmap = p.role == 0 ? &p.xmap[tap.plane] : &p.dymap;
+            const int a_dh = p.role == 0 ? 0 : tap.dh, a_dw = p.role == 0 ? 0 : tap.dw;
+            const int b_dh = p.role == 0 ? tap.dh : 0, b_dw = p.role == 0 ? tap.dw : 0;
+            for (int i = 0; i < num_k; ++i) {
+                const int s = i % WG_STAGES;
+                const uint32_t ph = (i / WG_STAGES) & 1;
+                mbar_wait(smem_u32(&bars[WG_STAGES + s]), ph ^ 1);
+                int kb = kb0 + i;
+                const int wb = kb % p.nWB; kb /= p.nWB;
+                const int hb = kb % p.nHB; kb /= p.nHB;
+                const int w0 = wb * p.PW, h0 = hb * p.PH, nn0 = kb * p.PN;
+                const uint32_t full = smem_u32(&bars[s]);
+                const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
+                mbar_expect_tx(full, (uint32_t)stage_bytes);
+                tma_load_4d(a_dst, amap, full, w0 + a_dw, h0 + a_dh, m0, nn0);
+                tma_load_4d(a_dst + TC_A_BYTES, bmap, full, w0 + b_dw, h0 + b_dh, n0, nn0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+            for (int i = 0; i < num_k; ++i) {
+                const int s = i % WG_STAGES;
+                const uint32_t ph = (i / WG_STAGES) & 1;
+                mbar_wait(smem_u32(&bars[s]), ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)
+                    tc_mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
+                tc_commit(smem_u32(&bars[WG_STAGES + s]));
+            }
+            tc_commit(smem_u32(&bars[2 * WG_STAGES]));
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        mbar_wait(smem_u32(&bars[2 * WG_STAGES]), 0);
+        tc_fence_after();
+        const int Mdim = p.role == 0 ? p.Cout : p.Cin;
+        const int Ndim = p.role == 0 ? p.Cin : p.Cout;
+        const int m = m0 + row;
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (m < Mdim) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c + j;
+                    if (c + j < BN && n < Ndim) {
+                        const int co = p.role == 0 ? m : n, ci = p.role == 0 ? n : m;
+                        atomicAdd(dw + ((long long)co * p.ntaps + tap_i) * p.Cin + ci, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------ NHWC -> planar (channel-major) transpose
+// dst[plane][n][c][hq][w] (row pitch `pitch`) <- src (N, Hs, Ws, C) NHWC slice (ld, coff), seen through an optional
+// nearest x2 upsample (up) as an (H, W) = (Hs*up, Ws*up) image:
+//   plane = s * nph + ph ;  row = hq * rstride + ph ;  col = w * cstride + s - pad     (zero outside the image)
+// dy uses nph = 1, rstride = cstride = 1, s = pad = 0.
+__global__ void k_to_planar(const float* __restrict__ src, float* __restrict__ dst, int N, int Hs, int Ws, int C, int ld, int coff,
+                            int up, int nph, int rstride, int cstride, int pad, int Hq, int Wq, int pitch) {
+    __shared__ float tile[32][33];
+    const int w0 = blockIdx.x * 32, c0 = blockIdx.z * 32;
+    int y = blockIdx.y;                       // (plane * N + n) * Hq + hq
+    const int hq = y % Hq; y /= Hq;
+    const int n = y % N;
+    const int plane = y / N;
+    const int s = plane / nph, ph = plane - s * nph;
+    const int H = Hs * up, W = Ws * up;
+    const int row = hq * rstride + ph;
+    for (int i = threadIdx.y; i < 32; i += 8) {       // i = pixel within the tile, threadIdx.x = channel
+        int w = w0 + i, c = c0 + threadIdx.x;
+        int col = w * cstride + s - pad;
+        float v = 0.f;
+        if (row < H && w < Wq && col >= 0 && col < W && c < C)
+            v = src[(((long long)n * Hs + row / up) * Ws + col / up) * ld + coff + c];
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {       // i = channel within the tile, threadIdx.x = pixel
+        int c = c0 + i, w = w0 + threadIdx.x;
+        if (c < C && w < pitch)
+            dst[((((long long)plane * N + n) * C + c) * Hq + hq) * pitch + w] = tile[threadIdx.x][i];
+    }
+}
+
+static int launch_to_planar(const float* src, float* dst, int N, int Hs, int Ws, int C, int ld, int coff, int up, int nph, int rstride,
+                            int cstride, int pad, int Hq, int Wq, int pitch, int planes, cudaStream_t st) {
+    dim3 grid(fsv_cdiv(pitch, 32), planes * N * Hq, fsv_cdiv(C, 32));
+    FSV_REQUIRE((long long)planes * N * Hq <= 2147483647LL && grid.z <= 65535, "to_planar: grid too large");
+    k_to_planar<<<grid, dim3(32, 8), 0, st>>>(src, dst, N, Hs, Ws, C, ld, coff, up, nph, rstride, cstride, pad, Hq, Wq, pitch);
+    FSV_CHECK_LAUNCH("to_planar");
+    return FSV_OK;
+}
+
+// ------------------------------------------------------------------ host side
+static int wg_bn(int nsmall) {
+    if (nsmall >= 128) return 128;
+    if (nsmall % 16 == 0) return nsmall;
+    return 0;
+}
+static inline int pitch4(int w) { return (w + 3) & ~3; }
+
+struct WgGeom { int Hq, nph, planes, pitch; long long x_floats, dy_floats; };
+static WgGeom wg_geom(const fsv_conv_desc* d) {
+    WgGeom g;
+    g.nph = d->stride == 2 ? 2 : 1;
+    g.Hq = d->stride == 2 ? (d->H + 1) / 2 : d->H;
+    g.planes = d->kw * g.nph;
+    g.pitch = pitch4(d->Wo);
+    g.x_floats = (long long)g.planes * d->N * d->Cin * g.Hq * g.pitch;
+    g.dy_floats = (long long)d->N * d->Cout * d->Ho * g.pitch;
+    return g;
+}
+
+extern "C" int fsv_conv2d_wgrad_tc_eligible(const fsv_conv_desc* d) {
+    if (!d) return 0;
+    if (d->w_nstride != 0 || d->in_act != FSV_ACT_NONE) return 0;
+    if (d->stride != 1 && d->stride != 2) return 0;
+    if (d->stride == 2 && d->up != 1) return 0;
+    if (d->kh * d->kw > WG_MAX_TAPS || d->kw > 4) return 0;
+    if (d->Cin % 16 != 0 || d->Cout % 16 != 0) return 0;
+    if (d->Cin < 32 && d->Cout < 32) return 0;
+    int nsmall = d->Cin < d->Cout ? d->Cin : d->Cout;
+    if (wg_bn(nsmall) == 0) return 0;
+    if (d->Wo < 32) return 0;                        // K rows are 32 pixels of one image row (128-byte TMA inner box)
+    if ((long long)d->N * d->Ho * d->Wo < 1024) return 0;
+    return fsv_get_encode_tiled() != nullptr ? 1 : 0;
+}
+
+extern "C" long long fsv_conv2d_wgrad_tc_workspace(const fsv_conv_desc* d) {
+    if (!fsv_conv2d_wgrad_tc_eligible(d)) return 0;
+    WgGeom g = wg_geom(d);
+    return (g.x_floats + g.dy_floats) * 4 + 256;
+}
+
+static int encode_planar(CUtensorMap* m, const float* base, int Wd, int Hd, int N, int C, int pitch, int Hq, int CB) {
+    // dims (W, H, C, N) in memory order; strides in bytes for H, C, N.  The K block is 32 pixels of one image row,
+    // so the box is (32, 1, CB, 1): CB channel rows of 128 contiguous bytes, starting on a 128-byte boundary.
+    cuuint64_t dims[4] = {(cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)C, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * Hq * 4, (cuuint64_t)pitch * Hq * C * 4};
+    cuuint32_t box[4] = {32, 1, (cuuint32_t)CB, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fsv_get_encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+extern "C" int fsv_conv2d_wgrad_tc(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, float* workspace,
+                                   int accumulate, void* stream) {
+    FSV_REQUIRE(d != nullptr && workspace != nullptr, "conv2d_wgrad_tc: null descriptor / workspace");
+    if (!fsv_conv2d_wgrad_tc_eligible(d)) {
+        fsv_set_error("conv2d_wgrad_tc: shape not eligible for the tcgen05 path");
+        return FSV_ENOTSUP;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    WgGeom g = wg_geom(d);
+    float* xT = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float* dyT = xT + g.x_floats;
+    const int taps = d->kh * d->kw;
+    if (!accumulate) FSV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * taps * d->Cin, st));
+    int rc = launch_to_planar(x, xT, d->N, d->H / d->up, d->W / d->up, d->Cin, d->x_ld, d->x_coff, d->up, g.nph, d->stride, d->stride,
+                              d->pad, g.Hq, d->Wo, g.pitch, g.planes, st);
+    if (rc) return rc;
+    rc = launch_to_planar(dy, dyT, d->N, d->Ho, d->Wo, d->Cout, d->y_ld, d->y_coff, 1, 1, 1, 1, 0, d->Ho, d->Wo, g.pitch, 1, st);
+    if (rc) return rc;
+
+    WgParams p;
+    memset(&p, 0, sizeof(p));
+    p.ntaps = taps; p.Cin = d->Cin; p.Cout = d->Cout; p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
+    p.PW = 32; p.PH = 1; p.PN = 1;
+    p.nWB = fsv_cdiv(d->Wo, p.PW); p.nHB = d->Ho; p.nNB = d->N;
+    p.role = d->Cout >= d->Cin ? 0 : 1;
+    const int Mdim = p.role == 0 ? d->Cout : d->Cin, Ndim = p.role == 0 ? d->Cin : d->Cout;
+    p.BN = wg_bn(Ndim);
+    p.mtiles = fsv_cdiv(Mdim, TC_BM); p.ntiles = fsv_cdiv(Ndim, p.BN);
+    const int dyCB = p.role == 0 ? TC_BM : p.BN, xCB = p.role == 0 ? p.BN : TC_BM;
+    rc = encode_planar(&p.dymap, dyT, d->Wo, d->Ho, d->N, d->Cout, g.pitch, d->Ho, dyCB);
+    FSV_REQUIRE(rc == 0, "conv2d_wgrad_tc: cuTensorMapEncodeTiled(dy) failed with %d", rc);
+    for (int pl = 0; pl < g.planes; ++pl) {
+        int ph = pl % g.nph;
+        int Hd = d->stride == 2 ? (d->H - ph + 1) / 2 : d->H;      // valid rows of this parity
+        if (Hd < 1) Hd = 1;
+        rc = encode_planar(&p.xmap[pl], xT + (long long)pl * d->N * d->Cin * g.Hq * g.pitch, d->Wo, Hd, d->N, d->Cin, g.pitch, g.Hq, xCB);
+        FSV_REQUIRE(rc == 0, "conv2d_wgrad_tc: cuTensorMapEncodeTiled(x plane %d) failed with %d", pl, rc);
+    }
+    for (int r = 0; r < d->kh; ++r)
+        for (int s2 = 0; s2 < d->kw; ++s2) {
+            WgTap& t = p.taps[r * d->kw + s2];
+            int qh = r - d->pad;
+            int ph = d->stride == 2 ? ((qh % 2) + 2) % 2 : 0;
+            t.plane = s2 * g.nph + ph;
+            t.dh = d->stride == 2 ? (qh - ph) / 2 : qh;
+            t.dw = 0;                                             // the column shift lives in the plane
+        }
+    const int KB = p.nWB * p.nHB * p.nNB;
+    const long long base = (long long)taps * p.mtiles * p.ntiles;
+    long long splits = ((long long)fsv_sm_count() * 3 + base - 1) / base;
+    if (splits > KB / 8) splits = KB / 8;             // at least 8 K blocks per CTA
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (int)((KB + splits - 1) / splits);
+    splits = (KB + p.kb_per_split - 1) / p.kb_per_split;
+    const int smem_bytes = WG_STAGES * (TC_A_BYTES + p.BN * TC_BK * 4) + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        FSV_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    dim3 grid((unsigned)splits, taps, p.mtiles * p.ntiles);
+    k_wgrad_tc<<<grid, 192, smem_bytes, st>>>(p, dw);
+    FSV_CHECK_LAUNCH("conv2d_wgrad_tc");
+    return FSV_OK;
+}

@@ -52,6 +52,9 @@ SIGNATURES = {
     'fsv_conv2d_tc_eligible': [_CD],
     'fsv_conv2d_dgrad_tc_eligible': [_CD],
     'fsv_conv2d_dgrad_tc': [_CD, c_vp, c_vp, c_vp, c_vp],
+    'fsv_conv2d_wgrad_tc_eligible': [_CD],
+    'fsv_conv2d_wgrad_tc_workspace': [_CD],
+    'fsv_conv2d_wgrad_tc': [_CD, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
     'fsv_norm_stats': [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'fsv_norm_finalize': [c_vp, c_vp, c_int, c_int, c_double, c_double, c_float, c_float, c_vp, c_vp, c_int, c_vp, c_vp, c_vp],
     'fsv_norm_from_running': [c_vp, c_vp, c_int, c_float, c_vp, c_vp, c_vp],
@@ -76,6 +79,7 @@ def _load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = c_int
+    lib.fsv_conv2d_wgrad_tc_workspace.restype = c_ll
     lib.fsv_last_error.argtypes = []
     lib.fsv_last_error.restype = ctypes.c_char_p
     return lib

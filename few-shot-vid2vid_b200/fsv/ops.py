@@ -311,8 +311,15 @@ class Conv2dFn(torch.autograd.Function):
             dw = torch.empty_like(wbase) if shared else torch.zeros_like(wbase)
             if need_b:
                 db = dw if ctx.same_base else torch.zeros(ctx.bshape, device=dy.device, dtype=torch.float32)
-            _call(lib.fsv_conv2d_wgrad, ctypes.byref(d), ptr(x), ptr(g), _off(dw, cfg.get('w_off', 0)) if need_w else None,
-                  _off(db, cfg.get('b_off', 0)) if need_b else None, 0 if shared else 1, st)
+            w_done = False
+            if need_w and shared and d.use_tc != 0 and lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(d)):
+                ws = torch.empty(int(lib.fsv_conv2d_wgrad_tc_workspace(ctypes.byref(d))) // 4 + 1, device=dy.device, dtype=torch.float32)
+                _call(lib.fsv_conv2d_wgrad_tc, ctypes.byref(d), ptr(x), ptr(g), ptr(dw), ptr(ws), 0, st)
+                w_done = True
+            if not w_done or need_b:
+                _call(lib.fsv_conv2d_wgrad, ctypes.byref(d), ptr(x), ptr(g),
+                      _off(dw, cfg.get('w_off', 0)) if (need_w and not w_done) else None,
+                      _off(db, cfg.get('b_off', 0)) if need_b else None, 0 if shared else 1, st)
             if ctx.same_base:
                 db = None          # the single flat gradient is returned through wbase
             if not need_w:

@@ -105,6 +105,13 @@ int fsv_conv2d_tc_eligible(const fsv_conv_desc* d);
  * epilogue.  dx is fully overwritten.  FSV_ENOTSUP when fsv_conv2d_dgrad_tc_eligible() is 0. */
 int fsv_conv2d_dgrad_tc_eligible(const fsv_conv_desc* d);
 int fsv_conv2d_dgrad_tc(const fsv_conv_desc* d, const float* dy, const float* wt, float* dx, void* stream);
+/* Weight gradient on tcgen05: dw[co][r][s][ci] (+= if accumulate) = sum_pixels dy * x.  The operands are first
+ * re-laid out into planar channel-major buffers inside `workspace` (fsv_conv2d_wgrad_tc_workspace() bytes, caller
+ * allocated) so that the pixel axis is the contiguous GEMM-K axis.  Bias gradients stay with fsv_conv2d_wgrad. */
+int fsv_conv2d_wgrad_tc_eligible(const fsv_conv_desc* d);
+long long fsv_conv2d_wgrad_tc_workspace(const fsv_conv_desc* d);
+int fsv_conv2d_wgrad_tc(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, float* workspace,
+                        int accumulate, void* stream);
 
 /* ------------------------------------------------------------------ normalisation */
 /* per-(group, channel) sum and sum of squares of an NHWC slice; groups = 1 (batch) or N (instance).

@@ -118,3 +118,38 @@ def test_conv_tc_dgrad(case):
     yg = ops.conv2d(xg, wg, None, stride=stride, pad=pad, use_tc=-1)
     (yg * to_nhwc(go.float().cuda())).sum().backward()
     assert grad_err(xg.grad.permute(0, 3, 1, 2), x.grad) < TOL_TF32
+
+
+WGRAD_CASES = [
+    # N, H, W (conv-input dims), Cin, Cout, k, stride, pad, up
+    (2, 32, 32, 32, 64, 3, 1, 1, 1),
+    (2, 64, 64, 64, 32, 3, 2, 1, 1),
+    (1, 64, 128, 32, 32, 4, 2, 2, 1),
+    (2, 32, 32, 128, 32, 3, 1, 1, 2),
+    (2, 40, 40, 32, 160, 3, 1, 1, 1),
+    (2, 32, 32, 64, 64, 1, 1, 0, 1),
+    (2, 65, 67, 32, 64, 4, 2, 2, 1),
+    (1, 34, 34, 256, 512, 4, 1, 2, 1),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_conv_tc_wgrad(case):
+    """tcgen05 weight gradient (planar re-layout + pixel-K GEMM + split-K fp32 reductions) vs float64."""
+    from fsv import ops, _lib
+    N, H, W, Cin, Cout, k, stride, pad, up = case
+    x = rnd(N, Cin, H // up, W // up)
+    w = rnd(Cout, Cin, k, k, scale=0.1).requires_grad_(True)
+    b = rnd(Cout).requires_grad_(True)
+    y = F.conv2d(O.up2(x) if up == 2 else x, w, b, stride=stride, padding=pad)
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    d = ops._conv_desc(N, H, W, Cin, Cout, k, k, stride, pad, up)
+    assert _lib.lib.fsv_conv2d_wgrad_tc_eligible(d) == 1
+    xg = to_nhwc(x.float().cuda())
+    wg = w.detach().float().cuda().requires_grad_(True)
+    bg = b.detach().float().cuda().requires_grad_(True)
+    yg = ops.conv2d(xg, wg.permute(0, 2, 3, 1).contiguous(), bg, stride=stride, pad=pad, up=up, use_tc=-1)
+    (yg * to_nhwc(go.float().cuda())).sum().backward()
+    assert grad_err(wg.grad, w.grad) < TOL_TF32
+    assert grad_err(bg.grad, b.grad) < 1e-4
