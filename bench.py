@@ -236,7 +236,7 @@ def run_fsv(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
         step(devin)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -246,6 +246,10 @@ def run_fsv(args):
     launches = (ops.LAUNCHES[0] - n0) // args.steps
     clk = clocks.stop() if rank == 0 else None
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({'quick': True, 'ms_per_step': ms / args.steps, 'note': 'profiling aid, not a bench value'}))
+        return
     # e2e: host inputs (pinned) -> device every step, losses read back to the host every step
     d2h = [0]
 
@@ -351,6 +355,7 @@ def main():
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the workload\'s)')
     ap.add_argument('--simt', action='store_true', help='force the exact-fp32 SIMT conv path')
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='profiling aid: W warm-up + K timed steps only (no e2e / instrumented / CPU passes); not a bench result')
     ap.add_argument('--breakdown', default=None, help='write a per-kernel/per-shape time breakdown of one step to this file')
     args = ap.parse_args()
     if args.impl == 'reference':
