@@ -343,6 +343,9 @@ __global__ void k_colsum(const float* __restrict__ dy, int ld, int coff, long lo
     }
 }
 
+extern "C" int fsv_conv2d_thin_kind(const fsv_conv_desc* d);
+extern "C" int fsv_conv2d_wgrad_thin(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, void* stream);
+
 extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                                 int accumulate, void* stream) {
     int rc = fsv_conv_validate(d, "conv2d_wgrad");
@@ -362,6 +365,12 @@ extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const fl
                 FSV_CUDA(cudaMemset2DAsync(dw, sizeof(float) * d->w_nstride, 0, sizeof(float) * wsize, d->N, st));
             }
         }
+        if (fsv_conv2d_thin_kind(d)) {
+            int trc = fsv_conv2d_wgrad_thin(d, x, dy, dw, stream);
+            if (trc) return trc;
+            goto bias_part;
+        }
+        {
         int co_tiles = fsv_cdiv(d->Cout, BM), ci_tiles = fsv_cdiv(d->Cin, BN);
         long long base = (long long)co_tiles * ci_tiles * taps;
         long long want = ((long long)fsv_sm_count() * 16 + base - 1) / base;      // ~16 CTAs per SM (short K loops: latency-bound otherwise)
@@ -376,7 +385,9 @@ extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const fl
         FSV_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv2d_wgrad: grid too large");
         k_conv_wgrad<<<grid, 256, 0, st>>>(p, x, dy, dw, ci_tiles, chunks_per_sample, pix_per_chunk);
         FSV_CHECK_LAUNCH("conv2d_wgrad");
+        }
     }
+bias_part:
     if (dbias) {
         int groups = d->b_nstride ? d->N : 1;
         long long rpg = d->b_nstride ? MP : (long long)d->N * MP;

@@ -55,6 +55,15 @@ CONV_CASES = [
     (2, 32, 32, 8, 8, 3, 1, 1, 1, 0, True, True),      # up_1.conv_1 of the tiny golden generator
     (2, 16, 16, 16, 16, 3, 1, 1, 1, 0, True, True),
     (2, 64, 64, 4, 4, 3, 1, 1, 1, 0, True, True),
+    # thin layers (dedicated streaming kernels, N*Ho*Wo >= 4096)
+    (2, 48, 48, 1, 32, 3, 1, 1, 1, 1, True, False),
+    (2, 64, 64, 5, 32, 3, 1, 1, 1, 1, True, False),
+    (2, 65, 63, 8, 32, 4, 2, 2, 1, 1, True, False),
+    (2, 48, 48, 3, 48, 3, 1, 1, 1, 0, True, True),
+    (1, 64, 64, 32, 3, 3, 1, 1, 1, 2, True, False),
+    (2, 48, 48, 32, 1, 3, 1, 1, 1, 3, True, False),
+    (4, 40, 40, 64, 2, 3, 1, 1, 1, 0, True, False),
+    (16, 18, 18, 512, 1, 4, 1, 2, 1, 0, True, False),
 ]
 
 
