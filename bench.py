@@ -195,6 +195,7 @@ def run_fsv(args):
     rank, world, local_rank = parallel.init_from_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    torch.cuda.set_stream(torch.cuda.Stream())      # everything (eager, capture, replay, timing events) on one non-default stream
     wl = WORKLOADS[args.workload]
     batch = wl['batch'] if args.batch is None else args.batch
     opt = make_opt(args.workload)
@@ -204,16 +205,29 @@ def run_fsv(args):
     netD = networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, opt.num_D, True, gpu_ids=[local_rank])
     netG.train(), netD.train()
     parallel.broadcast_state(netG), parallel.broadcast_state(netD)
-    optG, optD = trainer.make_optimizers(opt, netG, netD)
+    use_graph = args.graph and world == 1
+    optG, optD = trainer.make_optimizers(opt, netG, netD, capturable=use_graph)
     syncG = parallel.GradSync(netG.parameters()) if world > 1 else None
     syncD = parallel.GradSync(netD.parameters()) if world > 1 else None
     host = synth_inputs(args.workload, batch, seed=1234 + rank, pin=True)
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
-    def step(inp):
+    def eager_step(inp):
         return trainer.train_step(opt, netG, netD, optG, optD, inp['tgt_label'], inp['tgt_image'], inp['ref_labels'], inp['ref_images'],
                                   sync_G=syncG, sync_D=syncD)
+    step = eager_step
+    n_eager0 = ops.LAUNCHES[0]
+    eager_step(devin)
+    launches_per_step = ops.LAUNCHES[0] - n_eager0
+    graph_note = None
+    if use_graph:
+        try:
+            step = trainer.GraphedStep(opt, netG, netD, optG, optD, devin, sync_G=syncG, sync_D=syncD)
+        except Exception as e:      # capture is an optimisation of the launch path only; the eager path runs the same kernels
+            graph_note = 'capture failed, eager launches used: %s' % str(e)[:200]
+            use_graph = False
+            torch.cuda.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -243,7 +257,7 @@ def run_fsv(args):
         clocks.start()
     n0 = ops.LAUNCHES[0]
     ms = timed(lambda: step(devin), args.steps)
-    launches = (ops.LAUNCHES[0] - n0) // args.steps
+    launches = launches_per_step      # C-ABI kernel-launching calls per step (counted on an eager step; a graph replays the same launches)
     clk = clocks.stop() if rank == 0 else None
 
     if args.quick:
@@ -284,7 +298,7 @@ def run_fsv(args):
         ops._call = prof_call
         psteps = 2
         for _ in range(psteps):
-            step(devin)
+            eager_step(devin)
         torch.cuda.synchronize()
         ops._call = real_call
         spade_bytes = 0.0
@@ -331,7 +345,7 @@ def run_fsv(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'fp32' if ops.CONV_USE_TC == 0 else 'tf32', 'data': 'synthetic',
             'config': {'workload': '%s %dx%d --adaptive_spade --warp_ref --spade_combine --no_flow_gt --no_vgg_loss' % (args.workload, wl['H'], wl['W']),
-                       'per_gpu_batch': batch, 'global_batch': gbatch, 'parallelism': 'dp%d' % world,
+                       'per_gpu_batch': batch, 'global_batch': gbatch, 'parallelism': 'dp%d' % world, 'cuda_graph': bool(use_graph), 'cuda_graph_note': graph_note,
                        'l2': 'per-step working set (activations of a %d-frame batch) is far larger than the 126 MB L2' % batch},
             'clocks': clk, 'gpu_launches': int(launches),
             'e2e': {'value': gbatch / (ms_e2e / args.steps / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h[0]},
@@ -355,6 +369,8 @@ def main():
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the workload\'s)')
     ap.add_argument('--simt', action='store_true', help='force the exact-fp32 SIMT conv path')
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    ap.add_argument('--graph', dest='graph', action='store_true', default=True, help='replay the step from a CUDA graph (default, single GPU)')
+    ap.add_argument('--no-graph', dest='graph', action='store_false')
     ap.add_argument('--quick', action='store_true', help='profiling aid: W warm-up + K timed steps only (no e2e / instrumented / CPU passes); not a bench result')
     ap.add_argument('--breakdown', default=None, help='write a per-kernel/per-shape time breakdown of one step to this file')
     args = ap.parse_args()

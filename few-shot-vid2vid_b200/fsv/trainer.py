@@ -88,14 +88,47 @@ def generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_imag
     return losses, fake
 
 
-def make_optimizers(opt, netG, netD):
-    """base_model.py:39-48 Adam with TTUR."""
+def make_optimizers(opt, netG, netD, capturable=False):
+    """base_model.py:39-48 Adam with TTUR.  ``capturable`` keeps the step counters on the device so the whole
+    iteration can be recorded into a CUDA graph (same arithmetic)."""
     if opt.no_TTUR:
         beta1, beta2, g_lr, d_lr = opt.beta1, 0.999, opt.lr, opt.lr
     else:
         beta1, beta2, g_lr, d_lr = 0.0, opt.beta2, opt.lr / 2, opt.lr * 2
-    return (torch.optim.Adam(netG.parameters(), lr=g_lr, betas=(beta1, beta2)),
-            torch.optim.Adam(netD.parameters(), lr=d_lr, betas=(beta1, beta2)))
+    return (torch.optim.Adam(netG.parameters(), lr=g_lr, betas=(beta1, beta2), capturable=capturable),
+            torch.optim.Adam(netD.parameters(), lr=d_lr, betas=(beta1, beta2), capturable=capturable))
+
+
+class GraphedStep:
+    """The whole training iteration (train.py:58-62: D-step + G-step incl. both Adam updates) recorded once into a
+    CUDA graph and replayed: ~5000 kernel launches (ours + the parameter-side torch ops) become one graph launch,
+    which removes the host-side launch latency between the many small kernels.  Inputs are copied into static
+    buffers before each replay; the returned losses are static tensors overwritten by each replay."""
+
+    def __init__(self, opt, netG, netD, optG, optD, example, sync_G=None, sync_D=None, warmup=3):
+        self.static = {k: v.clone() for k, v in example.items()}
+        st = self.static
+
+        def run():
+            return train_step(opt, netG, netD, optG, optD, st['tgt_label'], st['tgt_image'], st['ref_labels'], st['ref_images'],
+                              sync_G=sync_G, sync_D=sync_D)
+        # Capture on the stream the eager iterations already ran on (it must not be the legacy default stream): autograd's
+        # AccumulateGrad nodes remember the stream they were created on, and a cross-stream wait would invalidate capture.
+        cur = torch.cuda.current_stream()
+        if cur == torch.cuda.default_stream():
+            raise RuntimeError('GraphedStep: run the training loop under a non-default stream (torch.cuda.set_stream)')
+        for _ in range(warmup):
+            run()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=cur):
+            self.ld, self.lg, self.fake = run()
+
+    def __call__(self, inp):
+        for k, v in inp.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.ld, self.lg, self.fake
 
 
 def loss_backward(losses, optimizer, grad_sync=None):
