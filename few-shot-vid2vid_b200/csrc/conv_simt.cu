@@ -229,10 +229,14 @@ extern "C" int fsv_conv2d_fwd_simt(const fsv_conv_desc* d, const float* x, const
     return FSV_OK;
 }
 
+extern "C" int fsv_conv2d_dgrad_thin_ok(const fsv_conv_desc* d);
+extern "C" int fsv_conv2d_dgrad_thin(const fsv_conv_desc* d, const float* dy, const float* w, float* dx, int accumulate, void* stream);
+
 extern "C" int fsv_conv2d_dgrad(const fsv_conv_desc* d, const float* dy, const float* w, float* dx, int accumulate, void* stream) {
     int rc = fsv_conv_validate(d, "conv2d_dgrad");
     if (rc) return rc;
     FSV_REQUIRE(d->up == 1, "conv2d_dgrad: up must be 1 (take the gradient at conv-input resolution, then fsv_upsample2x_bwd)");
+    if (fsv_conv2d_dgrad_thin_ok(d) && (((uintptr_t)dy) & 15) == 0) return fsv_conv2d_dgrad_thin(d, dy, w, dx, accumulate, stream);
     ConvP p = make_p(d, accumulate);
     dim3 grid(fsv_cdiv((long long)d->H * d->W, BM), fsv_cdiv(d->Cin, BN), d->N);
     k_conv_simt<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p, dy, w, nullptr, nullptr, dx);

@@ -27,6 +27,7 @@ struct SpadeP {
     int N, H, W, C, up, instance, act, nmaps;
     int K[FSV_SPADE_MAX_MAPS], m_ld[FSV_SPADE_MAX_MAPS], m_coff[FSV_SPADE_MAX_MAPS];
     long long w_nstride[FSV_SPADE_MAX_MAPS];
+    int dgb_ld[FSV_SPADE_MAX_MAPS];
     const float* maps[FSV_SPADE_MAX_MAPS];
     const float* wg[FSV_SPADE_MAX_MAPS];
     const float* bg[FSV_SPADE_MAX_MAPS];
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(256) k_spade_bwd(SpadeP p, const float* __rest
                 for (int s = 0; s < 4; ++s) {
                     int c = c0 + tx * 4 + s;
                     if (px < HW && c < p.C) {
-                        long long o = ((long long)n * HW + px) * p.C + c;
+                        long long o = ((long long)n * HW + px) * p.dgb_ld[i] + c;
                         p.dbeta[i][o] = g[r][s];
                         p.dgamma[i][o] = g[r][s] * vprev[i][r][s];
                     }
@@ -246,6 +247,7 @@ static int fill_p(SpadeP& p, const fsv_spade_desc* d, const float* const* maps, 
         bool on = i < d->nmaps;
         p.K[i] = on ? d->K[i] : 0; p.m_ld[i] = on ? d->m_ld[i] : 0; p.m_coff[i] = on ? d->m_coff[i] : 0;
         p.w_nstride[i] = on ? d->w_nstride[i] : 0;
+        p.dgb_ld[i] = (on && d->dgb_ld[i] > 0) ? d->dgb_ld[i] : d->C;
         p.maps[i] = on ? maps[i] : nullptr; p.wg[i] = on ? wg[i] : nullptr; p.bg[i] = on ? bg[i] : nullptr;
         p.wb[i] = on ? wb[i] : nullptr; p.bb[i] = on ? bb[i] : nullptr;
         p.dgamma[i] = nullptr; p.dbeta[i] = nullptr;

@@ -243,6 +243,60 @@ __global__ void __launch_bounds__(128) k_thin_cout_wgrad(ThinP p, const float* _
     }
 }
 
+// ------------------------------------------------------------------ Cin <= 8 data gradient (thin OUTPUT dx, wide dy)
+// dx[n,h,w,ci] = sum_{r,s,co} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,co] * w[co][r][s][ci]; one thread per dx pixel.
+// Needed for the discriminator's first conv (8 -> 32, k4 s2): its input carries the generated image.
+__global__ void __launch_bounds__(128) k_thin_cin_dgrad(ThinP p, const float* __restrict__ dy, const float* __restrict__ w,
+                                                        float* __restrict__ dx, int accumulate) {
+    extern __shared__ float ws[];                 // [tap][co][ci8]
+    const int taps = p.kh * p.kw;
+    for (int i = threadIdx.x; i < taps * p.Cout * 8; i += blockDim.x) {
+        int ci = i & 7, tco = i >> 3;
+        int co = tco % p.Cout, tap = tco / p.Cout;
+        ws[i] = ci < p.Cin ? w[((long long)co * taps + tap) * p.Cin + ci] : 0.f;
+    }
+    __syncthreads();
+    const long long total = (long long)p.N * p.H * p.W;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= total) return;
+    const int wq = (int)(pix % p.W);
+    const long long q = pix / p.W;
+    const int hq = (int)(q % p.H);
+    const long long n = q / p.H;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int r = 0; r < p.kh; ++r) {
+        int th = hq + p.pad - r;
+        if (th < 0 || (th % p.stride) != 0) continue;
+        int oh = th / p.stride;
+        if (oh >= p.Ho) continue;
+        for (int s = 0; s < p.kw; ++s) {
+            int tw = wq + p.pad - s;
+            if (tw < 0 || (tw % p.stride) != 0) continue;
+            int ow = tw / p.stride;
+            if (ow >= p.Wo) continue;
+            const float4* dp = reinterpret_cast<const float4*>(dy + ((n * p.Ho + oh) * p.Wo + ow) * p.y_ld + p.y_coff);
+            const float* wt = ws + (r * p.kw + s) * p.Cout * 8;
+            for (int c4 = 0; c4 < p.Cout / 4; ++c4) {
+                float4 dv = dp[c4];
+                float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wt + (c4 * 4 + j) * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wt + (c4 * 4 + j) * 8 + 4);
+                    acc[0] += d4[j] * w0.x; acc[1] += d4[j] * w0.y; acc[2] += d4[j] * w0.z; acc[3] += d4[j] * w0.w;
+                    acc[4] += d4[j] * w1.x; acc[5] += d4[j] * w1.y; acc[6] += d4[j] * w1.z; acc[7] += d4[j] * w1.w;
+                }
+            }
+        }
+    }
+    float* xp = dx + pix * p.x_ld + p.x_coff;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (c < p.Cin) { if (accumulate) xp[c] += acc[c]; else xp[c] = acc[c]; }
+}
+
 // ------------------------------------------------------------------ host side
 static bool thin_common_ok(const fsv_conv_desc* d) {
     return d->up == 1 && d->w_nstride == 0 && d->b_nstride == 0 && d->kh * d->kw <= 16 && (long long)d->N * d->Ho * d->Wo >= 4096;
@@ -299,5 +353,20 @@ extern "C" int fsv_conv2d_wgrad_thin(const fsv_conv_desc* d, const float* x, con
         else k_thin_cout_wgrad<16><<<grid, block, 0, st>>>(p, x, dy, dw, pix_per_warp);
     }
     FSV_CHECK_LAUNCH("conv2d_wgrad_thin");
+    return FSV_OK;
+}
+
+extern "C" int fsv_conv2d_dgrad_thin_ok(const fsv_conv_desc* d) {
+    return d && d->up == 1 && d->w_nstride == 0 && d->Cin <= 8 && d->Cout >= 16 && d->Cout % 4 == 0 && d->y_ld % 4 == 0 &&
+           d->y_coff % 4 == 0 && d->kh * d->kw <= 16 && (long long)d->kh * d->kw * d->Cout * 8 * 4 <= 40 * 1024 &&
+           (long long)d->N * d->H * d->W >= 4096;
+}
+extern "C" int fsv_conv2d_dgrad_thin(const fsv_conv_desc* d, const float* dy, const float* w, float* dx, int accumulate, void* stream) {
+    FSV_REQUIRE(fsv_conv2d_dgrad_thin_ok(d), "conv2d_dgrad_thin: not eligible");
+    FSV_REQUIRE((((uintptr_t)dy) & 15) == 0, "conv2d_dgrad_thin: dy must be 16-byte aligned");
+    ThinP p = thin_p(d);
+    const long long total = (long long)d->N * d->H * d->W;
+    k_thin_cin_dgrad<<<fsv_cdiv(total, 128), 128, (size_t)d->kh * d->kw * d->Cout * 8 * sizeof(float), (cudaStream_t)stream>>>(p, dy, w, dx, accumulate);
+    FSV_CHECK_LAUNCH("conv2d_dgrad_thin");
     return FSV_OK;
 }

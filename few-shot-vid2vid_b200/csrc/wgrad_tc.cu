@@ -150,39 +150,49 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(const __grid_constant__ WgP
 // dst[plane][n][c][hq][w] (row pitch `pitch`) <- src (N, Hs, Ws, C) NHWC slice (ld, coff), seen through an optional
 // nearest x2 upsample (up) as an (H, W) = (Hs*up, Ws*up) image:
 //   plane = s * nph + ph ;  row = hq * rstride + ph ;  col = w * cstride + s - pad     (zero outside the image)
-// dy uses nph = 1, rstride = cstride = 1, s = pad = 0.
-__global__ void k_to_planar(const float* __restrict__ src, float* __restrict__ dst, int N, int Hs, int Ws, int C, int ld, int coff,
-                            int up, int nph, int rstride, int cstride, int pad, int Hq, int Wq, int pitch) {
-    __shared__ float tile[32][33];
+// dy uses ns = nph = 1, rstride = cstride = 1, pad = 0.
+// One block reads the (32*cstride + ns - 1) source pixels x 32 channels that feed a 32-column x 32-channel output tile
+// ONCE (128-byte coalesced rows) and writes all ns column-shifted planes from shared memory (128-byte rows again).
+#define TP_MAXSPAN 68
+__global__ void __launch_bounds__(256) k_to_planar(const float* __restrict__ src, float* __restrict__ dst, int N, int Hs, int Ws, int C,
+                                                   int ld, int coff, int up, int ns, int nph, int rstride, int cstride, int pad,
+                                                   int Hq, int Wq, int pitch) {
+    __shared__ float tile[TP_MAXSPAN][33];
     const int w0 = blockIdx.x * 32, c0 = blockIdx.z * 32;
-    int y = blockIdx.y;                       // (plane * N + n) * Hq + hq
+    int y = blockIdx.y;                       // (ph * N + n) * Hq + hq
     const int hq = y % Hq; y /= Hq;
     const int n = y % N;
-    const int plane = y / N;
-    const int s = plane / nph, ph = plane - s * nph;
+    const int ph = y / N;
     const int H = Hs * up, W = Ws * up;
     const int row = hq * rstride + ph;
-    for (int i = threadIdx.y; i < 32; i += 8) {       // i = pixel within the tile, threadIdx.x = channel
-        int w = w0 + i, c = c0 + threadIdx.x;
-        int col = w * cstride + s - pad;
+    const int span = 31 * cstride + ns;       // source columns col0 .. col0+span-1 cover every (w, s) of this tile
+    const int col0 = w0 * cstride - pad;
+    for (int i = threadIdx.y; i < span; i += 8) {     // i = source column within the span, threadIdx.x = channel
+        int col = col0 + i, c = c0 + threadIdx.x;
         float v = 0.f;
-        if (row < H && w < Wq && col >= 0 && col < W && c < C)
+        if (row < H && col >= 0 && col < W && c < C)
             v = src[(((long long)n * Hs + row / up) * Ws + col / up) * ld + coff + c];
         tile[i][threadIdx.x] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {       // i = channel within the tile, threadIdx.x = pixel
-        int c = c0 + i, w = w0 + threadIdx.x;
-        if (c < C && w < pitch)
-            dst[((((long long)plane * N + n) * C + c) * Hq + hq) * pitch + w] = tile[threadIdx.x][i];
+    for (int s = 0; s < ns; ++s) {
+        const int plane = s * nph + ph;
+        for (int i = threadIdx.y; i < 32; i += 8) {   // i = channel within the tile, threadIdx.x = output column
+            int c = c0 + i, w = w0 + threadIdx.x;
+            if (c < C && w < pitch) {
+                float v = w < Wq ? tile[threadIdx.x * cstride + s][i] : 0.f;
+                dst[((((long long)plane * N + n) * C + c) * Hq + hq) * pitch + w] = v;
+            }
+        }
     }
 }
 
-static int launch_to_planar(const float* src, float* dst, int N, int Hs, int Ws, int C, int ld, int coff, int up, int nph, int rstride,
-                            int cstride, int pad, int Hq, int Wq, int pitch, int planes, cudaStream_t st) {
-    dim3 grid(fsv_cdiv(pitch, 32), planes * N * Hq, fsv_cdiv(C, 32));
-    FSV_REQUIRE((long long)planes * N * Hq <= 2147483647LL && grid.z <= 65535, "to_planar: grid too large");
-    k_to_planar<<<grid, dim3(32, 8), 0, st>>>(src, dst, N, Hs, Ws, C, ld, coff, up, nph, rstride, cstride, pad, Hq, Wq, pitch);
+static int launch_to_planar(const float* src, float* dst, int N, int Hs, int Ws, int C, int ld, int coff, int up, int ns, int nph,
+                            int rstride, int cstride, int pad, int Hq, int Wq, int pitch, cudaStream_t st) {
+    FSV_REQUIRE(31 * cstride + ns <= TP_MAXSPAN, "to_planar: span too large");
+    dim3 grid(fsv_cdiv(pitch, 32), nph * N * Hq, fsv_cdiv(C, 32));
+    FSV_REQUIRE(grid.z <= 65535, "to_planar: grid too large");
+    k_to_planar<<<grid, dim3(32, 8), 0, st>>>(src, dst, N, Hs, Ws, C, ld, coff, up, ns, nph, rstride, cstride, pad, Hq, Wq, pitch);
     FSV_CHECK_LAUNCH("to_planar");
     return FSV_OK;
 }
@@ -217,8 +227,10 @@ extern "C" int fsv_conv2d_wgrad_tc_eligible(const fsv_conv_desc* d) {
     if (d->Cin < 32 && d->Cout < 32) return 0;
     int nsmall = d->Cin < d->Cout ? d->Cin : d->Cout;
     if (wg_bn(nsmall) == 0) return 0;
-    if (d->Wo < 32) return 0;                        // K rows are 32 pixels of one image row (128-byte TMA inner box)
-    if ((long long)d->N * d->Ho * d->Wo < 1024) return 0;
+    // K rows are 32 pixels of one image row (128-byte TMA inner box); rows narrower than 32 are zero-filled by TMA, which
+    // wastes MMA issue slots but keeps the (small, low-resolution) layers off the FFMA path
+    if (d->Wo < 4) return 0;
+    if ((long long)d->N * d->Ho * d->Wo < 256) return 0;
     return fsv_get_encode_tiled() != nullptr ? 1 : 0;
 }
 
@@ -254,10 +266,10 @@ extern "C" int fsv_conv2d_wgrad_tc(const fsv_conv_desc* d, const float* x, const
     float* dyT = xT + g.x_floats;
     const int taps = d->kh * d->kw;
     if (!accumulate) FSV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * taps * d->Cin, st));
-    int rc = launch_to_planar(x, xT, d->N, d->H / d->up, d->W / d->up, d->Cin, d->x_ld, d->x_coff, d->up, g.nph, d->stride, d->stride,
-                              d->pad, g.Hq, d->Wo, g.pitch, g.planes, st);
+    int rc = launch_to_planar(x, xT, d->N, d->H / d->up, d->W / d->up, d->Cin, d->x_ld, d->x_coff, d->up, d->kw, g.nph, d->stride,
+                              d->stride, d->pad, g.Hq, d->Wo, g.pitch, st);
     if (rc) return rc;
-    rc = launch_to_planar(dy, dyT, d->N, d->Ho, d->Wo, d->Cout, d->y_ld, d->y_coff, 1, 1, 1, 1, 0, d->Ho, d->Wo, g.pitch, 1, st);
+    rc = launch_to_planar(dy, dyT, d->N, d->Ho, d->Wo, d->Cout, d->y_ld, d->y_coff, 1, 1, 1, 1, 1, 0, d->Ho, d->Wo, g.pitch, st);
     if (rc) return rc;
 
     WgParams p;

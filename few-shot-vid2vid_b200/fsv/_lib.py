@@ -28,7 +28,7 @@ class ConvDesc(ctypes.Structure):
 class SpadeDesc(ctypes.Structure):
     _fields_ = [('N', c_int), ('H', c_int), ('W', c_int), ('C', c_int), ('up', c_int), ('mode', c_int), ('act', c_int),
                 ('nmaps', c_int), ('K', c_int * SPADE_MAX_MAPS), ('m_ld', c_int * SPADE_MAX_MAPS),
-                ('m_coff', c_int * SPADE_MAX_MAPS), ('w_nstride', c_ll * SPADE_MAX_MAPS)]
+                ('m_coff', c_int * SPADE_MAX_MAPS), ('w_nstride', c_ll * SPADE_MAX_MAPS), ('dgb_ld', c_int * SPADE_MAX_MAPS)]
 
 
 PtrArray = c_vp * SPADE_MAX_MAPS

@@ -348,7 +348,8 @@ def batch_conv1x1(x, flat, cout, cin, w_off, b_off, act=ACT_NONE):
 def linear(x2d, w, bias, act=ACT_NONE):
     """F.linear on (rows, K) with w (out, K): a 1x1 conv over a rows x 1 'image'."""
     rows, k = x2d.shape
-    y = conv2d(x2d.reshape(1, rows, 1, k), w.reshape(w.shape[0], 1, 1, k), bias, act=act)
+    wcols = 32 if rows % 32 == 0 else 1      # a 1x1 conv does not care how the rows are arranged as an image; 32-wide rows
+    y = conv2d(x2d.reshape(1, rows // wcols, wcols, k), w.reshape(w.shape[0], 1, 1, k), bias, act=act)   # suit the TMA boxes
     return y.reshape(rows, w.shape[0])
 
 
@@ -472,11 +473,21 @@ class SpadeFn(torch.autograd.Function):
         nm = len(cfg['maps'])
         d, arrays = SpadeFn._desc(cfg, n, h, w, c, tensors)
         dxhat = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
-        dgs = [torch.empty((n, h, w, c), device=dev, dtype=torch.float32) for _ in range(nm)]
-        dbs = [torch.empty((n, h, w, c), device=dev, dtype=torch.float32) for _ in range(nm)]
+        # fixed-weight maps get ONE interleaved (N,H,W,2C) [dgamma | dbeta] buffer so that their 1x1 data / weight gradients
+        # are single GEMMs over 2C channels (tensor-core eligible); per-sample (hyper-weight) maps keep separate buffers
+        # because their gamma / beta weights are not adjacent inside the hyper-network's flat output
+        fused = [mc.get('nstride', 0) == 0 for mc in cfg['maps']]
+        dgb, dgs, dbs = [None] * nm, [None] * nm, [None] * nm
         pg, pb = PtrArray(), PtrArray()
         for i in range(nm):
-            pg[i], pb[i] = dgs[i].data_ptr(), dbs[i].data_ptr()
+            if fused[i]:
+                dgb[i] = torch.empty((n, h, w, 2 * c), device=dev, dtype=torch.float32)
+                pg[i], pb[i] = dgb[i].data_ptr(), dgb[i].data_ptr() + 4 * c
+                d.dgb_ld[i] = 2 * c
+            else:
+                dgs[i] = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+                dbs[i] = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+                pg[i], pb[i] = dgs[i].data_ptr(), dbs[i].data_ptr()
         _call(lib.fsv_spade_bwd, ctypes.byref(d), ptr(x), ptr(mean), ptr(rstd), *arrays, ptr(dout), ptr(dxhat), pg, pb, st)
         mode = cfg['mode']
         groups = n if mode == NORM_INSTANCE else 1
@@ -501,10 +512,36 @@ class SpadeFn(torch.autograd.Function):
         for i, mc in enumerate(cfg['maps']):
             m = tensors[5 * i]
             K = mc['K']
+            need_m = ctx.needs_input_grad[4 + 5 * i]
+            if fused[i]:
+                wg_t, bg_t, wb_t, bb_t = tensors[5 * i + 1:5 * i + 5]
+                cd = _conv_desc(n, h, w, K, 2 * c, 1, 1, 1, 0, 1, ACT_NONE, 1.0, 0, 0, CONV_USE_TC)
+                cd.x_ld = m.shape[3]
+                wcat = torch.cat([wg_t.reshape(c, K), wb_t.reshape(c, K)], 0)            # (2C, K): tiny, parameter-side
+                if need_m:
+                    dm = torch.empty_like(m)
+                    if cd.use_tc != 0 and lib.fsv_conv2d_dgrad_tc_eligible(ctypes.byref(cd)):
+                        _call(lib.fsv_conv2d_dgrad_tc, ctypes.byref(cd), ptr(dgb[i]), ptr(wcat.t().contiguous()), ptr(dm), st)
+                    else:
+                        _call(lib.fsv_conv2d_dgrad, ctypes.byref(cd), ptr(dgb[i]), ptr(wcat), ptr(dm), 0, st)
+                    grads[5 * i] = dm
+                if ctx.needs_input_grad[4 + 5 * i + 1] or ctx.needs_input_grad[4 + 5 * i + 3]:
+                    dwcat = torch.empty((2 * c, K), device=dev, dtype=torch.float32)
+                    dbcat = torch.empty(2 * c, device=dev, dtype=torch.float32) if bg_t is not None else None
+                    if cd.use_tc != 0 and lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(cd)):
+                        ws = torch.empty(int(lib.fsv_conv2d_wgrad_tc_workspace(ctypes.byref(cd))) // 4 + 1, device=dev, dtype=torch.float32)
+                        _call(lib.fsv_conv2d_wgrad_tc, ctypes.byref(cd), ptr(m), ptr(dgb[i]), ptr(dwcat), ptr(ws), 0, st)
+                        if dbcat is not None:
+                            _call(lib.fsv_conv2d_wgrad, ctypes.byref(cd), ptr(m), ptr(dgb[i]), None, ptr(dbcat), 0, st)
+                    else:
+                        _call(lib.fsv_conv2d_wgrad, ctypes.byref(cd), ptr(m), ptr(dgb[i]), ptr(dwcat), ptr(dbcat), 0, st)
+                    grads[5 * i + 1], grads[5 * i + 3] = dwcat[:c].reshape(wg_t.shape), dwcat[c:].reshape(wb_t.shape)
+                    if dbcat is not None:
+                        grads[5 * i + 2], grads[5 * i + 4] = dbcat[:c], dbcat[c:]
+                continue
             ns = mc.get('nstride', 0)
             cd = _conv_desc(n, h, w, K, c, 1, 1, 1, 0, 1, ACT_NONE, 1.0, ns, ns, 0)
             cd.x_ld = m.shape[3]
-            need_m = ctx.needs_input_grad[4 + 5 * i]
             if need_m:
                 dm = torch.empty_like(m) if m.shape[3] == K else torch.zeros_like(m)
                 _call(lib.fsv_conv2d_dgrad, ctypes.byref(cd), ptr(dgs[i]), _off(tensors[5 * i + 1], mc.get('wg_off', 0)), ptr(dm), 0, st)

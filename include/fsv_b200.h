@@ -151,6 +151,8 @@ typedef struct fsv_spade_desc {
     int m_ld[FSV_SPADE_MAX_MAPS];      /* channel stride of map i's buffer (map is N,H,W,K at offset m_coff) */
     int m_coff[FSV_SPADE_MAX_MAPS];
     long long w_nstride[FSV_SPADE_MAX_MAPS];  /* 0 = fixed mlp_gamma/mlp_beta weights; else per-sample stride (hyper-weights) */
+    int dgb_ld[FSV_SPADE_MAX_MAPS];    /* backward only: pixel stride of the dgamma[i]/dbeta[i] buffers (0 = C); 2C lets the
+                                          caller interleave them as one (N,H,W,2C) tensor for a single 1x1 dgrad/wgrad */
 } fsv_spade_desc;
 /* out = act( (((x-mean)*rstd) * (1+g_0) + b_0) * (1+g_1) + b_1 ... ),  g_i = Wg_i . map_i + bg_i  (1x1).
  * bg[i] / bb[i] may be NULL (no bias): the reference's adaptive path applies the hyper-weights without their

@@ -130,6 +130,11 @@ WGRAD_CASES = [
     (2, 32, 32, 64, 64, 1, 1, 0, 1),
     (2, 65, 67, 32, 64, 4, 2, 2, 1),
     (1, 34, 34, 256, 512, 4, 1, 2, 1),
+    (2, 16, 16, 64, 128, 3, 1, 1, 1),     # rows narrower than the 32-pixel K block (zero-filled by TMA)
+    (4, 8, 8, 256, 128, 3, 1, 1, 1),
+    (2, 17, 17, 64, 96, 4, 1, 2, 1),
+    (4, 16, 16, 64, 128, 3, 2, 1, 1),
+    (1, 64, 32, 160, 48, 1, 1, 0, 1),
 ]
 
 
