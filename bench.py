@@ -205,7 +205,7 @@ def run_fsv(args):
     netD = networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, opt.num_D, True, gpu_ids=[local_rank])
     netG.train(), netD.train()
     parallel.broadcast_state(netG), parallel.broadcast_state(netD)
-    use_graph = args.graph and world == 1
+    use_graph = args.graph          # NCCL collectives are capturable too (one graph per rank, replayed in lock-step)
     optG, optD = trainer.make_optimizers(opt, netG, netD, capturable=use_graph)
     syncG = parallel.GradSync(netG.parameters()) if world > 1 else None
     syncD = parallel.GradSync(netD.parameters()) if world > 1 else None
@@ -275,12 +275,15 @@ def run_fsv(args):
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
-    # instrumented pass: CUDA-event time per C-ABI kernel family
+    # instrumented pass: CUDA-event time per C-ABI kernel family (every rank runs the steps -- they contain the gradient
+    # all-reduce -- but only rank 0 records events)
     prof = {}
+    detail = {}
+    spade_bytes = 0.0
+    psteps = 2
     if rank == 0:
         real_call = ops._call
         pending = []
-        detail = {}
         from fsv._lib import lib
 
         def prof_call(fn, *a):
@@ -296,12 +299,11 @@ def run_fsv(args):
             detail.setdefault(key, [0.0, 0])
             pending.append((fn.__name__, a, s, e, key))
         ops._call = prof_call
-        psteps = 2
-        for _ in range(psteps):
-            eager_step(devin)
-        torch.cuda.synchronize()
+    for _ in range(psteps):
+        eager_step(devin)
+    torch.cuda.synchronize()
+    if rank == 0:
         ops._call = real_call
-        spade_bytes = 0.0
         for name, a, s, e, key in pending:
             d = prof.setdefault(name, [0.0, 0])
             d[0] += s.elapsed_time(e) / psteps
@@ -383,6 +385,9 @@ def main():
         from fsv import ops
         ops.CONV_USE_TC = 0
     run_fsv(args)
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
