@@ -1,0 +1,266 @@
+// Fused SPADE forward on tcgen05 tensor cores (TF32 gamma/beta GEMM, fp32 modulation).  sm_100a only.
+//
+// Same contract as fsv_spade_fwd (spade.cu; reference normalization.py:37-52 + architecture.py:96-97), for the shapes
+// that carry the cost: C % 64 == 0 and every label map with K % 32 == 0.  The SIMT kernel is FFMA-bound on the
+// per-pixel 1x1 GEMM (measured 341 us = 0.78 TB/s at up_0, 8.6 GFMA); here that GEMM runs on the tensor cores
+// and the kernel goes back to being the HBM stream it should be:
+//
+//   per CTA: 128 pixels (TN x TH x TW patch) x 64 channels
+//     for each label map i, each 32-channel K block:  TMA  map tile (128 px x 32)            -> smem (K-major, SW128)
+//                                                     TMA  Wgamma_i[64 x 32], Wbeta_i[64 x 32] -> smem (one 128-row B tile)
+//                                                     tcgen05.mma  D_i[128 px x (64 gamma | 64 beta)] += A * B^T   (TMEM)
+//     epilogue (4 warps, thread = pixel): v = (x[n, h/up, w/up, c] - mean) * rstd   (nearest x2 upsample folded into the load)
+//                                          for each map: v = v * (1 + gamma_i + bg_i) + beta_i + bb_i   (gamma/beta from TMEM)
+//                                          out = LeakyReLU(v)                                        (16-byte stores)
+// Per-sample hyper-weights (map 0 of the adaptive layers) are addressed through a 3-D tensor map over the
+// hyper-network's flat output (K, C, sample) -- still zero-copy.  gamma/beta never touch HBM.
+// Roofline: HBM, algorithmic bytes 4*(|x|/up^2 + sum|map_i| + |out|) per launch (weights: L2-resident).
+#include "tc_common.cuh"
+
+#define SP_STAGES 3
+#define SP_CB 64                                   // channels per CTA
+#define SP_STAGE_BYTES (TC_A_BYTES + 2 * SP_CB * TC_BK * 4)   // 16 KB map tile + 8 KB gamma + 8 KB beta
+
+struct __align__(64) SpTcParams {
+    CUtensorMap mmap[FSV_SPADE_MAX_MAPS];
+    CUtensorMap gmap[FSV_SPADE_MAX_MAPS];
+    CUtensorMap bmap[FSV_SPADE_MAX_MAPS];
+    const float* bg[FSV_SPADE_MAX_MAPS];
+    const float* bb[FSV_SPADE_MAX_MAPS];
+    long long b_nstride[FSV_SPADE_MAX_MAPS];
+    int K[FSV_SPADE_MAX_MAPS], per_sample[FSV_SPADE_MAX_MAPS];
+    int nmaps, N, H, W, C, up, instance, act;
+    int TW, TH, TN, tiles_w, tiles_h;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 2) k_spade_tc(const __grid_constant__ SpTcParams p, const float* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     float* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + SP_STAGES * SP_STAGE_BYTES);   // full[S], empty[S], tmem_full
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * SP_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int mt = blockIdx.x;
+    const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+    const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
+    const int n0 = mt * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+    const int c0 = blockIdx.y * SP_CB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SP_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[SP_STAGES + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * SP_STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    const uint32_t tmem_cols = p.nmaps <= 1 ? 128u : (p.nmaps == 2 ? 256u : 512u);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    int num_k = 0;
+    for (int i = 0; i < p.nmaps; ++i) num_k += p.K[i] / TC_BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int i = 0; i < p.nmaps; ++i) {
+                const int kbs = p.K[i] / TC_BK;
+                const int wn = p.per_sample[i] ? n0 : 0;
+                for (int kb = 0; kb < kbs; ++kb, ++it) {
+                    const int s = it % SP_STAGES;
+                    const uint32_t ph = (it / SP_STAGES) & 1;
+                    mbar_wait(smem_u32(&bars[SP_STAGES + s]), ph ^ 1);
+                    const uint32_t full = smem_u32(&bars[s]);
+                    const uint32_t dst = smem_u32(smem + s * SP_STAGE_BYTES);
+                    mbar_expect_tx(full, (uint32_t)SP_STAGE_BYTES);
+                    tma_load_4d(dst, &p.mmap[i], full, kb * TC_BK, w0, h0, n0);
+                    tma_load_3d(dst + TC_A_BYTES, &p.gmap[i], full, kb * TC_BK, c0, wn);
+                    tma_load_3d(dst + TC_A_BYTES + SP_CB * TC_BK * 4, &p.bmap[i], full, kb * TC_BK, c0, wn);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, 2 * SP_CB);
+            int it = 0;
+            for (int i = 0; i < p.nmaps; ++i) {
+                const int kbs = p.K[i] / TC_BK;
+                for (int kb = 0; kb < kbs; ++kb, ++it) {
+                    const int s = it % SP_STAGES;
+                    const uint32_t ph = (it / SP_STAGES) & 1;
+                    mbar_wait(smem_u32(&bars[s]), ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * SP_STAGE_BYTES);
+                    const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        tc_mma_tf32(tmem_base + (uint32_t)(i * 2 * SP_CB), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                    (kb | k) != 0);
+                    tc_commit(smem_u32(&bars[SP_STAGES + s]));
+                }
+            }
+            tc_commit(smem_u32(&bars[2 * SP_STAGES]));
+        }
+    } else {
+        // ===== epilogue: thread = pixel of the tile; while the MMAs run, fetch and normalise x
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int tw = row % p.TW, r2 = row / p.TW;
+        const int th = r2 % p.TH, tn = r2 / p.TH;
+        const int n = n0 + tn, h = h0 + th, w = w0 + tw;
+        const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+        const int Hs = p.H / p.up, Ws = p.W / p.up;
+        float v[SP_CB];
+        if (valid) {
+            const float4* xr = reinterpret_cast<const float4*>(x + (((long long)n * Hs + h / p.up) * Ws + w / p.up) * p.C + c0);
+            const float* mp = mean + (p.instance ? n * p.C : 0) + c0;
+            const float* rp = rstd + (p.instance ? n * p.C : 0) + c0;
+#pragma unroll
+            for (int j = 0; j < SP_CB / 4; ++j) {
+                float4 t = xr[j];
+                float4 m = *reinterpret_cast<const float4*>(mp + 4 * j);
+                float4 r = *reinterpret_cast<const float4*>(rp + 4 * j);
+                v[4 * j + 0] = (t.x - m.x) * r.x; v[4 * j + 1] = (t.y - m.y) * r.y;
+                v[4 * j + 2] = (t.z - m.z) * r.z; v[4 * j + 3] = (t.w - m.w) * r.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SP_CB; ++j) v[j] = 0.f;
+        }
+        mbar_wait(smem_u32(&bars[2 * SP_STAGES]), 0);
+        tc_fence_after();
+        for (int i = 0; i < p.nmaps; ++i) {
+            const float* bgp = p.bg[i] ? p.bg[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 : nullptr;
+            const float* bbp = p.bb[i] ? p.bb[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 : nullptr;
+#pragma unroll
+            for (int c = 0; c < SP_CB; c += 32) {
+                uint32_t g[32], b[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * 2 * SP_CB + c);
+                tc_ld32(taddr, g);
+                tc_ld32(taddr + SP_CB, b);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float gv = __uint_as_float(g[j]) + (bgp ? bgp[c + j] : 0.f);
+                        float bv = __uint_as_float(b[j]) + (bbp ? bbp[c + j] : 0.f);
+                        v[c + j] = v[c + j] * (1.f + gv) + bv;
+                    }
+                }
+            }
+        }
+        if (valid) {
+            float4* orow = reinterpret_cast<float4*>(out + (((long long)n * p.H + h) * p.W + w) * p.C + c0);
+#pragma unroll
+            for (int j = 0; j < SP_CB / 4; ++j)
+                orow[j] = make_float4(fsv_act(v[4 * j], p.act), fsv_act(v[4 * j + 1], p.act), fsv_act(v[4 * j + 2], p.act),
+                                      fsv_act(v[4 * j + 3], p.act));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static void sp_pick_tile(int H, int W, int& TW, int& TH, int& TN) {
+    TW = 16; TH = 8; TN = 1;
+    if (W < 16) {
+        TW = 1; while (TW * 2 <= W && TW < 16) TW *= 2;
+        int rem = 128 / TW;
+        TH = 1; while (TH * 2 <= H && TH * 2 <= rem) TH *= 2;
+        TN = rem / TH;
+    }
+}
+
+extern "C" int fsv_spade_fwd_tc_eligible(const fsv_spade_desc* d) {
+    if (!d || d->nmaps < 1 || d->nmaps > FSV_SPADE_MAX_MAPS) return 0;
+    if (d->C % SP_CB != 0) return 0;
+    int TW, TH, TN;
+    sp_pick_tile(d->H, d->W, TW, TH, TN);
+    for (int i = 0; i < d->nmaps; ++i) {
+        if (d->K[i] % TC_BK != 0 || d->m_ld[i] % 4 != 0 || d->m_coff[i] % 4 != 0) return 0;
+        if (d->w_nstride[i] != 0 && (TN != 1 || d->w_nstride[i] % 4 != 0)) return 0;   // per-sample weights: tiles must not span samples
+    }
+    if ((long long)d->N * d->H * d->W < 128) return 0;
+    return fsv_get_encode_tiled() != nullptr ? 1 : 0;
+}
+
+extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
+                                const float* const* maps, const float* const* wg, const float* const* bg,
+                                const float* const* wb, const float* const* bb, float* out, void* stream) {
+    FSV_REQUIRE(d != nullptr, "spade_fwd_tc: null descriptor");
+    if (!fsv_spade_fwd_tc_eligible(d)) {
+        fsv_set_error("spade_fwd_tc: shape not eligible (need C%%64==0, K%%32==0)");
+        return FSV_ENOTSUP;
+    }
+    FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0 && (((uintptr_t)mean) & 15) == 0 && (((uintptr_t)rstd) & 15) == 0,
+                "spade_fwd_tc: pointers must be 16-byte aligned");
+    SpTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.nmaps = d->nmaps; p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.up = d->up; p.instance = d->mode == FSV_NORM_INSTANCE; p.act = d->act;
+    sp_pick_tile(d->H, d->W, p.TW, p.TH, p.TN);
+    p.tiles_w = fsv_cdiv(d->W, p.TW); p.tiles_h = fsv_cdiv(d->H, p.TH);
+    const int tiles_n = fsv_cdiv(d->N, p.TN);
+    PFN_encodeTiled enc = fsv_get_encode_tiled();
+    for (int i = 0; i < d->nmaps; ++i) {
+        FSV_REQUIRE(maps[i] && wg[i] && wb[i], "spade_fwd_tc: map %d has null pointers", i);
+        FSV_REQUIRE((((uintptr_t)(maps[i] + d->m_coff[i])) & 15) == 0 && (((uintptr_t)wg[i]) & 15) == 0 && (((uintptr_t)wb[i]) & 15) == 0,
+                    "spade_fwd_tc: map %d pointers must be 16-byte aligned", i);
+        p.K[i] = d->K[i];
+        p.per_sample[i] = d->w_nstride[i] != 0;
+        p.bg[i] = bg[i]; p.bb[i] = bb[i]; p.b_nstride[i] = d->w_nstride[i];
+        const long long ld = d->m_ld[i];
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d->K[i], (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+            cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * d->W * 4, (cuuint64_t)ld * d->W * d->H * 4};
+            cuuint32_t box[4] = {TC_BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = enc(&p.mmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(maps[i] + d->m_coff[i]), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            FSV_REQUIRE(r == CUDA_SUCCESS, "spade_fwd_tc: cuTensorMapEncodeTiled(map %d) failed with %d", i, (int)r);
+        }
+        for (int which = 0; which < 2; ++which) {
+            const float* wp = which == 0 ? wg[i] : wb[i];
+            const int nw = p.per_sample[i] ? d->N : 1;
+            const long long ns = p.per_sample[i] ? d->w_nstride[i] : (long long)d->C * d->K[i];
+            cuuint64_t dims[3] = {(cuuint64_t)d->K[i], (cuuint64_t)d->C, (cuuint64_t)nw};
+            cuuint64_t strides[2] = {(cuuint64_t)d->K[i] * 4, (cuuint64_t)ns * 4};
+            cuuint32_t box[3] = {TC_BK, SP_CB, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = enc(which == 0 ? &p.gmap[i] : &p.bmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)wp, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            FSV_REQUIRE(r == CUDA_SUCCESS, "spade_fwd_tc: cuTensorMapEncodeTiled(weights %d/%d) failed with %d", i, which, (int)r);
+        }
+    }
+    const int smem_bytes = SP_STAGES * SP_STAGE_BYTES + (2 * SP_STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        configured = true;
+    }
+    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->C / SP_CB);
+    k_spade_tc<<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(p, x, mean, rstd, out);
+    FSV_CHECK_LAUNCH("spade_fwd_tc");
+    return FSV_OK;
+}

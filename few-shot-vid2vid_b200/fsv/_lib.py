@@ -61,6 +61,8 @@ SIGNATURES = {
     'fsv_norm_apply_fwd': [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     'fsv_norm_apply_bwd': [c_vp] * 10 + [c_int] * 6 + [c_vp],
     'fsv_spade_fwd': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp],
+    'fsv_spade_fwd_tc_eligible': [_SD],
+    'fsv_spade_fwd_tc': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp],
     'fsv_spade_bwd': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp, PtrArray, PtrArray, c_vp],
     'fsv_spade_norm_bwd': [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp],
     'fsv_warp_fwd': [c_vp] * 5 + [c_int] * 7 + [c_vp],

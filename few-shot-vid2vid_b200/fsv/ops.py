@@ -434,7 +434,8 @@ class SpadeFn(torch.autograd.Function):
                             cfg.get('momentum', 0.1), unbias_mul=up * up)
         d, arrays = SpadeFn._desc(cfg, n, h, w, c, tensors)
         out = torch.empty((n, h, w, c), device=x.device, dtype=torch.float32)
-        _call(lib.fsv_spade_fwd, ctypes.byref(d), ptr(x), ptr(mean), ptr(rstd), *arrays, ptr(out), stream())
+        fwd = lib.fsv_spade_fwd_tc if (CONV_USE_TC != 0 and lib.fsv_spade_fwd_tc_eligible(ctypes.byref(d))) else lib.fsv_spade_fwd
+        _call(fwd, ctypes.byref(d), ptr(x), ptr(mean), ptr(rstd), *arrays, ptr(out), stream())
         ctx.cfg = cfg
         ctx.dims = (n, h, w, c)
         ctx.save_for_backward(x, mean, rstd, *tensors)

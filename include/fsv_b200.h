@@ -160,6 +160,12 @@ typedef struct fsv_spade_desc {
 int fsv_spade_fwd(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
                   const float* const* maps, const float* const* wg, const float* const* bg,
                   const float* const* wb, const float* const* bb, float* out, void* stream);
+/* Same contract on the tcgen05 path (TF32 gamma/beta GEMM in TMEM, fp32 modulation epilogue) for C % 64 == 0 and
+ * K_i % 32 == 0; FSV_ENOTSUP otherwise. */
+int fsv_spade_fwd_tc_eligible(const fsv_spade_desc* d);
+int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
+                     const float* const* maps, const float* const* wg, const float* const* bg,
+                     const float* const* wb, const float* const* bb, float* out, void* stream);
 /* Backward.  Recomputes gamma/beta and the pre-activation value (so `out` is not needed), walks the modulation chain backwards and emits
  *   dxhat  (N,H,W,C): gradient w.r.t. the normalised activation (feed to fsv_spade_norm_bwd)
  *   dgamma[i], dbeta[i] (N,H,W,C each): gradients of the 1x1 conv outputs (feed to fsv_conv2d_dgrad/wgrad) */

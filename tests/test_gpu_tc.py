@@ -158,3 +158,52 @@ def test_conv_tc_wgrad(case):
     (yg * to_nhwc(go.float().cuda())).sum().backward()
     assert grad_err(wg.grad, w.grad) < TOL_TF32
     assert grad_err(bg.grad, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize('kind,C,Hs,up,Ks,adaptive,N', [
+    ('batch', 64, 16, 2, [32, 32], True, 2), ('batch', 128, 16, 1, [64], False, 2), ('batch', 64, 8, 1, [32], False, 4),
+    ('instance', 64, 24, 1, [32, 64, 32], True, 1), ('batch', 192, 20, 1, [32, 32], True, 2)])
+def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N):
+    """fused SPADE on tcgen05 (TF32 gamma/beta GEMM in TMEM) vs the float64 oracle; backward runs the exact-fp32 kernels."""
+    from fsv import ops
+    from fsv.networks.layers import SPADE
+    old = ops.CONV_USE_TC
+    ops.CONV_USE_TC = -1
+    try:
+        H = Hs * up
+        x = (rnd(N, C, Hs, Hs) * 1.5 + 0.3).requires_grad_(True)
+        maps = [rnd(N, K, H, H).requires_grad_(True) for K in Ks]
+        mod = SPADE(C, Ks, norm='spectralspadesync' + kind, ks=1, params_free=adaptive).cuda()
+        mod.train()
+        sd = {}
+        for n_, p_ in mod.named_parameters():
+            p_.data.normal_(0, 0.2)
+            sd['s.' + n_] = p_.detach().cpu().double().requires_grad_(True)
+        if kind == 'batch':
+            sd['s.norm.running_mean'] = mod.norm.running_mean.cpu().double().clone()
+            sd['s.norm.running_var'] = mod.norm.running_var.cpu().double().clone()
+            sd['s.norm.num_batches_tracked'] = torch.tensor(0)
+        flat = wts = wloc = None
+        if adaptive:
+            K0 = Ks[0]
+            n_gb = C * K0 + C
+            flat = rnd(N, 2 * n_gb, scale=0.2).requires_grad_(True)
+            wts = O.slice_gamma_beta(flat, [C, K0, 1, 1])
+        y = O.lrelu(O.spade(O.up2(x) if up == 2 else x, maps, sd, 's', kind, True, wts))
+        go = rnd(*y.shape)
+        (y * go).sum().backward()
+        xg = to_nhwc(x.detach().float().cuda()).requires_grad_(True)
+        mg = [to_nhwc(m.detach().float().cuda()).requires_grad_(True) for m in maps]
+        if adaptive:
+            fg = flat.detach().float().cuda().requires_grad_(True)
+            wloc = (fg, 0, C * Ks[0], C * Ks[0] + C, 2 * C * Ks[0] + C)
+        n0 = ops.LAUNCHES[0]
+        yg = mod(xg, mg, wloc, up=up, act=ops.ACT_LRELU)
+        assert rel_err(yg.permute(0, 3, 1, 2), y) < TOL_TF32
+        (yg * to_nhwc(go.float().cuda())).sum().backward()
+        from util import l2_err
+        assert l2_err(xg.grad.permute(0, 3, 1, 2), x.grad) < 1e-2          # kink-robust metric (TF32 forward vs fp32 recompute)
+        for a, b in zip(mg, maps):
+            assert l2_err(a.grad.permute(0, 3, 1, 2), b.grad) < 1e-2
+    finally:
+        ops.CONV_USE_TC = old
