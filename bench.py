@@ -310,7 +310,7 @@ def run_fsv(args):
             d[1] += 1.0 / psteps
             detail[key][0] += s.elapsed_time(e) / psteps
             detail[key][1] += 1.0 / psteps
-            if name == 'fsv_spade_fwd':
+            if name in ('fsv_spade_fwd', 'fsv_spade_fwd_tc'):
                 sd = a[0]._obj
                 px = sd.N * sd.H * sd.W
                 spade_bytes += 4.0 * (px * sd.C / (sd.up * sd.up) + sum(px * sd.K[i] for i in range(sd.nmaps)) + px * sd.C) / psteps
@@ -337,11 +337,12 @@ def run_fsv(args):
         roof = {'bound': 'tensor', 'kernel': 'fsv_conv2d_{fwd,dgrad,wgrad} (all launches of one step)', 'achieved': ach,
                 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
                 'peak_source': peaks['src'] + ', dense bf16 sustained', 'share_of_step_kernel_time': conv_ms / total_ms if total_ms else None}
-    sp = prof.get('fsv_spade_fwd')
+    sp_ms = sum(prof[k][0] for k in ('fsv_spade_fwd', 'fsv_spade_fwd_tc') if k in prof)
+    sp = [sp_ms]
     roof_spade = None
-    if sp and sp[0] > 0:
+    if sp_ms > 0:
         ach = spade_bytes / (sp[0] / 1e3) / 1e9
-        roof_spade = {'bound': 'hbm', 'kernel': 'fsv_spade_fwd (all launches of one step)', 'achieved': ach, 'peak': peaks['hbm'],
+        roof_spade = {'bound': 'hbm', 'kernel': 'fsv_spade_fwd[_tc] (all launches of one step)', 'achieved': ach, 'peak': peaks['hbm'],
                       'unit': 'GB/s', 'frac': ach / peaks['hbm'], 'traffic': None, 'peak_source': peaks['src']}
     line = {'metric': 'frames_per_sec_full_G+D_fwd_bwd', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

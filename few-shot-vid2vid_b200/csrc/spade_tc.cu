@@ -18,8 +18,8 @@
 #include "tc_common.cuh"
 
 #define SP_STAGES 3
-#define SP_CB 64                                   // channels per CTA
-#define SP_STAGE_BYTES (TC_A_BYTES + 2 * SP_CB * TC_BK * 4)   // 16 KB map tile + 8 KB gamma + 8 KB beta
+// channels per CTA: template parameter SP_CB (64, or 32 for the C=32 layer at full resolution)
+#define SP_STAGE_BYTES_OF(CB) (TC_A_BYTES + 2 * (CB) * TC_BK * 4)   // 16 KB map tile + gamma rows + beta rows
 
 struct __align__(64) SpTcParams {
     CUtensorMap mmap[FSV_SPADE_MAX_MAPS];
@@ -39,9 +39,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+template <int SP_CB>
 __global__ void __launch_bounds__(192, 2) k_spade_tc(const __grid_constant__ SpTcParams p, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      float* __restrict__ out) {
+    constexpr int SP_STAGE_BYTES = SP_STAGE_BYTES_OF(SP_CB);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + SP_STAGES * SP_STAGE_BYTES);   // full[S], empty[S], tmem_full
@@ -62,7 +64,8 @@ __global__ void __launch_bounds__(192, 2) k_spade_tc(const __grid_constant__ SpT
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    const uint32_t tmem_cols = p.nmaps <= 1 ? 128u : (p.nmaps == 2 ? 256u : 512u);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(p.nmaps * 2 * SP_CB)) tmem_cols <<= 1;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -193,7 +196,7 @@ static void sp_pick_tile(int H, int W, int& TW, int& TH, int& TN) {
 
 extern "C" int fsv_spade_fwd_tc_eligible(const fsv_spade_desc* d) {
     if (!d || d->nmaps < 1 || d->nmaps > FSV_SPADE_MAX_MAPS) return 0;
-    if (d->C % SP_CB != 0) return 0;
+    if (d->C % 32 != 0) return 0;
     int TW, TH, TN;
     sp_pick_tile(d->H, d->W, TW, TH, TN);
     for (int i = 0; i < d->nmaps; ++i) {
@@ -209,11 +212,12 @@ extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const f
                                 const float* const* wb, const float* const* bb, float* out, void* stream) {
     FSV_REQUIRE(d != nullptr, "spade_fwd_tc: null descriptor");
     if (!fsv_spade_fwd_tc_eligible(d)) {
-        fsv_set_error("spade_fwd_tc: shape not eligible (need C%%64==0, K%%32==0)");
+        fsv_set_error("spade_fwd_tc: shape not eligible (need C%%32==0, K%%32==0)");
         return FSV_ENOTSUP;
     }
     FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0 && (((uintptr_t)mean) & 15) == 0 && (((uintptr_t)rstd) & 15) == 0,
                 "spade_fwd_tc: pointers must be 16-byte aligned");
+    const int CB = d->C % 64 == 0 ? 64 : 32;
     SpTcParams p;
     memset(&p, 0, sizeof(p));
     p.nmaps = d->nmaps; p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.up = d->up; p.instance = d->mode == FSV_NORM_INSTANCE; p.act = d->act;
@@ -245,7 +249,7 @@ extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const f
             const long long ns = p.per_sample[i] ? d->w_nstride[i] : (long long)d->C * d->K[i];
             cuuint64_t dims[3] = {(cuuint64_t)d->K[i], (cuuint64_t)d->C, (cuuint64_t)nw};
             cuuint64_t strides[2] = {(cuuint64_t)d->K[i] * 4, (cuuint64_t)ns * 4};
-            cuuint32_t box[3] = {TC_BK, SP_CB, 1};
+            cuuint32_t box[3] = {TC_BK, (cuuint32_t)CB, 1};
             cuuint32_t estr[3] = {1, 1, 1};
             CUresult r = enc(which == 0 ? &p.gmap[i] : &p.bmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)wp, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -253,14 +257,16 @@ extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const f
             FSV_REQUIRE(r == CUDA_SUCCESS, "spade_fwd_tc: cuTensorMapEncodeTiled(weights %d/%d) failed with %d", i, which, (int)r);
         }
     }
-    const int smem_bytes = SP_STAGES * SP_STAGE_BYTES + (2 * SP_STAGES + 1) * 8 + 16 + 1024;
+    const int smem_bytes = SP_STAGES * SP_STAGE_BYTES_OF(CB) + (2 * SP_STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {
-        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         configured = true;
     }
-    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->C / SP_CB);
-    k_spade_tc<<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(p, x, mean, rstd, out);
+    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->C / CB);
+    if (CB == 64) k_spade_tc<64><<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(p, x, mean, rstd, out);
+    else k_spade_tc<32><<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(p, x, mean, rstd, out);
     FSV_CHECK_LAUNCH("spade_fwd_tc");
     return FSV_OK;
 }

@@ -162,7 +162,8 @@ def test_conv_tc_wgrad(case):
 
 @pytest.mark.parametrize('kind,C,Hs,up,Ks,adaptive,N', [
     ('batch', 64, 16, 2, [32, 32], True, 2), ('batch', 128, 16, 1, [64], False, 2), ('batch', 64, 8, 1, [32], False, 4),
-    ('instance', 64, 24, 1, [32, 64, 32], True, 1), ('batch', 192, 20, 1, [32, 32], True, 2)])
+    ('instance', 64, 24, 1, [32, 64, 32], True, 1), ('batch', 192, 20, 1, [32, 32], True, 2),
+    ('batch', 32, 32, 1, [32, 32], True, 2), ('batch', 96, 16, 2, [32], False, 2)])
 def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N):
     """fused SPADE on tcgen05 (TF32 gamma/beta GEMM in TMEM) vs the float64 oracle; backward runs the exact-fp32 kernels."""
     from fsv import ops
