@@ -20,6 +20,7 @@
 // M-tiles x N-tiles).  Warp roles and the smem ring are those of conv_tc.cu; the epilogue adds the tile into
 // dW with fp32 atomics (red.global.add.f32).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 #define WG_STAGES 4
 #define WG_MAX_TAPS 16
@@ -111,6 +112,148 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc(const __grid_constant__ WgP
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k)
                     tc_mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
+                tc_commit(smem_u32(&bars[WG_STAGES + s]));
+            }
+            tc_commit(smem_u32(&bars[2 * WG_STAGES]));
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        mbar_wait(smem_u32(&bars[2 * WG_STAGES]), 0);
+        tc_fence_after();
+        const int Mdim = p.role == 0 ? p.Cout : p.Cin;
+        const int Ndim = p.role == 0 ? p.Cin : p.Cout;
+        const int m = m0 + row;
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (m < Mdim) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c + j;
+                    if (c + j < BN && n < Ndim) {
+                        const int co = p.role == 0 ? m : n, ci = p.role == 0 ? n : m;
+                        atomicAdd(dw + ((long long)co * p.ntaps + tap_i) * p.Cin + ci, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------ MN-major variant: operands straight from NHWC
+// tcgen05 also accepts TF32 operands whose M/N index is the contiguous one ("MN-major"), provided the tile uses the
+// SWIZZLE_128B_BASE32B shared-memory layout (cute: Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over 4 K-rows x 128 B;
+// TMA produces it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  With that, a K block of 32 pixels is one TMA box
+// (32 channels, PW, PH, PN) of the NHWC tensor per 32-channel column block -- rows = pixels (K), 128 contiguous
+// bytes = 32 channels (M or N) -- exactly how the activations already sit in HBM: no re-layout pass, no workspace,
+// and (the box's inner dimension being channels) pixel shifts of +-1 are plain outer coordinates again.
+//   UMMA descriptor: layout type 1, SBO = 512 B (next group of 4 K-rows), LBO = 4096 B (next 32-channel block),
+//   K step of 8 pixels = +1024 B on the start address; instruction descriptor a_major = b_major = 1.
+#define WGMN_BLOCK_BYTES (32 * 128)          // one 32-channel x 32-pixel block
+
+struct __align__(64) WgMnParams {
+    CUtensorMap dymap;          // NHWC dy: dims (Cout, Wo, Ho, N)
+    CUtensorMap xmap[4];        // NHWC x (stride 1: map 0; stride 2: parity maps): dims (Cin, Wq, Hq, N)
+    WgTap taps[WG_MAX_TAPS];
+    int ntaps, Cin, Cout, N, Ho, Wo;
+    int PW, PH, PN, nWB, nHB, nNB;
+    int role, BN, mtiles, ntiles, kb_per_split;
+    int lbo16, sbo16, kstep16, ltype;   // descriptor fields in 16-byte units (tunable while bringing the layout up)
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, int lbo16, int sbo16, int ltype) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(lbo16 & 0x3FFF) << 16;          // LBO: next 32-element block along M/N
+    d |= (uint64_t)(sbo16 & 0x3FFF) << 32;          // SBO: next group of K rows
+    d |= (uint64_t)1 << 46;                          // version (Blackwell)
+    d |= (uint64_t)(ltype & 7) << 61;                // 1 = SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ WgMnParams p, float* __restrict__ dw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BN = p.BN;
+    const int a_bytes = 4 * WGMN_BLOCK_BYTES, b_bytes = (BN / 32) * WGMN_BLOCK_BYTES;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* bars = (uint64_t*)(smem + WG_STAGES * stage_bytes);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WG_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap_i = blockIdx.y;
+    const WgTap tap = p.taps[tap_i];
+    const int mt = blockIdx.z / p.ntiles, nt = blockIdx.z - mt * p.ntiles;
+    const int m0 = mt * TC_BM, n0 = nt * BN;
+    const int KB = p.nWB * p.nHB * p.nNB;
+    const int kb0 = blockIdx.x * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, KB);
+    const int num_k = kb1 - kb0;
+    if (num_k <= 0) return;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[WG_STAGES + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * WG_STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const CUtensorMap* amap = p.role == 0 ? &p.dymap : &p.xmap[tap.plane];
+            const CUtensorMap* bmap = p.role == 0 ? &p.xmap[tap.plane] : &p.dymap;
+            const int a_dh = p.role == 0 ? 0 : tap.dh, a_dw = p.role == 0 ? 0 : tap.dw;
+            const int b_dh = p.role == 0 ? tap.dh : 0, b_dw = p.role == 0 ? tap.dw : 0;
+            for (int i = 0; i < num_k; ++i) {
+                const int s = i % WG_STAGES;
+                const uint32_t ph = (i / WG_STAGES) & 1;
+                mbar_wait(smem_u32(&bars[WG_STAGES + s]), ph ^ 1);
+                int kb = kb0 + i;
+                const int wb = kb % p.nWB; kb /= p.nWB;
+                const int hb = kb % p.nHB; kb /= p.nHB;
+                const int w0 = wb * p.PW, h0 = hb * p.PH, nn0 = kb * p.PN;
+                const uint32_t full = smem_u32(&bars[s]);
+                const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
+                mbar_expect_tx(full, (uint32_t)stage_bytes);
+                for (int j = 0; j < 4; ++j)
+                    tma_load_4d(a_dst + j * WGMN_BLOCK_BYTES, amap, full, m0 + 32 * j, w0 + a_dw, h0 + a_dh, nn0);
+                for (int j = 0; j < BN / 32; ++j)
+                    tma_load_4d(a_dst + a_bytes + j * WGMN_BLOCK_BYTES, bmap, full, n0 + 32 * j, w0 + b_dw, h0 + b_dh, nn0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, BN) | (1u << 15) | (1u << 16);   // A and B MN-major
+            for (int i = 0; i < num_k; ++i) {
+                const int s = i % WG_STAGES;
+                const uint32_t ph = (i / WG_STAGES) & 1;
+                mbar_wait(smem_u32(&bars[s]), ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint64_t adesc = make_mnmajor_desc(a_addr, p.lbo16, p.sbo16, p.ltype);
+                const uint64_t bdesc = make_mnmajor_desc(a_addr + a_bytes, p.lbo16, p.sbo16, p.ltype);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)     // 8 pixels = 8 rows of 128 B = +1024 B = +64 in (addr >> 4)
+                    tc_mma_tf32(tmem_base, adesc + (uint64_t)(k * p.kstep16), bdesc + (uint64_t)(k * p.kstep16), idesc, (i | k) != 0);
                 tc_commit(smem_u32(&bars[WG_STAGES + s]));
             }
             tc_commit(smem_u32(&bars[2 * WG_STAGES]));
@@ -253,6 +396,107 @@ static int encode_planar(CUtensorMap* m, const float* base, int Wd, int Hd, int 
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+static int g_wgrad_mn = -1;
+extern "C" void fsv_set_wgrad_mn(int on) { g_wgrad_mn = on; }
+static bool wgrad_mn_enabled() {
+    if (g_wgrad_mn < 0) {
+        const char* e = getenv("FSV_WGRAD_MN");
+        g_wgrad_mn = e ? atoi(e) : 1;      // default: operands in place (MN-major); FSV_WGRAD_MN=0 selects the planar re-layout path
+    }
+    return g_wgrad_mn != 0;
+}
+
+static int encode_nhwc_box(CUtensorMap* m, const float* base, int C, long long ld, int Wd, int Hd, int N, long long sw, long long sh,
+                           long long sn, int PW, int PH, int PN) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sn * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)PW, (cuuint32_t)PH, (cuuint32_t)PN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    (void)ld;
+    CUresult r = fsv_get_encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// operands read in place (NHWC), no workspace use except a materialised x2 upsample
+static int wgrad_tc_mn(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, float* workspace, int accumulate, cudaStream_t st) {
+    const int taps = d->kh * d->kw;
+    if (!accumulate) FSV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * taps * d->Cin, st));
+    const float* xb = x + d->x_coff;
+    long long xld = d->x_ld;
+    if (d->up == 2) {     // dense boxes need the upsampled image: rebuild it in the workspace (HBM-cheap, not kept from forward)
+        float* xu = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        int rc = fsv_upsample2x_fwd(x + d->x_coff, xu, d->N, d->H / 2, d->W / 2, d->Cin, st);
+        if (rc) return rc;
+        FSV_REQUIRE(d->x_ld == d->Cin && d->x_coff == 0, "conv2d_wgrad_tc: up=2 needs a dense x");
+        xb = xu; xld = d->Cin;
+    }
+    WgMnParams p;
+    memset(&p, 0, sizeof(p));
+    p.ntaps = taps; p.Cin = d->Cin; p.Cout = d->Cout; p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
+    int PW = 1; while (PW * 2 <= d->Wo && PW < 32) PW *= 2;
+    int PH = 1; while (PH * 2 <= d->Ho && PW * PH * 2 <= 32) PH *= 2;
+    int PN = 32 / (PW * PH);
+    p.PW = PW; p.PH = PH; p.PN = PN;
+    p.nWB = fsv_cdiv(d->Wo, PW); p.nHB = fsv_cdiv(d->Ho, PH); p.nNB = fsv_cdiv(d->N, PN);
+    p.role = d->Cout >= d->Cin ? 0 : 1;
+    const int Mdim = p.role == 0 ? d->Cout : d->Cin, Ndim = p.role == 0 ? d->Cin : d->Cout;
+    p.BN = Ndim >= 128 ? 128 : ((Ndim + 31) / 32) * 32;
+    p.mtiles = fsv_cdiv(Mdim, TC_BM); p.ntiles = fsv_cdiv(Ndim, p.BN);
+    const long long yld = d->y_ld;
+    int rc = encode_nhwc_box(&p.dymap, dy + d->y_coff, d->Cout, yld, d->Wo, d->Ho, d->N, yld, yld * d->Wo, yld * d->Wo * d->Ho, PW, PH, PN);
+    FSV_REQUIRE(rc == 0, "conv2d_wgrad_tc(mn): cuTensorMapEncodeTiled(dy) failed with %d", rc);
+    if (d->stride == 1) {
+        rc = encode_nhwc_box(&p.xmap[0], xb, d->Cin, xld, d->W, d->H, d->N, xld, xld * d->W, xld * d->W * d->H, PW, PH, PN);
+        FSV_REQUIRE(rc == 0, "conv2d_wgrad_tc(mn): cuTensorMapEncodeTiled(x) failed with %d", rc);
+        for (int r = 0; r < d->kh; ++r)
+            for (int s2 = 0; s2 < d->kw; ++s2) {
+                WgTap& t = p.taps[r * d->kw + s2];
+                t.plane = 0; t.dh = r - d->pad; t.dw = s2 - d->pad;
+            }
+    } else {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                int Hd = (d->H - ph + 1) / 2, Wd = (d->W - pw + 1) / 2;
+                if (Hd < 1) Hd = 1;
+                if (Wd < 1) Wd = 1;
+                rc = encode_nhwc_box(&p.xmap[ph * 2 + pw], xb + ((long long)ph * d->W + pw) * xld, d->Cin, xld, Wd, Hd, d->N, 2 * xld,
+                                     2 * xld * d->W, xld * d->W * d->H, PW, PH, PN);
+                FSV_REQUIRE(rc == 0, "conv2d_wgrad_tc(mn): cuTensorMapEncodeTiled(x parity) failed with %d", rc);
+            }
+        for (int r = 0; r < d->kh; ++r)
+            for (int s2 = 0; s2 < d->kw; ++s2) {
+                WgTap& t = p.taps[r * d->kw + s2];
+                int qh = r - d->pad, qw = s2 - d->pad;
+                int ph = ((qh % 2) + 2) % 2, pw = ((qw % 2) + 2) % 2;
+                t.plane = ph * 2 + pw; t.dh = (qh - ph) / 2; t.dw = (qw - pw) / 2;
+            }
+    }
+    // validated on B200 by a parameter sweep (scripts/mn_sweep.sh, round 1): only this combination reproduces the reference
+    p.lbo16 = WGMN_BLOCK_BYTES >> 4;   // 4096 B between 32-channel blocks
+    p.sbo16 = 512 >> 4;                // 512 B between groups of 4 K rows
+    p.kstep16 = 1024 >> 4;             // 8 pixels (one tf32 MMA K step) = 8 rows x 128 B
+    p.ltype = 1;                       // SWIZZLE_128B_BASE32B
+    const int KB = p.nWB * p.nHB * p.nNB;
+    const long long base = (long long)taps * p.mtiles * p.ntiles;
+    long long splits = ((long long)fsv_sm_count() * 3 + base - 1) / base;
+    if (splits > KB / 8) splits = KB / 8;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (int)((KB + splits - 1) / splits);
+    splits = (KB + p.kb_per_split - 1) / p.kb_per_split;
+    const int smem_bytes = WG_STAGES * (4 * WGMN_BLOCK_BYTES + (p.BN / 32) * WGMN_BLOCK_BYTES) + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        FSV_CUDA(cudaFuncSetAttribute(k_wgrad_tc_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    dim3 grid((unsigned)splits, taps, p.mtiles * p.ntiles);
+    k_wgrad_tc_mn<<<grid, 192, smem_bytes, st>>>(p, dw);
+    FSV_CHECK_LAUNCH("conv2d_wgrad_tc_mn");
+    return FSV_OK;
+}
+
 extern "C" int fsv_conv2d_wgrad_tc(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, float* workspace,
                                    int accumulate, void* stream) {
     FSV_REQUIRE(d != nullptr && workspace != nullptr, "conv2d_wgrad_tc: null descriptor / workspace");
@@ -260,6 +504,9 @@ extern "C" int fsv_conv2d_wgrad_tc(const fsv_conv_desc* d, const float* x, const
         fsv_set_error("conv2d_wgrad_tc: shape not eligible for the tcgen05 path");
         return FSV_ENOTSUP;
     }
+    if (wgrad_mn_enabled() && d->x_ld % 4 == 0 && d->x_coff % 4 == 0 && d->y_ld % 4 == 0 && d->y_coff % 4 == 0 &&
+        (d->up == 1 || (d->x_ld == d->Cin && d->x_coff == 0)))
+        return wgrad_tc_mn(d, x, dy, dw, workspace, accumulate, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     WgGeom g = wg_geom(d);
     float* xT = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
