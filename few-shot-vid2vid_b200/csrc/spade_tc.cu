@@ -31,6 +31,10 @@ struct __align__(64) SpTcParams {
     int K[FSV_SPADE_MAX_MAPS], per_sample[FSV_SPADE_MAX_MAPS];
     int nmaps, N, H, W, C, up, instance, act;
     int TW, TH, TN, tiles_w, tiles_h;
+    // backward only
+    float* dgamma[FSV_SPADE_MAX_MAPS];
+    float* dbeta[FSV_SPADE_MAX_MAPS];
+    int dgb_ld[FSV_SPADE_MAX_MAPS];
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -39,10 +43,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int SP_CB>
-__global__ void __launch_bounds__(192, 2) k_spade_tc(const __grid_constant__ SpTcParams p, const float* __restrict__ x,
+template <int SP_CB, bool BWD>
+__global__ void __launch_bounds__(192, BWD ? 1 : 2) k_spade_tc(const __grid_constant__ SpTcParams p, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                     float* __restrict__ out) {
+                                                     float* __restrict__ out, const float* __restrict__ dout,
+                                                     float* __restrict__ dxhat) {
     constexpr int SP_STAGE_BYTES = SP_STAGE_BYTES_OF(SP_CB);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -121,7 +126,6 @@ __global__ void __launch_bounds__(192, 2) k_spade_tc(const __grid_constant__ SpT
             tc_commit(smem_u32(&bars[2 * SP_STAGES]));
         }
     } else {
-        // ===== epilogue: thread = pixel of the tile; while the MMAs run, fetch and normalise x
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int tw = row % p.TW, r2 = row / p.TW;
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(192, 2) k_spade_tc(const __grid_constant__ SpT
         const int n = n0 + tn, h = h0 + th, w = w0 + tw;
         const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
         const int Hs = p.H / p.up, Ws = p.W / p.up;
+        if constexpr (!BWD) {
+        // ===== forward epilogue: thread = pixel of the tile; while the MMAs run, fetch and normalise x
         float v[SP_CB];
         if (valid) {
             const float4* xr = reinterpret_cast<const float4*>(x + (((long long)n * Hs + h / p.up) * Ws + w / p.up) * p.C + c0);
@@ -174,6 +180,94 @@ __global__ void __launch_bounds__(192, 2) k_spade_tc(const __grid_constant__ SpT
                 orow[j] = make_float4(fsv_act(v[4 * j], p.act), fsv_act(v[4 * j + 1], p.act), fsv_act(v[4 * j + 2], p.act),
                                       fsv_act(v[4 * j + 3], p.act));
         }
+        } else {
+        // ===== backward epilogue: per 32-channel chunk, rebuild the modulation chain from gamma/beta in TMEM, then walk it
+        // backwards: dbeta_i = g, dgamma_i = g * v_{i-1}, g *= (1 + gamma_i); finally dxhat = g.
+        mbar_wait(smem_u32(&bars[2 * SP_STAGES]), 0);
+        tc_fence_after();
+        const long long pix = ((long long)n * p.H + h) * p.W + w;
+#pragma unroll 1
+        for (int c = 0; c < SP_CB; c += 32) {
+            float v[32], vprev[FSV_SPADE_MAX_MAPS][32];
+            if (valid) {
+                const float4* xr = reinterpret_cast<const float4*>(x + (((long long)n * Hs + h / p.up) * Ws + w / p.up) * p.C + c0 + c);
+                const float* mp = mean + (p.instance ? n * p.C : 0) + c0 + c;
+                const float* rp = rstd + (p.instance ? n * p.C : 0) + c0 + c;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 t = xr[j];
+                    float4 m = *reinterpret_cast<const float4*>(mp + 4 * j);
+                    float4 r = *reinterpret_cast<const float4*>(rp + 4 * j);
+                    v[4 * j + 0] = (t.x - m.x) * r.x; v[4 * j + 1] = (t.y - m.y) * r.y;
+                    v[4 * j + 2] = (t.z - m.z) * r.z; v[4 * j + 3] = (t.w - m.w) * r.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < FSV_SPADE_MAX_MAPS; ++i) {
+                if (i < p.nmaps) {
+                    const float* bgp = p.bg[i] ? p.bg[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
+                    const float* bbp = p.bb[i] ? p.bb[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
+                    uint32_t g[32], b[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * 2 * SP_CB + c);
+                    tc_ld32(taddr, g);
+                    tc_ld32(taddr + SP_CB, b);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float gv = __uint_as_float(g[j]) + ((bgp && valid) ? bgp[j] : 0.f);
+                        float bv = __uint_as_float(b[j]) + ((bbp && valid) ? bbp[j] : 0.f);
+                        vprev[i][j] = v[j];
+                        v[j] = v[j] * (1.f + gv) + bv;
+                    }
+                }
+            }
+            float gr[32];
+            if (valid) {
+                const float4* dr = reinterpret_cast<const float4*>(dout + pix * p.C + c0 + c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 t = dr[j];
+                    gr[4 * j + 0] = t.x; gr[4 * j + 1] = t.y; gr[4 * j + 2] = t.z; gr[4 * j + 3] = t.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (p.act == FSV_ACT_LRELU) gr[j] *= (v[j] > 0.f ? 1.f : FSV_LRELU_SLOPE);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) gr[j] = 0.f;
+            }
+#pragma unroll
+            for (int i = FSV_SPADE_MAX_MAPS - 1; i >= 0; --i) {
+                if (i < p.nmaps) {
+                    const float* bgp = p.bg[i] ? p.bg[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
+                    uint32_t g[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * 2 * SP_CB + c), g);
+                    if (valid) {
+                        float4* db = reinterpret_cast<float4*>(p.dbeta[i] + pix * p.dgb_ld[i] + c0 + c);
+                        float4* dg = reinterpret_cast<float4*>(p.dgamma[i] + pix * p.dgb_ld[i] + c0 + c);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            db[j] = make_float4(gr[4 * j], gr[4 * j + 1], gr[4 * j + 2], gr[4 * j + 3]);
+                            dg[j] = make_float4(gr[4 * j] * vprev[i][4 * j], gr[4 * j + 1] * vprev[i][4 * j + 1],
+                                                gr[4 * j + 2] * vprev[i][4 * j + 2], gr[4 * j + 3] * vprev[i][4 * j + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float gv = __uint_as_float(g[j]) + ((bgp && valid) ? bgp[j] : 0.f);
+                        gr[j] *= (1.f + gv);
+                    }
+                }
+            }
+            if (valid) {
+                float4* dxr = reinterpret_cast<float4*>(dxhat + pix * p.C + c0 + c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dxr[j] = make_float4(gr[4 * j], gr[4 * j + 1], gr[4 * j + 2], gr[4 * j + 3]);
+            }
+        }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -207,16 +301,16 @@ extern "C" int fsv_spade_fwd_tc_eligible(const fsv_spade_desc* d) {
     return fsv_get_encode_tiled() != nullptr ? 1 : 0;
 }
 
-extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
-                                const float* const* maps, const float* const* wg, const float* const* bg,
-                                const float* const* wb, const float* const* bb, float* out, void* stream) {
-    FSV_REQUIRE(d != nullptr, "spade_fwd_tc: null descriptor");
+static int spade_tc_launch(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
+                           const float* const* maps, const float* const* wg, const float* const* bg,
+                           const float* const* wb, const float* const* bb, float* out, const float* dout, float* dxhat,
+                           float* const* dgamma, float* const* dbeta, bool bwd, void* stream, const char* who) {
+    FSV_REQUIRE(d != nullptr, "%s: null descriptor", who);
     if (!fsv_spade_fwd_tc_eligible(d)) {
-        fsv_set_error("spade_fwd_tc: shape not eligible (need C%%32==0, K%%32==0)");
+        fsv_set_error("%s: shape not eligible (need C%%32==0, K%%32==0)", who);
         return FSV_ENOTSUP;
     }
-    FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0 && (((uintptr_t)mean) & 15) == 0 && (((uintptr_t)rstd) & 15) == 0,
-                "spade_fwd_tc: pointers must be 16-byte aligned");
+    FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)mean) & 15) == 0 && (((uintptr_t)rstd) & 15) == 0, "%s: pointers must be 16-byte aligned", who);
     const int CB = d->C % 64 == 0 ? 64 : 32;
     SpTcParams p;
     memset(&p, 0, sizeof(p));
@@ -226,12 +320,18 @@ extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const f
     const int tiles_n = fsv_cdiv(d->N, p.TN);
     PFN_encodeTiled enc = fsv_get_encode_tiled();
     for (int i = 0; i < d->nmaps; ++i) {
-        FSV_REQUIRE(maps[i] && wg[i] && wb[i], "spade_fwd_tc: map %d has null pointers", i);
+        FSV_REQUIRE(maps[i] && wg[i] && wb[i], "%s: map %d has null pointers", who, i);
         FSV_REQUIRE((((uintptr_t)(maps[i] + d->m_coff[i])) & 15) == 0 && (((uintptr_t)wg[i]) & 15) == 0 && (((uintptr_t)wb[i]) & 15) == 0,
-                    "spade_fwd_tc: map %d pointers must be 16-byte aligned", i);
+                    "%s: map %d pointers must be 16-byte aligned", who, i);
         p.K[i] = d->K[i];
         p.per_sample[i] = d->w_nstride[i] != 0;
         p.bg[i] = bg[i]; p.bb[i] = bb[i]; p.b_nstride[i] = d->w_nstride[i];
+        if (bwd) {
+            FSV_REQUIRE(dgamma[i] && dbeta[i], "%s: null dgamma/dbeta for map %d", who, i);
+            p.dgamma[i] = dgamma[i]; p.dbeta[i] = dbeta[i];
+            p.dgb_ld[i] = d->dgb_ld[i] > 0 ? d->dgb_ld[i] : d->C;
+            FSV_REQUIRE(p.dgb_ld[i] % 4 == 0 && (((uintptr_t)dgamma[i]) & 15) == 0 && (((uintptr_t)dbeta[i]) & 15) == 0, "%s: dgamma/dbeta alignment", who);
+        }
         const long long ld = d->m_ld[i];
         {
             cuuint64_t dims[4] = {(cuuint64_t)d->K[i], (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
@@ -241,7 +341,7 @@ extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const f
             CUresult r = enc(&p.mmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(maps[i] + d->m_coff[i]), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            FSV_REQUIRE(r == CUDA_SUCCESS, "spade_fwd_tc: cuTensorMapEncodeTiled(map %d) failed with %d", i, (int)r);
+            FSV_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(map %d) failed with %d", who, i, (int)r);
         }
         for (int which = 0; which < 2; ++which) {
             const float* wp = which == 0 ? wg[i] : wb[i];
@@ -254,19 +354,42 @@ extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const f
             CUresult r = enc(which == 0 ? &p.gmap[i] : &p.bmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)wp, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            FSV_REQUIRE(r == CUDA_SUCCESS, "spade_fwd_tc: cuTensorMapEncodeTiled(weights %d/%d) failed with %d", i, which, (int)r);
+            FSV_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(weights %d/%d) failed with %d", who, i, which, (int)r);
         }
     }
     const int smem_bytes = SP_STAGES * SP_STAGE_BYTES_OF(CB) + (2 * SP_STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {
-        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         configured = true;
     }
     dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->C / CB);
-    if (CB == 64) k_spade_tc<64><<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(p, x, mean, rstd, out);
-    else k_spade_tc<32><<<grid, 192, smem_bytes, (cudaStream_t)stream>>>(p, x, mean, rstd, out);
-    FSV_CHECK_LAUNCH("spade_fwd_tc");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!bwd) {
+        if (CB == 64) k_spade_tc<64, false><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, out, nullptr, nullptr);
+        else k_spade_tc<32, false><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, out, nullptr, nullptr);
+    } else {
+        if (CB == 64) k_spade_tc<64, true><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, nullptr, dout, dxhat);
+        else k_spade_tc<32, true><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, nullptr, dout, dxhat);
+    }
+    FSV_CHECK_LAUNCH(who);
     return FSV_OK;
+}
+
+extern "C" int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
+                                const float* const* maps, const float* const* wg, const float* const* bg,
+                                const float* const* wb, const float* const* bb, float* out, void* stream) {
+    FSV_REQUIRE((((uintptr_t)out) & 15) == 0, "spade_fwd_tc: out must be 16-byte aligned");
+    return spade_tc_launch(d, x, mean, rstd, maps, wg, bg, wb, bb, out, nullptr, nullptr, nullptr, nullptr, false, stream, "spade_fwd_tc");
+}
+
+extern "C" int fsv_spade_bwd_tc(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
+                                const float* const* maps, const float* const* wg, const float* const* bg,
+                                const float* const* wb, const float* const* bb, const float* dout,
+                                float* dxhat, float* const* dgamma, float* const* dbeta, void* stream) {
+    FSV_REQUIRE((((uintptr_t)dout) & 15) == 0 && (((uintptr_t)dxhat) & 15) == 0, "spade_bwd_tc: dout/dxhat must be 16-byte aligned");
+    return spade_tc_launch(d, x, mean, rstd, maps, wg, bg, wb, bb, nullptr, dout, dxhat, dgamma, dbeta, true, stream, "spade_bwd_tc");
 }

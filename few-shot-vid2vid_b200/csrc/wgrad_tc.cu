@@ -480,7 +480,8 @@ static int wgrad_tc_mn(const fsv_conv_desc* d, const float* x, const float* dy, 
     p.ltype = 1;                       // SWIZZLE_128B_BASE32B
     const int KB = p.nWB * p.nHB * p.nNB;
     const long long base = (long long)taps * p.mtiles * p.ntiles;
-    long long splits = ((long long)fsv_sm_count() * 3 + base - 1) / base;
+    // split-K: enough CTAs for ~1.5 waves; every extra split costs Cout*taps*Cin fp32 reductions into dW through L2
+    long long splits = ((long long)fsv_sm_count() * 3 / 2 + base - 1) / base;
     if (splits > KB / 8) splits = KB / 8;
     if (splits < 1) splits = 1;
     p.kb_per_split = (int)((KB + splits - 1) / splits);

@@ -63,6 +63,7 @@ SIGNATURES = {
     'fsv_spade_fwd': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp],
     'fsv_spade_fwd_tc_eligible': [_SD],
     'fsv_spade_fwd_tc': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp],
+    'fsv_spade_bwd_tc': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp, PtrArray, PtrArray, c_vp],
     'fsv_spade_bwd': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp, PtrArray, PtrArray, c_vp],
     'fsv_spade_norm_bwd': [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp],
     'fsv_warp_fwd': [c_vp] * 5 + [c_int] * 7 + [c_vp],

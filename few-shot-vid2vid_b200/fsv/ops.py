@@ -489,7 +489,8 @@ class SpadeFn(torch.autograd.Function):
                 dgs[i] = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
                 dbs[i] = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
                 pg[i], pb[i] = dgs[i].data_ptr(), dbs[i].data_ptr()
-        _call(lib.fsv_spade_bwd, ctypes.byref(d), ptr(x), ptr(mean), ptr(rstd), *arrays, ptr(dout), ptr(dxhat), pg, pb, st)
+        bwd = lib.fsv_spade_bwd_tc if (CONV_USE_TC != 0 and lib.fsv_spade_fwd_tc_eligible(ctypes.byref(d))) else lib.fsv_spade_bwd
+        _call(bwd, ctypes.byref(d), ptr(x), ptr(mean), ptr(rstd), *arrays, ptr(dout), ptr(dxhat), pg, pb, st)
         mode = cfg['mode']
         groups = n if mode == NORM_INSTANCE else 1
         batch_stats = 1 if (cfg['training'] or mode == NORM_INSTANCE) else 0

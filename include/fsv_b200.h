@@ -166,6 +166,10 @@ int fsv_spade_fwd_tc_eligible(const fsv_spade_desc* d);
 int fsv_spade_fwd_tc(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
                      const float* const* maps, const float* const* wg, const float* const* bg,
                      const float* const* wb, const float* const* bb, float* out, void* stream);
+int fsv_spade_bwd_tc(const fsv_spade_desc* d, const float* x, const float* mean, const float* rstd,
+                     const float* const* maps, const float* const* wg, const float* const* bg,
+                     const float* const* wb, const float* const* bb, const float* dout,
+                     float* dxhat, float* const* dgamma, float* const* dbeta, void* stream);
 /* Backward.  Recomputes gamma/beta and the pre-activation value (so `out` is not needed), walks the modulation chain backwards and emits
  *   dxhat  (N,H,W,C): gradient w.r.t. the normalised activation (feed to fsv_spade_norm_bwd)
  *   dgamma[i], dbeta[i] (N,H,W,C each): gradients of the 1x1 conv outputs (feed to fsv_conv2d_dgrad/wgrad) */

@@ -206,5 +206,9 @@ def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N):
         assert l2_err(xg.grad.permute(0, 3, 1, 2), x.grad) < 1e-2          # kink-robust metric (TF32 forward vs fp32 recompute)
         for a, b in zip(mg, maps):
             assert l2_err(a.grad.permute(0, 3, 1, 2), b.grad) < 1e-2
+        for n_, p_ in mod.named_parameters():
+            assert l2_err(p_.grad, sd['s.' + n_].grad) < 1e-2, n_
+        if adaptive:
+            assert l2_err(fg.grad, flat.grad) < 1e-2
     finally:
         ops.CONV_USE_TC = old
