@@ -202,13 +202,17 @@ def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N):
         yg = mod(xg, mg, wloc, up=up, act=ops.ACT_LRELU)
         assert rel_err(yg.permute(0, 3, 1, 2), y) < TOL_TF32
         (yg * to_nhwc(go.float().cuda())).sum().backward()
+        # Gradients: TF32 rounding of gamma/beta (~5e-4) flips the LeakyReLU slope of the ~0.1% of elements whose
+        # pre-activation is that close to zero; each flip changes that element's gradient by 80%, i.e. an L2 error of
+        # ~sqrt(1e-3) ~ 1-3% on random inputs.  (The exact-fp32 kernels are held to 1e-4 in test_gpu_ops.py.)
         from util import l2_err
-        assert l2_err(xg.grad.permute(0, 3, 1, 2), x.grad) < 1e-2          # kink-robust metric (TF32 forward vs fp32 recompute)
+        GT = 3e-2
+        assert l2_err(xg.grad.permute(0, 3, 1, 2), x.grad) < GT
         for a, b in zip(mg, maps):
-            assert l2_err(a.grad.permute(0, 3, 1, 2), b.grad) < 1e-2
+            assert l2_err(a.grad.permute(0, 3, 1, 2), b.grad) < GT
         for n_, p_ in mod.named_parameters():
-            assert l2_err(p_.grad, sd['s.' + n_].grad) < 1e-2, n_
+            assert l2_err(p_.grad, sd['s.' + n_].grad) < GT, n_
         if adaptive:
-            assert l2_err(fg.grad, flat.grad) < 1e-2
+            assert l2_err(fg.grad, flat.grad) < GT
     finally:
         ops.CONV_USE_TC = old
