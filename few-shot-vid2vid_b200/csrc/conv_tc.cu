@@ -376,3 +376,57 @@ extern "C" int fsv_conv2d_dgrad_tc(const fsv_conv_desc* d, const float* dy, cons
     }
     return FSV_OK;
 }
+
+// ------------------------------------------------------------------ 3x3 conv over a nearest-x2-upsampled input, without the upsample
+// y = conv3x3(up2(x)).  An output pixel of parity (ph, pw) only ever sees a 2x2 neighbourhood of SOURCE pixels: the
+// three kernel rows collapse onto two source rows ({r0 | r1+r2} for even output rows, {r0+r1 | r2} for odd ones; same for
+// columns), so the layer is four stride-1 2x2-tap convolutions of the source image -- one per output parity, written
+// through the strided-output epilogue -- with pre-summed weights w4[co][ph][pw][a][b][ci] (built on the host side from
+// the 3x3 kernel; 16 "taps").  That is 4/9 of the MACs of the reference's Upsample -> Conv2d (generator.py:484,537) and no
+// 4x-size intermediate.
+extern "C" int fsv_conv2d_fwd_tc_up2_eligible(const fsv_conv_desc* d) {
+    if (!d || d->up != 2 || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1) return 0;
+    fsv_conv_desc t = *d;
+    t.up = 1;
+    return fsv_conv2d_tc_eligible(&t);
+}
+
+extern "C" int fsv_conv2d_fwd_tc_up2(const fsv_conv_desc* d, const float* x, const float* w4, const float* bias,
+                                     const float* residual, float* y, void* stream) {
+    FSV_REQUIRE(d != nullptr, "conv2d_fwd_tc_up2: null descriptor");
+    if (!fsv_conv2d_fwd_tc_up2_eligible(d)) {
+        fsv_set_error("conv2d_fwd_tc_up2: not eligible (need up=2, 3x3 stride 1 pad 1, Cin%%32==0, Cout%%16==0)");
+        return FSV_ENOTSUP;
+    }
+    FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w4) & 15) == 0 && (((uintptr_t)y) & 15) == 0, "conv2d_fwd_tc_up2: pointers must be 16-byte aligned");
+    const int Hs = d->H / 2, Ws = d->W / 2;
+    const int BN = pick_bn(d->Cout);
+    const long long ld = d->x_ld;
+    for (int cls = 0; cls < 4; ++cls) {
+        const int ph = cls >> 1, pw = cls & 1;
+        TcParams p;
+        memset(&p, 0, sizeof(p));
+        int TW, TH, TN;
+        pick_tile(Hs, Ws, TW, TH, TN);
+        p.TW = TW; p.TH = TH; p.TN = TN;
+        p.tiles_w = fsv_cdiv(Ws, TW); p.tiles_h = fsv_cdiv(Hs, TH);
+        const int tiles_n = fsv_cdiv(d->N, TN);
+        p.Cin = d->Cin; p.Cout = d->Cout; p.N = d->N; p.Ho = Hs; p.Wo = Ws;
+        p.OH = d->Ho; p.OW = d->Wo; p.os = 2; p.oph = ph; p.opw = pw;
+        p.y_ld = d->y_ld; p.y_coff = d->y_coff; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.act = d->act; p.out_scale = d->out_scale;
+        p.BN = BN;
+        p.ntaps = 4;
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+                TcTap& t = p.taps[a * 2 + b];
+                t.map = 0; t.dh = a + ph - 1; t.dw = b + pw - 1; t.wk = ((ph * 2 + pw) * 2 + a) * 2 + b;
+            }
+        int rc = encode_act_map(&p.amap[0], x + d->x_coff, d->Cin, d->x_ld, Ws, Hs, d->N, ld, ld * Ws, ld * Ws * Hs, TW, TH, TN);
+        FSV_REQUIRE(rc == 0, "conv2d_fwd_tc_up2: cuTensorMapEncodeTiled(A) failed with %d", rc);
+        rc = encode_weight_map(&p.bmap, w4, 16LL * d->Cin, d->Cout, BN);
+        FSV_REQUIRE(rc == 0, "conv2d_fwd_tc_up2: cuTensorMapEncodeTiled(B) failed with %d", rc);
+        rc = launch_tc(p, tiles_n, bias, residual, y, (cudaStream_t)stream, "conv2d_fwd_tc_up2");
+        if (rc) return rc;
+    }
+    return FSV_OK;
+}

@@ -231,6 +231,18 @@ def _conv_desc(n, h, w, cin, cout, kh, kw, stride, pad, up=1, act=ACT_NONE, out_
     return d
 
 
+_UP2_SEL = {}
+
+
+def _up2_selector(device):
+    """sel[parity][a][r]: which kernel rows r land on source-row offset a for an output row of that parity
+    (even rows: {r0} | {r1, r2};  odd rows: {r0, r1} | {r2})."""
+    key = str(device)
+    if key not in _UP2_SEL:
+        _UP2_SEL[key] = torch.tensor([[[1., 0., 0.], [0., 1., 1.]], [[1., 1., 0.], [0., 0., 1.]]], device=device)
+    return _UP2_SEL[key]
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = act(conv(x, w) + b + residual) * out_scale on NHWC.
 
@@ -249,19 +261,28 @@ class Conv2dFn(torch.autograd.Function):
                        up, cfg.get('act', ACT_NONE), cfg.get('out_scale', 1.0), cfg.get('w_nstride', 0), cfg.get('b_nstride', 0),
                        cfg.get('use_tc'), cfg.get('in_act', ACT_NONE))
         y = torch.empty((n, d.Ho, d.Wo, d.Cout), device=x.device, dtype=torch.float32)
-        xin, dcall = x, d
-        if up == 2 and d.use_tc != 0:
-            # the tcgen05 path reads dense TMA boxes: materialise the nearest upsample once (HBM-cheap next to the
-            # 9-tap conv it feeds) when that makes the layer tensor-core eligible; the weight gradient still reads x
-            # through the fused upsample-on-load, so only x (not its 4x copy) is kept for backward.
-            du = ConvDesc.from_buffer_copy(d)
-            du.up = 1
-            if lib.fsv_conv2d_tc_eligible(ctypes.byref(du)):
-                xin = torch.empty((n, d.H, d.W, cin), device=x.device, dtype=torch.float32)
-                _call(lib.fsv_upsample2x_fwd, ptr(x), ptr(xin), n, hs, ws, cin, stream())
-                dcall = du
-        _call(lib.fsv_conv2d_fwd, ctypes.byref(dcall), ptr(xin), _off(wbase, cfg.get('w_off', 0)),
-              None if bbase is None else _off(bbase, cfg.get('b_off', 0)), ptr(residual), ptr(y), stream())
+        done = False
+        if up == 2 and d.use_tc != 0 and cfg.get('w_off', 0) == 0 and lib.fsv_conv2d_fwd_tc_up2_eligible(ctypes.byref(d)):
+            # conv3x3(up2(x)) == four 2x2-tap convs of x (one per output parity) with row/column-summed weights:
+            # no 4x intermediate and 4/9 of the MACs.  Weight prep is a tiny parameter-side einsum.
+            with torch.no_grad():
+                w33 = wbase.reshape(d.Cout, 3, 3, d.Cin)
+                sel = _up2_selector(x.device)                                   # (parity, tap a, kernel row r)
+                w4 = torch.einsum('par,qbs,orsc->opqabc', sel, sel, w33).reshape(d.Cout, 16, d.Cin).contiguous()
+            _call(lib.fsv_conv2d_fwd_tc_up2, ctypes.byref(d), ptr(x), ptr(w4), None if bbase is None else _off(bbase, cfg.get('b_off', 0)),
+                  ptr(residual), ptr(y), stream())
+            done = True
+        if not done:
+            xin, dcall = x, d
+            if up == 2 and d.use_tc != 0:
+                du = ConvDesc.from_buffer_copy(d)
+                du.up = 1
+                if lib.fsv_conv2d_tc_eligible(ctypes.byref(du)):
+                    xin = torch.empty((n, d.H, d.W, cin), device=x.device, dtype=torch.float32)
+                    _call(lib.fsv_upsample2x_fwd, ptr(x), ptr(xin), n, hs, ws, cin, stream())
+                    dcall = du
+            _call(lib.fsv_conv2d_fwd, ctypes.byref(dcall), ptr(xin), _off(wbase, cfg.get('w_off', 0)),
+                  None if bbase is None else _off(bbase, cfg.get('b_off', 0)), ptr(residual), ptr(y), stream())
         ctx.cfg, ctx.d = cfg, d
         ctx.has_b, ctx.has_r = bbase is not None, residual is not None
         ctx.same_base = bbase is not None and bbase.data_ptr() == wbase.data_ptr() and bbase.numel() == wbase.numel()

@@ -100,6 +100,12 @@ int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const float* dy, fl
                      int accumulate, void* stream);
 /* 1 if the tcgen05/TMA implicit-GEMM path can serve this descriptor (fwd) */
 int fsv_conv2d_tc_eligible(const fsv_conv_desc* d);
+/* y = conv3x3(nearest_up2(x)) without materialising the upsample: four 2x2-tap stride-1 convolutions of the source image (one
+ * per output parity) with host-pre-summed weights w4[co][ph][pw][a][b][ci] (Cout,16,Cin); d describes the conv at the
+ * upsampled resolution with up = 2.  4/9 of the MACs of Upsample -> Conv2d (generator.py:484,537). */
+int fsv_conv2d_fwd_tc_up2_eligible(const fsv_conv_desc* d);
+int fsv_conv2d_fwd_tc_up2(const fsv_conv_desc* d, const float* x, const float* w4, const float* bias,
+                          const float* residual, float* y, void* stream);
 /* Data gradient on the tcgen05/TMA kernel.  wt is the weight with its channel axes swapped: wt[ci][r][s][co]
  * (Cin, kh, kw, Cout).  Stride 1: one launch; stride 2: one launch per output parity class with a strided-output
  * epilogue.  dx is fully overwritten.  FSV_ENOTSUP when fsv_conv2d_dgrad_tc_eligible() is 0. */

@@ -216,3 +216,36 @@ def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N):
             assert l2_err(fg.grad, flat.grad) < GT
     finally:
         ops.CONV_USE_TC = old
+
+
+@pytest.mark.parametrize('N,Hs,Ws,Cin,Cout,act,has_r', [(2, 16, 16, 64, 32, 1, False), (1, 8, 8, 128, 64, 0, True), (2, 20, 12, 32, 48, 1, False),
+                                                        (3, 5, 7, 32, 32, 0, False)])
+def test_conv_tc_up2_forward_and_grads(N, Hs, Ws, Cin, Cout, act, has_r):
+    """conv3x3(nearest_up2(x)) as four parity 2x2-tap convs of x with pre-summed weights (no materialised upsample)."""
+    from fsv import ops, _lib
+    x = rnd(N, Cin, Hs, Ws).requires_grad_(True)
+    w = rnd(Cout, Cin, 3, 3, scale=0.1).requires_grad_(True)
+    b = rnd(Cout).requires_grad_(True)
+    y = F.conv2d(O.up2(x), w, b, padding=1)
+    r = rnd(*y.shape) if has_r else None
+    if has_r:
+        y = y + r
+    if act:
+        y = O.lrelu(y)
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    d = ops._conv_desc(N, 2 * Hs, 2 * Ws, Cin, Cout, 3, 3, 1, 1, 2)
+    assert _lib.lib.fsv_conv2d_fwd_tc_up2_eligible(d) == 1
+    xg = to_nhwc(x.detach().float().cuda()).requires_grad_(True)
+    wg = w.detach().float().cuda().requires_grad_(True)
+    bg = b.detach().float().cuda().requires_grad_(True)
+    rg = to_nhwc(r.float().cuda()) if has_r else None
+    n0 = ops.LAUNCHES[0]
+    yg = ops.conv2d(xg, wg.permute(0, 2, 3, 1).contiguous(), bg, pad=1, up=2, act=act, residual=rg, use_tc=-1)
+    assert ops.LAUNCHES[0] - n0 == 1          # one C-ABI call, no separate upsample kernel
+    assert rel_err(yg.permute(0, 3, 1, 2), y) < TOL_TF32
+    if not act:                                # (with LeakyReLU a TF32 sign flip at the kink dominates a max-norm comparison)
+        (yg * to_nhwc(go.float().cuda())).sum().backward()
+        assert grad_err(xg.grad.permute(0, 3, 1, 2), x.grad) < TOL_TF32
+        assert grad_err(wg.grad, w.grad) < TOL_TF32
+        assert grad_err(bg.grad, b.grad) < 1e-4
