@@ -37,6 +37,8 @@ struct __align__(64) TcParams {
     int y_ld, y_coff, res_ld, res_coff, act;
     float out_scale;
     int BN;
+    int w_per_sample;           // B operand: 3-D tensor map (K, rows, sample); tiles never span samples (TN == 1)
+    long long b_nstride;        // per-sample bias stride (floats), 0 = shared
     int OH, OW, os, oph, opw;   // output buffer dims and pixel stride/offset: pixel (ho,wo) of the GEMM lands at (ho*os+oph, wo*os+opw)
 };
 
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
                 const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
                 mbar_expect_tx(full, (uint32_t)stage_bytes);
                 tma_load_4d(a_dst, &p.amap[tap.map], full, cb * TC_BK, w0 + tap.dw, h0 + tap.dh, n0);
-                tma_load_2d(a_dst + TC_A_BYTES, &p.bmap, full, tap.wk * p.Cin + cb * TC_BK, co0);
+                tma_load_3d(a_dst + TC_A_BYTES, &p.bmap, full, tap.wk * p.Cin + cb * TC_BK, co0, p.w_per_sample ? n0 : 0);
             }
         }
     } else if (warp == 1) {
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
                         o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
                         o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
                         if (bias) {
-                            float4 b = *reinterpret_cast<const float4*>(bias + co0 + c + j);
+                            float4 b = *reinterpret_cast<const float4*>(bias + (long long)n * p.b_nstride + co0 + c + j);
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
                         if (rrow) {
@@ -231,12 +233,14 @@ static void pick_tile(int Ho, int Wo, int& TW, int& TH, int& TN) {
     }
 }
 
-static int encode_weight_map(CUtensorMap* m, const float* w, long long kdim, int rows, int BN) {
-    cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)kdim * 4};
-    cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr,
+static int encode_weight_map(CUtensorMap* m, const float* w, long long kdim, int rows, int BN, int nsamples = 1, long long nstride = 0) {
+    // (K, rows, sample): shared weights are the 1-sample case
+    if (nsamples <= 1 || nstride == 0) { nsamples = 1; nstride = kdim * rows; }
+    cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)rows, (cuuint64_t)nsamples};
+    cuuint64_t strides[2] = {(cuuint64_t)kdim * 4, (cuuint64_t)nstride * 4};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
@@ -316,7 +320,12 @@ extern "C" int fsv_conv2d_fwd_tc(const fsv_conv_desc* d, const float* x, const f
 //             and writes its quarter of dx through the strided-output epilogue.
 extern "C" int fsv_conv2d_dgrad_tc_eligible(const fsv_conv_desc* d) {
     if (!d) return 0;
-    if (d->up != 1 || d->w_nstride != 0) return 0;
+    if (d->up != 1) return 0;
+    if (d->w_nstride != 0) {   // per-sample weights: wt is (N, Cin, taps, Cout) and a tile must stay inside one sample
+        int TW, TH, TN;
+        pick_tile(d->stride == 1 ? d->H : (d->H + 1) / 2, d->stride == 1 ? d->W : (d->W + 1) / 2, TW, TH, TN);
+        if (TN != 1 || d->stride != 1) return 0;
+    }
     if (d->Cout % TC_BK != 0 || d->y_coff % 4 != 0 || d->y_ld % 4 != 0) return 0;
     if (pick_bn(d->Cin) == 0 || d->x_ld % 4 != 0 || d->x_coff % 4 != 0) return 0;
     if (d->kh * d->kw > TC_MAX_TAPS) return 0;
@@ -369,7 +378,9 @@ extern "C" int fsv_conv2d_dgrad_tc(const fsv_conv_desc* d, const float* dy, cons
         }
         int rc = encode_act_map(&p.amap[0], dyb, d->Cout, d->y_ld, d->Wo, d->Ho, d->N, ld, ld * d->Wo, ld * d->Wo * d->Ho, TW, TH, TN);
         FSV_REQUIRE(rc == 0, "conv2d_dgrad_tc: cuTensorMapEncodeTiled(A) failed with %d", rc);
-        rc = encode_weight_map(&p.bmap, wt, (long long)taps_all * d->Cout, d->Cin, BN);
+        p.w_per_sample = d->w_nstride != 0;
+        rc = encode_weight_map(&p.bmap, wt, (long long)taps_all * d->Cout, d->Cin, BN, p.w_per_sample ? d->N : 1,
+                               (long long)taps_all * d->Cout * d->Cin);
         FSV_REQUIRE(rc == 0, "conv2d_dgrad_tc: cuTensorMapEncodeTiled(B) failed with %d", rc);
         rc = launch_tc(p, tiles_n, nullptr, nullptr, dx, (cudaStream_t)stream, "conv2d_dgrad_tc");
         if (rc) return rc;

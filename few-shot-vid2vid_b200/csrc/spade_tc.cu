@@ -37,12 +37,6 @@ struct __align__(64) SpTcParams {
     int dgb_ld[FSV_SPADE_MAX_MAPS];
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-
 template <int SP_CB, bool BWD>
 __global__ void __launch_bounds__(192, BWD ? 1 : 2) k_spade_tc(const __grid_constant__ SpTcParams p, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,

@@ -165,6 +165,8 @@ struct __align__(64) WgMnParams {
     int ntaps, Cin, Cout, N, Ho, Wo;
     int PW, PH, PN, nWB, nHB, nNB;
     int role, BN, mtiles, ntiles, kb_per_split;
+    int per_sample, KBs, spn;          // per-sample weights: K blocks per sample, splits per sample (grid.x = N * spn)
+    long long dw_nstride;
     int lbo16, sbo16, kstep16, ltype;   // descriptor fields in 16-byte units (tunable while bringing the layout up)
 };
 
@@ -192,8 +194,14 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ 
     const int mt = blockIdx.z / p.ntiles, nt = blockIdx.z - mt * p.ntiles;
     const int m0 = mt * TC_BM, n0 = nt * BN;
     const int KB = p.nWB * p.nHB * p.nNB;
-    const int kb0 = blockIdx.x * p.kb_per_split;
-    const int kb1 = min(kb0 + p.kb_per_split, KB);
+    int kb0 = blockIdx.x * p.kb_per_split;
+    int kb1 = min(kb0 + p.kb_per_split, KB);
+    if (p.per_sample) {            // split-K chunks never straddle a sample; each sample reduces into its own dW
+        const int sn = blockIdx.x / p.spn, sj = blockIdx.x - sn * p.spn;
+        kb0 = sn * p.KBs + sj * p.kb_per_split;
+        kb1 = min(kb0 + p.kb_per_split, (sn + 1) * p.KBs);
+        dw += (long long)sn * p.dw_nstride;
+    }
     const int num_k = kb1 - kb0;
     if (num_k <= 0) return;
 
@@ -341,6 +349,7 @@ static int launch_to_planar(const float* src, float* dst, int N, int Hs, int Ws,
 }
 
 // ------------------------------------------------------------------ host side
+static bool wgrad_mn_enabled();
 static int wg_bn(int nsmall) {
     if (nsmall >= 128) return 128;
     if (nsmall % 16 == 0) return nsmall;
@@ -362,7 +371,13 @@ static WgGeom wg_geom(const fsv_conv_desc* d) {
 
 extern "C" int fsv_conv2d_wgrad_tc_eligible(const fsv_conv_desc* d) {
     if (!d) return 0;
-    if (d->w_nstride != 0 || d->in_act != FSV_ACT_NONE) return 0;
+    if (d->in_act != FSV_ACT_NONE) return 0;
+    if (d->w_nstride != 0) {      // per-sample dW: MN-major path only, and a 32-pixel K block must fit inside one sample
+        if (!wgrad_mn_enabled() || d->up != 1 || (long long)d->Ho * d->Wo < 32 || d->w_nstride % 4 != 0) return 0;
+        int PW = 1; while (PW * 2 <= d->Wo && PW < 32) PW *= 2;
+        int PH = 1; while (PH * 2 <= d->Ho && PW * PH * 2 <= 32) PH *= 2;
+        if (PW * PH != 32) return 0;
+    }
     if (d->stride != 1 && d->stride != 2) return 0;
     if (d->stride == 2 && d->up != 1) return 0;
     if (d->kh * d->kw > WG_MAX_TAPS || d->kw > 4) return 0;
@@ -422,7 +437,12 @@ static int encode_nhwc_box(CUtensorMap* m, const float* base, int C, long long l
 // operands read in place (NHWC), no workspace use except a materialised x2 upsample
 static int wgrad_tc_mn(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, float* workspace, int accumulate, cudaStream_t st) {
     const int taps = d->kh * d->kw;
-    if (!accumulate) FSV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * taps * d->Cin, st));
+    if (!accumulate) {
+        const size_t wsize = (size_t)d->Cout * taps * d->Cin;
+        if (d->w_nstride == 0) FSV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * wsize, st));
+        else if ((size_t)d->w_nstride == wsize) FSV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * wsize * d->N, st));
+        else FSV_CUDA(cudaMemset2DAsync(dw, sizeof(float) * d->w_nstride, 0, sizeof(float) * wsize, d->N, st));
+    }
     const float* xb = x + d->x_coff;
     long long xld = d->x_ld;
     if (d->up == 2) {     // dense boxes need the upsampled image: rebuild it in the workspace (HBM-cheap, not kept from forward)
@@ -486,6 +506,16 @@ static int wgrad_tc_mn(const fsv_conv_desc* d, const float* x, const float* dy, 
     if (splits < 1) splits = 1;
     p.kb_per_split = (int)((KB + splits - 1) / splits);
     splits = (KB + p.kb_per_split - 1) / p.kb_per_split;
+    if (d->w_nstride != 0) {
+        FSV_REQUIRE(PN == 1, "conv2d_wgrad_tc: per-sample weights need K blocks inside one sample");
+        p.per_sample = 1; p.dw_nstride = d->w_nstride; p.KBs = p.nWB * p.nHB;
+        long long spn = ((long long)fsv_sm_count() * 3 / 2 + base * d->N - 1) / (base * d->N);
+        if (spn > p.KBs / 8) spn = p.KBs / 8;
+        if (spn < 1) spn = 1;
+        p.kb_per_split = (int)((p.KBs + spn - 1) / spn);
+        p.spn = (int)((p.KBs + p.kb_per_split - 1) / p.kb_per_split);
+        splits = (long long)d->N * p.spn;
+    }
     const int smem_bytes = WG_STAGES * (4 * WGMN_BLOCK_BYTES + (p.BN / 32) * WGMN_BLOCK_BYTES) + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {

@@ -498,7 +498,19 @@ class SpadeFn(torch.autograd.Function):
         # fixed-weight maps get ONE interleaved (N,H,W,2C) [dgamma | dbeta] buffer so that their 1x1 data / weight gradients
         # are single GEMMs over 2C channels (tensor-core eligible); per-sample (hyper-weight) maps keep separate buffers
         # because their gamma / beta weights are not adjacent inside the hyper-network's flat output
-        fused = [mc.get('nstride', 0) == 0 for mc in cfg['maps']]
+        # plan per map: 'fixed' (shared weights), 'ps_tc' (per-sample hyper-weights, tcgen05 GEMMs), 'ps' (per-sample, SIMT)
+        plan = []
+        for i, mc in enumerate(cfg['maps']):
+            if mc.get('nstride', 0) == 0:
+                plan.append('fixed')
+                continue
+            K = mc['K']
+            cdp = _conv_desc(n, h, w, K, 2 * c, 1, 1, 1, 0, 1, ACT_NONE, 1.0, 2 * c * K, 0, CONV_USE_TC)
+            cdp.x_ld = tensors[5 * i].shape[3]
+            ok = (CONV_USE_TC != 0 and lib.fsv_conv2d_dgrad_tc_eligible(ctypes.byref(cdp)) and
+                  lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(cdp)))
+            plan.append('ps_tc' if ok else 'ps')
+        fused = [pl != 'ps' for pl in plan]
         dgb, dgs, dbs = [None] * nm, [None] * nm, [None] * nm
         pg, pb = PtrArray(), PtrArray()
         for i in range(nm):
@@ -536,6 +548,26 @@ class SpadeFn(torch.autograd.Function):
             m = tensors[5 * i]
             K = mc['K']
             need_m = ctx.needs_input_grad[4 + 5 * i]
+            if plan[i] == 'ps_tc':
+                # per-sample hyper-weights on tcgen05: gather this map's [Wgamma ; Wbeta] into one (B, 2C, K) tensor (tiny),
+                # one data-gradient GEMM and one weight-gradient GEMM per map, then scatter dW back into the flat layout
+                flat = tensors[5 * i + 1]
+                go, bo = mc.get('wg_off', 0), mc.get('wb_off', 0)
+                wcat = torch.cat([flat[:, go:go + c * K].reshape(n, c, K), flat[:, bo:bo + c * K].reshape(n, c, K)], 1).contiguous()
+                cd = _conv_desc(n, h, w, K, 2 * c, 1, 1, 1, 0, 1, ACT_NONE, 1.0, 2 * c * K, 0, CONV_USE_TC)
+                cd.x_ld = m.shape[3]
+                if need_m:
+                    dm = torch.empty_like(m)
+                    _call(lib.fsv_conv2d_dgrad_tc, ctypes.byref(cd), ptr(dgb[i]), ptr(wcat.transpose(1, 2).contiguous()), ptr(dm), st)
+                    grads[5 * i] = dm
+                if ctx.needs_input_grad[4 + 5 * i + 1]:
+                    dwcat = torch.empty((n, 2 * c, K), device=dev, dtype=torch.float32)
+                    ws = torch.empty(int(lib.fsv_conv2d_wgrad_tc_workspace(ctypes.byref(cd))) // 4 + 64, device=dev, dtype=torch.float32)
+                    _call(lib.fsv_conv2d_wgrad_tc, ctypes.byref(cd), ptr(m), ptr(dgb[i]), ptr(dwcat), ptr(ws), 0, st)
+                    gflat = buf_for(5 * i + 1)
+                    gflat[:, go:go + c * K] += dwcat[:, :c].reshape(n, c * K)
+                    gflat[:, bo:bo + c * K] += dwcat[:, c:].reshape(n, c * K)
+                continue
             if fused[i]:
                 wg_t, bg_t, wb_t, bb_t = tensors[5 * i + 1:5 * i + 5]
                 cd = _conv_desc(n, h, w, K, 2 * c, 1, 1, 1, 0, 1, ACT_NONE, 1.0, 0, 0, CONV_USE_TC)
