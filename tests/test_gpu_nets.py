@@ -181,3 +181,40 @@ def test_generator_matches_oracle_on_fresh_seeded_inputs():
     assert rel_err(out[1][0], ref[1][0]) < TOL
     assert rel_err(out[2][0], ref[2][0]) < TOL
     assert rel_err(out[4][0], ref[4][0]) < TOL
+
+
+def test_generator_tensor_core_path_vs_oracle():
+    """The default product path (tcgen05 TF32 convs / SPADE, CUDA-core thin layers) on a tensor-core-sized generator
+    (ngf 32 -> channels 32..256) against the CPU oracle on the same seeded weights and inputs.  Stated tolerance for the
+    TF32 path through ~40 layers: 1e-2 relative on the frames."""
+    from fsv import networks, ops
+    zg = load_npz('g_face_tiny.npz')
+    old = ops.CONV_USE_TC
+    ops.CONV_USE_TC = -1
+    try:
+        opt = opt_from(zg)
+        opt.gpu_ids = [0]
+        opt.ngf, opt.nff, opt.n_downsample_G, opt.n_adaptive_layers, opt.n_blocks_F = 32, 32, 3, 2, 2
+        torch.manual_seed(9)
+        G = networks.define_G(opt)
+        G.train()
+        sd = {k: v.detach().cpu().clone() for k, v in G.state_dict().items()}
+        g = torch.Generator().manual_seed(13)
+        B, H, W = 2, 64, 64
+        label = (torch.rand(B, 1, H, W, generator=g) < 0.05).float()
+        lref = (torch.rand(B, 1, 1, H, W, generator=g) < 0.05).float()
+        iref = torch.rand(B, 1, 3, H, W, generator=g) * 2 - 1
+        n0 = ops.LAUNCHES[0]
+        out = G(label.cuda(), lref.cuda(), iref.cuda())
+        (out[0].square().mean() + out[2][0].mean()).backward()
+        assert ops.LAUNCHES[0] > n0
+        opt_cpu = opt_from(zg)
+        opt_cpu.ngf, opt_cpu.nff, opt_cpu.n_downsample_G, opt_cpu.n_adaptive_layers, opt_cpu.n_blocks_F = 32, 32, 3, 2, 2
+        ref = ON.generator_forward(sd, opt_cpu, label, lref, iref, training=True)
+        assert rel_err(out[0], ref[0]) < 1e-2
+        assert rel_err(out[1][0], ref[1][0]) < 1e-2
+        assert rel_err(out[2][0], ref[2][0]) < 1e-2
+        assert rel_err(out[4][0], ref[4][0]) < 1e-2
+        assert all(torch.isfinite(p.grad).all() for p in G.parameters() if p.grad is not None)
+    finally:
+        ops.CONV_USE_TC = old
