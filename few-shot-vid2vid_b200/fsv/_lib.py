@@ -72,6 +72,9 @@ SIGNATURES = {
     'fsv_warp_bwd': [c_vp] * 9 + [c_int] * 7 + [c_vp],
     'fsv_softmax_rows_fwd': [c_vp, c_vp, c_ll, c_int, c_vp],
     'fsv_softmax_rows_bwd': [c_vp, c_vp, c_vp, c_ll, c_int, c_vp],
+    'fsv_spectral_workspace': [c_int, c_int],
+    'fsv_spectral_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp],
+    'fsv_spectral_bwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
 }
 
 
@@ -85,6 +88,7 @@ def _load():
         fn.argtypes = argtypes
         fn.restype = c_int
     lib.fsv_conv2d_wgrad_tc_workspace.restype = c_ll
+    lib.fsv_spectral_workspace.restype = c_ll
     lib.fsv_last_error.argtypes = []
     lib.fsv_last_error.restype = ctypes.c_char_p
     return lib

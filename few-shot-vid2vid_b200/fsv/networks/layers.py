@@ -2,13 +2,15 @@
 
 Every class keeps the attribute names (hence ``state_dict`` keys) of the reference module it
 stands in for, so reference checkpoints load unchanged; the forward bodies
-call the fsv C ABI through ``fsv.ops`` on NHWC activations.  Spectral normalisation stays the
-parameter-side ``torch.nn.utils.spectral_norm`` hook (buffers ``weight_orig/_u/_v``, one power
-iteration per training forward) exactly as the reference applies it.
+call the fsv C ABI through ``fsv.ops`` on NHWC activations.  Spectral normalisation keeps the
+``torch.nn.utils.spectral_norm`` registration (parameter ``weight_orig``, buffers ``weight_u/_v``, state_dict
+hooks) exactly as the reference applies it, but the per-forward weight computation (one power iteration in
+training mode) runs in ``fsv_spectral_fwd/bwd`` instead of the ~20-launch torch hook.
 """
 import torch
 import torch.nn as nn
 from torch.nn.utils import spectral_norm as _sn
+from torch.nn.utils.spectral_norm import SpectralNorm as _SNHook
 
 from .. import ops
 from ..ops import ACT_NONE, ACT_LRELU, NORM_BATCH, NORM_INSTANCE
@@ -26,6 +28,8 @@ class Conv2d(nn.Module):
         nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
 
     def ohwi(self):
+        if getattr(self, 'fsv_spectral', False):
+            return ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v, self.training, self.fsv_spectral_eps)
         return self.weight.permute(0, 2, 3, 1).contiguous()
 
     def forward(self, x, up=1, act=ACT_NONE, residual=None, out_scale=1.0, in_act=ACT_NONE):
@@ -44,11 +48,25 @@ class Linear(nn.Module):
         nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
 
     def forward(self, x, act=ACT_NONE):
-        return ops.linear(x, self.weight, self.bias, act=act)
+        if getattr(self, 'fsv_spectral', False):
+            w = ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v, self.training, self.fsv_spectral_eps)
+        else:
+            w = self.weight
+        return ops.linear(x, w, self.bias, act=act)
 
 
 def spectral(module):
-    return _sn(module)
+    """torch.nn.utils.spectral_norm(module) as the reference calls it (default name 'weight', 1 power iteration, eps
+    1e-12, dim 0): same parameter / buffer registration, initial u / v draw and state_dict hooks; the forward-pre-hook
+    that recomputes ``module.weight`` is dropped -- Conv2d / Linear call ``ops.spectral_weight`` on
+    ``weight_orig/_u/_v`` themselves (``module.weight`` is therefore a stale construction-time tensor: do not read it)."""
+    _sn(module)
+    for key, hook in list(module._forward_pre_hooks.items()):
+        if isinstance(hook, _SNHook):
+            module.fsv_spectral_eps = hook.eps
+            del module._forward_pre_hooks[key]
+    module.fsv_spectral = True
+    return module
 
 
 class BatchNorm(nn.Module):

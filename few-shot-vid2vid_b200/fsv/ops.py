@@ -374,6 +374,43 @@ def linear(x2d, w, bias, act=ACT_NONE):
     return y.reshape(rows, w.shape[0])
 
 
+# --------------------------------------------------------------------------- spectral normalisation of weights
+
+class SpectralWeightFn(torch.autograd.Function):
+    """torch.nn.utils.spectral_norm's weight computation (one power iteration in training mode, ``weight_u/_v`` advanced
+    in place) fused with the OIHW -> OHWI repack: weight_orig (R, Cin[, kh, kw]) -> W / sigma as (R[, kh, kw], Cin)."""
+
+    @staticmethod
+    def forward(ctx, w_orig, u, v, training, eps):
+        w = _c(w_orig)
+        _lib.require_cuda(u, v)
+        R, cin = w.shape[0], w.shape[1]
+        taps = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
+        K = cin * taps
+        out = torch.empty((R, w.shape[2], w.shape[3], cin) if w.dim() == 4 else (R, cin), device=w.device, dtype=torch.float32)
+        uvs = torch.empty(K + R + 1, device=w.device, dtype=torch.float32)
+        work = torch.empty(lib.fsv_spectral_workspace(R, K) // 4, device=w.device, dtype=torch.float32)
+        _call(lib.fsv_spectral_fwd, ptr(w), ptr(u), ptr(v), R, cin, taps, 1 if training else 0, float(eps), ptr(out), ptr(uvs),
+              ptr(work), stream())
+        ctx.save_for_backward(out, uvs)
+        ctx.dims = (R, cin, taps, tuple(w_orig.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        out, uvs = ctx.saved_tensors
+        R, cin, taps, shape = ctx.dims
+        dout = _c(dout)
+        dw = torch.empty(shape, device=dout.device, dtype=torch.float32)
+        work = torch.empty(lib.fsv_spectral_workspace(R, cin * taps) // 4, device=dout.device, dtype=torch.float32)
+        _call(lib.fsv_spectral_bwd, ptr(dout), ptr(out), ptr(uvs), R, cin, taps, ptr(dw), ptr(work), stream())
+        return dw, None, None, None, None
+
+
+def spectral_weight(w_orig, u, v, training, eps=1e-12):
+    return SpectralWeightFn.apply(w_orig, u, v, training, eps)
+
+
 # --------------------------------------------------------------------------- normalisation (+ activation)
 
 def _stats(x, n, hw, c, mode, training, running_mean, running_var, eps, momentum, unbias_mul=1):

@@ -369,3 +369,44 @@ def test_spade_resblock(fin, fout, Hs, up):
             assert p_.grad is None or float(p_.grad.abs().max()) == 0.0, n_
         else:
             assert grad_err(p_.grad, r) < TOL, n_
+
+
+# --------------------------------------------------------------------------- spectral norm (fsv_spectral_fwd/bwd)
+
+@pytest.mark.parametrize('R,cin,k', [(64, 32, 3), (32, 3, 3), (257, 128, 1), (514, 512, 1), (1024, 1024, 3), (512, 256, 4),
+                                     (1, 64, 4), (7, 5, 1)])
+@pytest.mark.parametrize('training', [True, False])
+def test_spectral_weight_vs_oracle(R, cin, k, training):
+    """Fused power iteration + W/sigma + OHWI repack against the oracle's restatement of torch.nn.utils.spectral_norm
+    (oracle/ops.py:spectral_weight): weight, advanced u / v buffers and the weight_orig gradient; two consecutive calls
+    (the discriminator is called several times per step) with the FIRST call's backward taken after the second call."""
+    from fsv import ops
+    from oracle import ops as OO
+    g = torch.Generator().manual_seed(R * 31 + cin + k)
+    shape = (R, cin, k, k) if k > 1 else (R, cin)
+    w = torch.randn(shape, generator=g) * 0.05
+    u = torch.nn.functional.normalize(torch.randn(R, generator=g), dim=0)
+    v = torch.nn.functional.normalize(torch.randn(cin * k * k, generator=g), dim=0)
+    g1 = torch.randn(shape, generator=g)
+    g2 = torch.randn(shape, generator=g)
+    sd = {'m.weight_orig': w.clone().requires_grad_(True), 'm.weight_u': u.clone(), 'm.weight_v': v.clone()}
+    r1 = OO.spectral_weight(sd, 'm', training)
+    r2 = OO.spectral_weight(sd, 'm', training)
+    (gr1,) = torch.autograd.grad((r1 * g1).sum(), sd['m.weight_orig'])
+    (gr2,) = torch.autograd.grad((r2 * g2).sum(), sd['m.weight_orig'])
+
+    wc = w.cuda().requires_grad_(True)
+    uc, vc = u.cuda(), v.cuda()
+    perm = (lambda t: t.permute(0, 2, 3, 1)) if k > 1 else (lambda t: t)
+    o1 = ops.spectral_weight(wc, uc, vc, training)
+    o2 = ops.spectral_weight(wc, uc, vc, training)
+    assert o1.shape == perm(w).shape and o1.is_contiguous()
+    (gc1,) = torch.autograd.grad((o1 * perm(g1).cuda()).sum(), wc)
+    (gc2,) = torch.autograd.grad((o2 * perm(g2).cuda()).sum(), wc)
+    tol = 2e-5
+    assert rel_err(o1, perm(r1.detach())) < tol
+    assert rel_err(o2, perm(r2.detach())) < tol
+    assert rel_err(uc, sd['m.weight_u']) < tol and rel_err(vc, sd['m.weight_v']) < tol
+    assert rel_err(gc1, gr1) < 1e-4 and rel_err(gc2, gr2) < 1e-4
+    if not training:
+        assert torch.equal(uc.cpu(), u) and torch.equal(vc.cpu(), v)
