@@ -236,7 +236,11 @@ extern "C" int fsv_conv2d_dgrad(const fsv_conv_desc* d, const float* dy, const f
     int rc = fsv_conv_validate(d, "conv2d_dgrad");
     if (rc) return rc;
     FSV_REQUIRE(d->up == 1, "conv2d_dgrad: up must be 1 (take the gradient at conv-input resolution, then fsv_upsample2x_bwd)");
-    if (fsv_conv2d_dgrad_thin_ok(d) && (((uintptr_t)dy) & 15) == 0) return fsv_conv2d_dgrad_thin(d, dy, w, dx, accumulate, stream);
+    {
+        int tk = fsv_conv2d_dgrad_thin_ok(d);
+        if ((tk == 1 && (((uintptr_t)dy) & 15) == 0) || (tk == 2 && (((uintptr_t)dx) & 15) == 0 && (((uintptr_t)w) & 15) == 0))
+            return fsv_conv2d_dgrad_thin(d, dy, w, dx, accumulate, stream);
+    }
     ConvP p = make_p(d, accumulate);
     dim3 grid(fsv_cdiv((long long)d->H * d->W, BM), fsv_cdiv(d->Cin, BN), d->N);
     k_conv_simt<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p, dy, w, nullptr, nullptr, dx);
@@ -432,7 +436,7 @@ __global__ void k_colsum(const float* __restrict__ dy, int ld, int coff, long lo
 }
 
 extern "C" int fsv_conv2d_thin_kind(const fsv_conv_desc* d);
-extern "C" int fsv_conv2d_wgrad_thin(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, void* stream);
+extern "C" int fsv_conv2d_wgrad_thin(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, int* handled, void* stream);
 
 extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                                 int accumulate, void* stream) {
@@ -473,9 +477,10 @@ extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const fl
             goto bias_part;
         }
         if (fsv_conv2d_thin_kind(d) == 2) {
-            int trc = fsv_conv2d_wgrad_thin(d, x, dy, dw, stream);
+            int handled = 0;
+            int trc = fsv_conv2d_wgrad_thin(d, x, dy, dw, &handled, stream);
             if (trc) return trc;
-            goto bias_part;
+            if (handled) goto bias_part;
         }
         {
         int co_tiles = fsv_cdiv(d->Cout, BM), ci_tiles = fsv_cdiv(d->Cin, BN);

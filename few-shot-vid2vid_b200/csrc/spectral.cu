@@ -18,6 +18,8 @@
 #define SN_THREADS 256
 
 __device__ unsigned int g_sn_ticket[4];
+#define SN_MAXCHUNKS 4096
+__device__ unsigned int g_sn_colticket[SN_MAXCHUNKS];
 
 __device__ __forceinline__ float block_sum(float v, float* sh) {
     v = warp_sum(v);
@@ -46,10 +48,10 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket, unsigned int nb
     return last;
 }
 
-// phase 1: t = W^T u  (partials over row splits), last block: v = t / max(|t|, eps)
+// phase 1: t = W^T u.  Grid (column chunks, row splits); the last row-split block of each column chunk (one ticket per
+// chunk) folds that chunk's partials in a fixed order into t (kept in split 0's slot) and leaves the chunk's |t|^2.
 __global__ void __launch_bounds__(SN_THREADS) k_sn_wtu(const float* __restrict__ W, const float* __restrict__ u, int R, int K,
-                                                       int rows_per_split, float eps, float* part,
-                                                       float* __restrict__ v_buf, float* __restrict__ v_save) {
+                                                       int rows_per_split, float* part, float* __restrict__ nrm_part) {
     __shared__ float sh[SN_THREADS / 32];
     __shared__ int flag;
     int c = blockIdx.x * SN_THREADS + threadIdx.x;
@@ -66,51 +68,75 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_wtu(const float* __restrict__
         for (; r < r1; ++r) a0 = fmaf(W[(size_t)r * K + c], u[r], a0);
         part[(size_t)blockIdx.y * K + c] = (a0 + a1) + (a2 + a3);
     }
-    if (!last_block(&g_sn_ticket[0], gridDim.x * gridDim.y, &flag)) return;
-    // this block alone: reduce the partials (fixed order), normalise
+    if (!last_block(&g_sn_colticket[blockIdx.x], gridDim.y, &flag)) return;
     const volatile float* vp = part;
-    float nrm = 0.f;
-    for (int k = threadIdx.x; k < K; k += SN_THREADS) {
-        float t = 0.f;
-        for (int s = 0; s < (int)gridDim.y; ++s) t += vp[(size_t)s * K + k];
-        part[k] = t;       // split 0's slot now holds the full sum (each k touched by one thread only)
-        nrm += t * t;
+    float t = 0.f;
+    if (c < K) {
+        for (int s = 0; s < (int)gridDim.y; ++s) t += vp[(size_t)s * K + c];
+        part[c] = t;
     }
-    nrm = block_sum(nrm, sh);
-    float inv = 1.f / fmaxf(sqrtf(nrm), eps);
-    for (int k = threadIdx.x; k < K; k += SN_THREADS) {
-        float t = part[k] * inv;
-        v_buf[k] = t;
-        v_save[k] = t;
-    }
+    float nrm = block_sum(t * t, sh);
+    if (threadIdx.x == 0) nrm_part[blockIdx.x] = nrm;
 }
 
-// phase 2: s = W v (warp per row); last block: sigma, u
-__global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ W, const float* __restrict__ v, int R, int K, int power,
-                                                      float eps, float* s, float* u_buf,
-                                                      float* __restrict__ u_save, float* __restrict__ sigma) {
+// phase 2: v = t / max(|t|, eps) (training), s = W v (warp per row); last block: sigma, u
+__global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ W, const float* __restrict__ t, const float* __restrict__ nrm_part,
+                                                      int nchunks, int R, int K, int power, float eps, float* s, float* u_buf,
+                                                      float* __restrict__ u_save, float* __restrict__ v_buf, float* __restrict__ v_save,
+                                                      float* __restrict__ sigma) {
     __shared__ float sh[SN_THREADS / 32];
     __shared__ int flag;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float inv = 1.f;
+    if (power) {
+        float n = 0.f;
+        for (int i = threadIdx.x; i < nchunks; i += SN_THREADS) n += nrm_part[i];
+        n = block_sum(n, sh);
+        inv = 1.f / fmaxf(sqrtf(n), eps);
+    }
     int r = blockIdx.x * (SN_THREADS / 32) + warp;
     if (r < R) {
         const float* wr = W + (size_t)r * K;
         float a = 0.f;
         if ((K & 3) == 0) {
             const float4* w4 = reinterpret_cast<const float4*>(wr);
-            const float4* v4 = reinterpret_cast<const float4*>(v);
-            for (int k = lane; k < (K >> 2); k += 32) {
+            const float4* v4 = reinterpret_cast<const float4*>(t);
+            float b = 0.f;
+            int k = lane;
+            for (; k + 32 < (K >> 2); k += 64) {
+                float4 a4 = w4[k], b4 = v4[k], c4 = w4[k + 32], d4 = v4[k + 32];
+                a = fmaf(a4.x, b4.x, a);
+                a = fmaf(a4.y, b4.y, a);
+                a = fmaf(a4.z, b4.z, a);
+                a = fmaf(a4.w, b4.w, a);
+                b = fmaf(c4.x, d4.x, b);
+                b = fmaf(c4.y, d4.y, b);
+                b = fmaf(c4.z, d4.z, b);
+                b = fmaf(c4.w, d4.w, b);
+            }
+            for (; k < (K >> 2); k += 32) {
                 float4 a4 = w4[k], b4 = v4[k];
                 a = fmaf(a4.x, b4.x, a);
                 a = fmaf(a4.y, b4.y, a);
                 a = fmaf(a4.z, b4.z, a);
                 a = fmaf(a4.w, b4.w, a);
             }
+            a += b;
         } else {
-            for (int k = lane; k < K; k += 32) a = fmaf(wr[k], v[k], a);
+            for (int k = lane; k < K; k += 32) a = fmaf(wr[k], t[k], a);
         }
-        a = warp_sum(a);
+        a = warp_sum(a) * inv;
         if (lane == 0) s[r] = a;
+    }
+    // the normalised v: every block writes its slice (training: also into the weight_v buffer)
+    {
+        int per = (K + gridDim.x - 1) / gridDim.x;
+        int k0 = blockIdx.x * per, k1 = min(K, k0 + per);
+        for (int k = k0 + threadIdx.x; k < k1; k += SN_THREADS) {
+            float vv = t[k] * inv;
+            v_save[k] = vv;
+            if (power) v_buf[k] = vv;
+        }
     }
     if (!last_block(&g_sn_ticket[1], gridDim.x, &flag)) return;
     const volatile float* sv = s;
@@ -118,10 +144,10 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ 
         float nrm = 0.f;
         for (int i = threadIdx.x; i < R; i += SN_THREADS) nrm += sv[i] * sv[i];
         nrm = block_sum(nrm, sh);
-        float inv = 1.f / fmaxf(sqrtf(nrm), eps);
+        float invs = 1.f / fmaxf(sqrtf(nrm), eps);
         float sg = 0.f;
         for (int i = threadIdx.x; i < R; i += SN_THREADS) {
-            float un = sv[i] * inv;
+            float un = sv[i] * invs;
             u_buf[i] = un;
             u_save[i] = un;
             sg += un * sv[i];     // sigma = u_new . (W v)
@@ -140,17 +166,30 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ 
     }
 }
 
-// phase 3: W_sn (R, taps, Cin) = W (R, Cin, taps) / sigma
-__global__ void __launch_bounds__(SN_THREADS) k_sn_scale(const float* __restrict__ W, const float* __restrict__ sigma, int Cin, int taps,
-                                                         long long total, float* __restrict__ out) {
+// phase 3: W_sn (R, taps, Cin) = W (R, Cin, taps) / sigma.  Block = (SN_CI input channels of one row): a coalesced
+// read of the SN_CI*taps contiguous floats, transposed through shared memory (odd pitch), coalesced writes per tap.
+#define SN_CI 128
+#define SN_MAXTAPS 16
+__global__ void __launch_bounds__(SN_CI) k_sn_scale(const float* __restrict__ W, const float* __restrict__ sigma, int Cin, int taps,
+                                                    float* __restrict__ out) {
+    __shared__ float sm[SN_CI * (SN_MAXTAPS + 1)];
     float inv = 1.f / *sigma;
-    int K = Cin * taps;
-    for (long long i = (long long)blockIdx.x * SN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * SN_THREADS) {
-        long long r = i / K;
-        int k = (int)(i - r * K);
-        int t = k / Cin, ci = k - t * Cin;
-        out[i] = W[r * K + (long long)ci * taps + t] * inv;
+    int r = blockIdx.y, ci0 = blockIdx.x * SN_CI;
+    int nci = min(SN_CI, Cin - ci0);
+    size_t K = (size_t)Cin * taps;
+    if (taps == 1) {
+        if ((int)threadIdx.x < nci) out[r * K + ci0 + threadIdx.x] = W[r * K + ci0 + threadIdx.x] * inv;
+        return;
     }
+    int tp = taps | 1;
+    const float* src = W + r * K + (size_t)ci0 * taps;
+    for (int e = threadIdx.x; e < nci * taps; e += SN_CI) {
+        int j = e / taps, t = e - j * taps;
+        sm[j * tp + t] = src[e] * inv;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nci)
+        for (int t = 0; t < taps; ++t) out[r * K + (size_t)t * Cin + ci0 + threadIdx.x] = sm[threadIdx.x * tp + t];
 }
 
 // backward phase 1: c = sum dW_sn * W_sn  (both OHWI, contiguous)
@@ -171,18 +210,32 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_dot(const float* __restrict__
     if (threadIdx.x == 0) *c_out = t;
 }
 
-// backward phase 2: dW (R, Cin, taps) = (dW_sn (R, taps, Cin) - c u v^T) / sigma
-__global__ void __launch_bounds__(SN_THREADS) k_sn_bwd(const float* __restrict__ dws, const float* __restrict__ u, const float* __restrict__ v,
-                                                       const float* __restrict__ sigma, const float* __restrict__ c, int Cin, int taps,
-                                                       long long total, float* __restrict__ dw) {
-    float inv = 1.f / *sigma, cc = *c;
-    int K = Cin * taps;
-    for (long long i = (long long)blockIdx.x * SN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * SN_THREADS) {
-        long long r = i / K;
-        int k = (int)(i - r * K);         // OIHW column: ci * taps + t
-        int ci = k / taps, t = k - ci * taps;
-        float g = dws[r * K + (long long)t * Cin + ci];
-        dw[i] = (g - cc * u[r] * v[k]) * inv;
+// backward phase 2: dW (R, Cin, taps) = (dW_sn (R, taps, Cin) - c u v^T) / sigma; same tiling as k_sn_scale, transposing back
+__global__ void __launch_bounds__(SN_CI) k_sn_bwd(const float* __restrict__ dws, const float* __restrict__ u, const float* __restrict__ v,
+                                                  const float* __restrict__ sigma, const float* __restrict__ c, int Cin, int taps,
+                                                  float* __restrict__ dw) {
+    __shared__ float sm[SN_CI * (SN_MAXTAPS + 1)];
+    float inv = 1.f / *sigma;
+    int r = blockIdx.y, ci0 = blockIdx.x * SN_CI;
+    int nci = min(SN_CI, Cin - ci0);
+    size_t K = (size_t)Cin * taps;
+    float cu = *c * u[r];
+    if (taps == 1) {
+        if ((int)threadIdx.x < nci) {
+            size_t i = r * K + ci0 + threadIdx.x;
+            dw[i] = (dws[i] - cu * v[ci0 + threadIdx.x]) * inv;
+        }
+        return;
+    }
+    int tp = taps | 1;
+    if ((int)threadIdx.x < nci)
+        for (int t = 0; t < taps; ++t) sm[threadIdx.x * tp + t] = dws[r * K + (size_t)t * Cin + ci0 + threadIdx.x];
+    __syncthreads();
+    float* dst = dw + r * K + (size_t)ci0 * taps;
+    const float* vv = v + (size_t)ci0 * taps;
+    for (int e = threadIdx.x; e < nci * taps; e += SN_CI) {
+        int j = e / taps, t = e - j * taps;
+        dst[e] = (sm[j * tp + t] - cu * vv[e]) * inv;
     }
 }
 
@@ -200,45 +253,44 @@ static int sn_splits(int R, int K, int* rows_per_split) {
 extern "C" long long fsv_spectral_workspace(int R, int K) {
     int rps;
     int rs = sn_splits(R, K, &rps);
-    long long a = (long long)rs * K + R;   // forward: partials + s
-    long long b = 4096 + 1;                // backward: block partials + c
+    long long a = (long long)rs * K + R + fsv_cdiv(K, SN_THREADS);   // forward: partials (t in split 0) + s + per-chunk |t|^2
+    long long b = 4096 + 1;                                          // backward: block partials + c
     return (a > b ? a : b) * (long long)sizeof(float);
 }
 
 extern "C" int fsv_spectral_fwd(const float* w_orig, float* u, float* v, int R, int Cin, int taps, int power, float eps,
                                 float* w_out, float* uvs, float* work, void* stream) {
-    FSV_REQUIRE(R > 0 && Cin > 0 && taps > 0, "spectral_fwd: bad dims");
+    FSV_REQUIRE(R > 0 && R <= 65535 && Cin > 0 && taps > 0 && taps <= SN_MAXTAPS, "spectral_fwd: bad dims (R %d Cin %d taps %d)", R, Cin, taps);
     FSV_REQUIRE(w_orig && u && v && w_out && uvs && work, "spectral_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     int K = Cin * taps;
+    int nchunks = fsv_cdiv(K, SN_THREADS);
+    FSV_REQUIRE(nchunks <= SN_MAXCHUNKS, "spectral_fwd: K = %d too large", K);
     int rps;
     int rs = sn_splits(R, K, &rps);
     float* part = work;
     float* s = work + (size_t)rs * K;
+    float* nrm_part = s + R;
     float* v_save = uvs;            // uvs = [v (K) | u (R) | sigma]: v first keeps it 16-byte aligned for the float4 loads
     float* u_save = uvs + K;
     float* sigma = uvs + K + R;
     if (power) {
-        dim3 g(fsv_cdiv(K, SN_THREADS), rs);
-        k_sn_wtu<<<g, SN_THREADS, 0, st>>>(w_orig, u, R, K, rps, eps, part, v, v_save);
+        dim3 g(nchunks, rs);
+        k_sn_wtu<<<g, SN_THREADS, 0, st>>>(w_orig, u, R, K, rps, part, nrm_part);
         FSV_CHECK_LAUNCH("spectral_wtu");
-    } else {
-        FSV_CUDA(cudaMemcpyAsync(v_save, v, (size_t)K * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    k_sn_wv<<<fsv_cdiv(R, SN_THREADS / 32), SN_THREADS, 0, st>>>(w_orig, v_save, R, K, power, eps, s, u, u_save, sigma);
+    k_sn_wv<<<fsv_cdiv(R, SN_THREADS / 32), SN_THREADS, 0, st>>>(w_orig, power ? part : v, nrm_part, nchunks, R, K, power, eps, s, u, u_save,
+                                                                 v, v_save, sigma);
     FSV_CHECK_LAUNCH("spectral_wv");
-    long long total = (long long)R * K;
-    int blocks = (int)((total + SN_THREADS * 4 - 1) / (SN_THREADS * 4));
-    int cap = 8 * fsv_sm_count();
-    if (blocks > cap) blocks = cap;
-    k_sn_scale<<<blocks, SN_THREADS, 0, st>>>(w_orig, sigma, Cin, taps, total, w_out);
+    dim3 g3(fsv_cdiv(Cin, SN_CI), R);
+    k_sn_scale<<<g3, SN_CI, 0, st>>>(w_orig, sigma, Cin, taps, w_out);
     FSV_CHECK_LAUNCH("spectral_scale");
     return FSV_OK;
 }
 
 extern "C" int fsv_spectral_bwd(const float* dw_ohwi, const float* w_sn_ohwi, const float* uvs, int R, int Cin, int taps, float* dw_orig,
                                 float* work, void* stream) {
-    FSV_REQUIRE(R > 0 && Cin > 0 && taps > 0, "spectral_bwd: bad dims");
+    FSV_REQUIRE(R > 0 && R <= 65535 && Cin > 0 && taps > 0 && taps <= SN_MAXTAPS, "spectral_bwd: bad dims (R %d Cin %d taps %d)", R, Cin, taps);
     FSV_REQUIRE(dw_ohwi && w_sn_ohwi && uvs && dw_orig && work, "spectral_bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     int K = Cin * taps;
@@ -251,10 +303,8 @@ extern "C" int fsv_spectral_bwd(const float* dw_ohwi, const float* w_sn_ohwi, co
     float* c = work + 4096;
     k_sn_dot<<<blocks, SN_THREADS, 0, st>>>(dw_ohwi, w_sn_ohwi, total, part, c);
     FSV_CHECK_LAUNCH("spectral_dot");
-    int b2 = (int)((total + SN_THREADS * 4 - 1) / (SN_THREADS * 4));
-    int cap2 = 8 * fsv_sm_count();
-    if (b2 > cap2) b2 = cap2;
-    k_sn_bwd<<<b2, SN_THREADS, 0, st>>>(dw_ohwi, uvs + K, uvs, uvs + K + R, c, Cin, taps, total, dw_orig);
+    dim3 g2(fsv_cdiv(Cin, SN_CI), R);
+    k_sn_bwd<<<g2, SN_CI, 0, st>>>(dw_ohwi, uvs + K, uvs, uvs + K + R, c, Cin, taps, dw_orig);
     FSV_CHECK_LAUNCH("spectral_bwd");
     return FSV_OK;
 }

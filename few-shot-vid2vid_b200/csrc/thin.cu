@@ -8,9 +8,11 @@
 // Here every kernel streams the wide tensor exactly once with 16-byte accesses and keeps the thin side in
 // registers / shared memory:
 //   thin_cin_fwd   : one thread per output pixel, 32 output channels in registers, weights [tap][ci][co] in smem
-//   thin_cout_fwd  : one thread per output pixel, <=4 accumulators, float4 loads of the 32+ input channels
-//   thin_cin_wgrad : one warp per pixel chunk, lane = output channel, taps*Cin accumulators per lane
-//   thin_cout_wgrad: one warp per pixel chunk, lane = input channel, taps*Cout accumulators per lane
+//   thin_cin_dgrad : one thread per input pixel (<= 8 channels), float4 loads of the wide dy
+//   tco_fwd/dgrad/wgrad (Cout <= 4): work item = (pixel, 4-channel group) -- LPP lanes per pixel, so a warp reads
+//                    32/LPP neighbouring pixels x LPP float4 as ONE contiguous run (the first version had one thread
+//                    per pixel: every 16-byte load touched 32 different 128-byte lines and the kernels ran at ~1/10 of
+//                    HBM speed); blocks own 16x8-pixel tiles so the 3x3 / 4x4 halo re-reads hit L1
 // Roofline: HBM; algorithmic bytes = 4*(|x| + |y|) (+ weights, negligible).
 #include "common.cuh"
 
@@ -97,149 +99,199 @@ __global__ void __launch_bounds__(128) k_thin_cin_fwd(ThinP p, const float* __re
     }
 }
 
-// ------------------------------------------------------------------ Cout <= 4 forward (Cin % 4 == 0)
-__global__ void __launch_bounds__(128) k_thin_cout_fwd(ThinP p, const float* __restrict__ x, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, const float* __restrict__ residual,
-                                                       float* __restrict__ y) {
-    extern __shared__ float ws[];                 // [co][tap][ci]
-    const int taps = p.kh * p.kw;
-    const int wn = p.Cout * taps * p.Cin;
-    for (int i = threadIdx.x; i < wn; i += blockDim.x) ws[i] = w[i];
+// ------------------------------------------------------------------ Cout <= 4 ("thin output"), Cin % 4 == 0
+#define TT_W 16
+#define TT_H 8
+#define TT_THREADS 256
+
+__device__ __forceinline__ float4 lrelu4(float4 v) {
+    v.x = fsv_act(v.x, FSV_ACT_LRELU); v.y = fsv_act(v.y, FSV_ACT_LRELU);
+    v.z = fsv_act(v.z, FSV_ACT_LRELU); v.w = fsv_act(v.w, FSV_ACT_LRELU);
+    return v;
+}
+
+// forward: grid (x tiles, y tiles, N); weights [co][tap][ci] (= OHWI as stored) in shared memory
+template <int COUT>
+__global__ void __launch_bounds__(TT_THREADS) k_tco_fwd(ThinP p, int lpp, const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ residual,
+                                                        float* __restrict__ y) {
+    extern __shared__ __align__(16) float ws[];
+    const int taps = p.kh * p.kw, cin4 = p.Cin >> 2;
+    for (int i = threadIdx.x; i < COUT * taps * p.Cin; i += TT_THREADS) ws[i] = w[i];
     __syncthreads();
-    const long long total = (long long)p.N * p.Ho * p.Wo;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= total) return;
-    const int wo = (int)(pix % p.Wo);
-    const long long q = pix / p.Wo;
-    const int ho = (int)(q % p.Ho);
-    const long long n = q / p.Ho;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = 0; r < p.kh; ++r) {
-        int ih = ho * p.stride + r - p.pad;
-        if (ih < 0 || ih >= p.H) continue;
-        for (int s = 0; s < p.kw; ++s) {
-            int iw = wo * p.stride + s - p.pad;
-            if (iw < 0 || iw >= p.W) continue;
-            const float4* xp = reinterpret_cast<const float4*>(x + ((n * p.H + ih) * p.W + iw) * p.x_ld + p.x_coff);
-            const int tap = r * p.kw + s;
-            for (int c4 = 0; c4 < p.Cin / 4; ++c4) {
-                float4 xv = xp[c4];
-                if (p.in_act == FSV_ACT_LRELU) {
-                    xv.x = fsv_act(xv.x, FSV_ACT_LRELU); xv.y = fsv_act(xv.y, FSV_ACT_LRELU);
-                    xv.z = fsv_act(xv.z, FSV_ACT_LRELU); xv.w = fsv_act(xv.w, FSV_ACT_LRELU);
-                }
+    const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
+    const long long n = blockIdx.z;
+    const int h0 = blockIdx.y * TT_H, w0 = blockIdx.x * TT_W;
+    for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
+        const int ho = h0 + pidx / TT_W, wo = w0 + (pidx % TT_W);
+        const bool valid = ho < p.Ho && wo < p.Wo;
+        float acc[COUT];
 #pragma unroll
-                for (int co = 0; co < 4; ++co) {
-                    if (co < p.Cout) {
-                        float4 wv = *reinterpret_cast<const float4*>(ws + (co * taps + tap) * p.Cin + c4 * 4);
-                        acc[co] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+        if (valid) {
+            for (int r = 0; r < p.kh; ++r) {
+                const int ih = ho * p.stride + r - p.pad;
+                if (ih < 0 || ih >= p.H) continue;
+                for (int s = 0; s < p.kw; ++s) {
+                    const int iw = wo * p.stride + s - p.pad;
+                    if (iw < 0 || iw >= p.W) continue;
+                    const float4* xp = reinterpret_cast<const float4*>(x + ((n * p.H + ih) * p.W + iw) * p.x_ld + p.x_coff);
+                    const float* wt = ws + (r * p.kw + s) * p.Cin;
+                    for (int c4 = sub; c4 < cin4; c4 += lpp) {
+                        float4 xv = xp[c4];
+                        if (p.in_act == FSV_ACT_LRELU) xv = lrelu4(xv);
+#pragma unroll
+                        for (int co = 0; co < COUT; ++co) {
+                            const float4 wv = *reinterpret_cast<const float4*>(wt + co * taps * p.Cin + c4 * 4);
+                            acc[co] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+                        }
                     }
                 }
             }
         }
-    }
-    float* yp = y + pix * p.y_ld + p.y_coff;
-    const float* rp = residual ? residual + pix * p.res_ld + p.res_coff : nullptr;
+        for (int o = lpp >> 1; o > 0; o >>= 1)
 #pragma unroll
-    for (int co = 0; co < 4; ++co) {
-        if (co < p.Cout) {
-            float t = acc[co];
-            if (bias) t += bias[co];
-            if (rp) t += rp[co];
-            yp[co] = fsv_act(t, p.act) * p.out_scale;
-        }
-    }
-}
-
-// ------------------------------------------------------------------ Cin <= 8 weight gradient: lane = output channel
-// dw[co][tap][ci] += sum_px dy[px][co] * x[px shifted][ci];  TC = compile-time bound on taps*Cin
-template <int TC>
-__global__ void __launch_bounds__(128) k_thin_cin_wgrad(ThinP p, const float* __restrict__ x, const float* __restrict__ dy,
-                                                        float* __restrict__ dw, int pix_per_warp) {
-    const int lane = threadIdx.x & 31;
-    const int warp_g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int co = blockIdx.y * 32 + lane;
-    const int taps = p.kh * p.kw;
-    const int tc = taps * p.Cin;
-    const long long total = (long long)p.N * p.Ho * p.Wo;
-    long long px0 = (long long)warp_g * pix_per_warp;
-    long long px1 = px0 + pix_per_warp;
-    if (px1 > total) px1 = total;
-    float acc[TC];
+            for (int co = 0; co < COUT; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+        if (valid && sub == 0) {
+            const long long pix = (n * p.Ho + ho) * p.Wo + wo;
+            float* yp = y + pix * p.y_ld + p.y_coff;
+            const float* rp = residual ? residual + pix * p.res_ld + p.res_coff : nullptr;
 #pragma unroll
-    for (int i = 0; i < TC; ++i) acc[i] = 0.f;
-    for (long long px = px0; px < px1; ++px) {
-        const int wo = (int)(px % p.Wo);
-        const long long q = px / p.Wo;
-        const int ho = (int)(q % p.Ho);
-        const long long n = q / p.Ho;
-        const float dv = co < p.Cout ? dy[px * p.y_ld + p.y_coff + co] : 0.f;
-#pragma unroll
-        for (int i = 0; i < TC; ++i) {
-            if (i < tc) {
-                int tap = i / p.Cin, ci = i - tap * p.Cin;
-                int r = tap / p.kw, s = tap - r * p.kw;
-                int ih = ho * p.stride + r - p.pad, iw = wo * p.stride + s - p.pad;
-                float xv = 0.f;
-                if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) xv = x[((n * p.H + ih) * p.W + iw) * p.x_ld + p.x_coff + ci];
-                if (p.in_act == FSV_ACT_LRELU) xv = fsv_act(xv, FSV_ACT_LRELU);
-                acc[i] += dv * xv;
+            for (int co = 0; co < COUT; ++co) {
+                float t = acc[co];
+                if (bias) t += bias[co];
+                if (rp) t += rp[co];
+                yp[co] = fsv_act(t, p.act) * p.out_scale;
             }
         }
     }
-    if (co < p.Cout) {
+}
+
+// data gradient: dx[n,h,w,ci] = sum_{r,s,co} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,co] * w[co][r][s][ci]; tiles over (H, W)
+template <int COUT>
+__global__ void __launch_bounds__(TT_THREADS) k_tco_dgrad(ThinP p, int lpp, const float* __restrict__ dy, const float* __restrict__ w,
+                                                          float* __restrict__ dx, int accumulate) {
+    extern __shared__ __align__(16) float ws[];
+    const int taps = p.kh * p.kw, cin4 = p.Cin >> 2;
+    for (int i = threadIdx.x; i < COUT * taps * p.Cin; i += TT_THREADS) ws[i] = w[i];
+    __syncthreads();
+    const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
+    const long long n = blockIdx.z;
+    const int h0 = blockIdx.y * TT_H, w0 = blockIdx.x * TT_W;
+    for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
+        const int hq = h0 + pidx / TT_W, wq = w0 + (pidx % TT_W);
+        if (hq >= p.H || wq >= p.W) continue;
+        for (int c4 = sub; c4 < cin4; c4 += lpp) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < p.kh; ++r) {
+                const int th = hq + p.pad - r;
+                if (th < 0 || (th % p.stride) != 0) continue;
+                const int oh = th / p.stride;
+                if (oh >= p.Ho) continue;
+                for (int s = 0; s < p.kw; ++s) {
+                    const int tw = wq + p.pad - s;
+                    if (tw < 0 || (tw % p.stride) != 0) continue;
+                    const int ow = tw / p.stride;
+                    if (ow >= p.Wo) continue;
+                    const float* dp = dy + ((n * p.Ho + oh) * p.Wo + ow) * p.y_ld + p.y_coff;
+                    const float* wt = ws + (r * p.kw + s) * p.Cin + c4 * 4;
 #pragma unroll
-        for (int i = 0; i < TC; ++i)
-            if (i < tc) atomicAdd(dw + (long long)co * tc + i, acc[i]);
+                    for (int co = 0; co < COUT; ++co) {
+                        const float dv = dp[co];
+                        const float4 wv = *reinterpret_cast<const float4*>(wt + co * taps * p.Cin);
+                        acc.x += dv * wv.x; acc.y += dv * wv.y; acc.z += dv * wv.z; acc.w += dv * wv.w;
+                    }
+                }
+            }
+            float4* xp = reinterpret_cast<float4*>(dx + ((n * p.H + hq) * p.W + wq) * p.x_ld + p.x_coff) + c4;
+            if (accumulate) {
+                float4 o = *xp;
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            *xp = acc;
+        }
     }
 }
 
-// ------------------------------------------------------------------ Cout <= 4 weight gradient: lane = input channel
-template <int TAPS>
-__global__ void __launch_bounds__(128) k_thin_cout_wgrad(ThinP p, const float* __restrict__ x, const float* __restrict__ dy,
-                                                         float* __restrict__ dw, int pix_per_warp) {
-    const int lane = threadIdx.x & 31;
-    const int warp_g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int ci = blockIdx.y * 32 + lane;
-    const int taps = p.kh * p.kw;
-    const long long total = (long long)p.N * p.Ho * p.Wo;
-    long long px0 = (long long)warp_g * pix_per_warp;
-    long long px1 = px0 + pix_per_warp;
-    if (px1 > total) px1 = total;
-    float acc[TAPS][4];
+// weight gradient: dw[co][tap][ci] += sum_px dy[px][co] * x[px + tap][ci].  Persistent blocks walk the tiles; every thread
+// keeps taps x COUT float4 accumulators for its 4 channels; one warp-shuffle + shared-memory reduction per block, then
+// taps*COUT*Cin global atomics per block.  grid.y = channel groups of lpp*4 (only > 1 when Cin > 128).
+template <int TAPS, int COUT>
+__global__ void __launch_bounds__(TT_THREADS) k_tco_wgrad(ThinP p, int lpp, int tiles_x, int tiles_y, long long ntiles,
+                                                          const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw) {
+    __shared__ float red[TAPS * COUT * 128];
+    const int taps = p.kh * p.kw, cin4 = p.Cin >> 2;
+    const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
+    const int c4 = blockIdx.y * lpp + sub;
+    const bool cvalid = c4 < cin4;
+    float4 acc[TAPS][COUT];
 #pragma unroll
     for (int t = 0; t < TAPS; ++t)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
-    for (long long px = px0; px < px1; ++px) {
-        const int wo = (int)(px % p.Wo);
-        const long long q = px / p.Wo;
-        const int ho = (int)(q % p.Ho);
-        const long long n = q / p.Ho;
-        float dv[4];
+        for (int co = 0; co < COUT; ++co) acc[t][co] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long q = tile / tiles_x;
+        const int ty = (int)(q % tiles_y);
+        const long long n = q / tiles_y;
+        for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
+            const int ho = ty * TT_H + pidx / TT_W, wo = tx * TT_W + (pidx % TT_W);
+            if (!cvalid || ho >= p.Ho || wo >= p.Wo) continue;
+            const float* dp = dy + ((n * p.Ho + ho) * p.Wo + wo) * p.y_ld + p.y_coff;
+            float dv[COUT];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) dv[c] = c < p.Cout ? dy[px * p.y_ld + p.y_coff + c] : 0.f;
+            for (int co = 0; co < COUT; ++co) dv[co] = dp[co];
+            int r = 0, s = 0;
 #pragma unroll
-        for (int t = 0; t < TAPS; ++t) {
-            if (t < taps) {
-                int r = t / p.kw, s = t - r * p.kw;
-                int ih = ho * p.stride + r - p.pad, iw = wo * p.stride + s - p.pad;
-                float xv = 0.f;
-                if (ci < p.Cin && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
-                    xv = x[((n * p.H + ih) * p.W + iw) * p.x_ld + p.x_coff + ci];
-                if (p.in_act == FSV_ACT_LRELU) xv = fsv_act(xv, FSV_ACT_LRELU);
+            for (int t = 0; t < TAPS; ++t) {
+                if (t < taps) {
+                    const int ih = ho * p.stride + r - p.pad, iw = wo * p.stride + s - p.pad;
+                    if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                        float4 xv = reinterpret_cast<const float4*>(x + ((n * p.H + ih) * p.W + iw) * p.x_ld + p.x_coff)[c4];
+                        if (p.in_act == FSV_ACT_LRELU) xv = lrelu4(xv);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[t][c] += dv[c] * xv;
+                        for (int co = 0; co < COUT; ++co) {
+                            acc[t][co].x += dv[co] * xv.x; acc[t][co].y += dv[co] * xv.y;
+                            acc[t][co].z += dv[co] * xv.z; acc[t][co].w += dv[co] * xv.w;
+                        }
+                    }
+                    if (++s == p.kw) { s = 0; ++r; }
+                }
             }
         }
     }
-    if (ci < p.Cin) {
+    // lanes with the same sub (same channels) inside a warp
+    for (int o = lpp; o < 32; o <<= 1) {
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                acc[t][co].x += __shfl_xor_sync(0xffffffffu, acc[t][co].x, o);
+                acc[t][co].y += __shfl_xor_sync(0xffffffffu, acc[t][co].y, o);
+                acc[t][co].z += __shfl_xor_sync(0xffffffffu, acc[t][co].z, o);
+                acc[t][co].w += __shfl_xor_sync(0xffffffffu, acc[t][co].w, o);
+            }
+    }
+    const int row = lpp * 4;                      // channels this block covers
+    for (int i = threadIdx.x; i < TAPS * COUT * row; i += TT_THREADS) red[i] = 0.f;
+    __syncthreads();
+    if ((threadIdx.x & 31) < lpp && cvalid) {
 #pragma unroll
         for (int t = 0; t < TAPS; ++t)
             if (t < taps)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < p.Cout) atomicAdd(dw + ((long long)c * taps + t) * p.Cin + ci, acc[t][c]);
+                for (int co = 0; co < COUT; ++co) {
+                    float* rp = red + (t * COUT + co) * row + sub * 4;
+                    atomicAdd(rp + 0, acc[t][co].x); atomicAdd(rp + 1, acc[t][co].y);
+                    atomicAdd(rp + 2, acc[t][co].z); atomicAdd(rp + 3, acc[t][co].w);
+                }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < taps * COUT * row; i += TT_THREADS) {
+        const int cc = i % row, tc = i / row;
+        const int co = tc % COUT, t = tc / COUT;
+        const int ci = blockIdx.y * row + cc;
+        if (ci < p.Cin) atomicAdd(dw + ((long long)co * taps + t) * p.Cin + ci, red[i]);
     }
 }
 
@@ -304,9 +356,14 @@ static bool thin_common_ok(const fsv_conv_desc* d) {
 extern "C" int fsv_conv2d_thin_kind(const fsv_conv_desc* d) {
     if (!d || !thin_common_ok(d)) return 0;
     if (d->Cin <= 8 && d->Cout >= 16) return 1;                                         // thin input
-    if (d->Cout <= 4 && d->Cin >= 16 && d->Cin % 4 == 0 && d->x_ld % 4 == 0 && d->x_coff % 4 == 0 &&
+    if (d->Cout <= 4 && d->Cin >= 16 && d->Cin % 4 == 0 && d->x_ld % 4 == 0 && d->x_coff % 4 == 0 && d->N <= 65535 &&
         (long long)d->Cout * d->kh * d->kw * d->Cin * 4 <= 40 * 1024) return 2;         // thin output
     return 0;
+}
+static int tt_lpp(int cin) {
+    int l = 1;
+    while (l * 2 <= cin / 4 && l < 32) l *= 2;
+    return l;
 }
 
 extern "C" int fsv_conv2d_fwd_thin(const fsv_conv_desc* d, const float* x, const float* w, const float* bias,
@@ -314,59 +371,91 @@ extern "C" int fsv_conv2d_fwd_thin(const fsv_conv_desc* d, const float* x, const
     int kind = fsv_conv2d_thin_kind(d);
     FSV_REQUIRE(kind != 0, "conv2d_fwd_thin: not a thin layer");
     ThinP p = thin_p(d);
+    cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)d->N * d->Ho * d->Wo;
     const int taps = d->kh * d->kw;
     if (kind == 1) {
         dim3 grid(fsv_cdiv(total, 128), fsv_cdiv(d->Cout, 32));
-        k_thin_cin_fwd<<<grid, 128, taps * d->Cin * 32 * sizeof(float), (cudaStream_t)stream>>>(p, x, w, bias, residual, y);
+        k_thin_cin_fwd<<<grid, 128, taps * d->Cin * 32 * sizeof(float), st>>>(p, x, w, bias, residual, y);
     } else {
         FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w) & 15) == 0, "conv2d_fwd_thin: pointers must be 16-byte aligned");
-        dim3 grid(fsv_cdiv(total, 128));
-        k_thin_cout_fwd<<<grid, 128, (size_t)d->Cout * taps * d->Cin * sizeof(float), (cudaStream_t)stream>>>(p, x, w, bias, residual, y);
+        dim3 grid(fsv_cdiv(d->Wo, TT_W), fsv_cdiv(d->Ho, TT_H), d->N);
+        size_t sm = (size_t)d->Cout * taps * d->Cin * sizeof(float);
+        int lpp = tt_lpp(d->Cin);
+        switch (d->Cout) {
+            case 1: k_tco_fwd<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); break;
+            case 2: k_tco_fwd<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); break;
+            case 3: k_tco_fwd<3><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); break;
+            default: k_tco_fwd<4><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); break;
+        }
     }
     FSV_CHECK_LAUNCH("conv2d_fwd_thin");
     return FSV_OK;
 }
 
-// dw only (the bias gradient stays with the column-sum kernel of conv_simt.cu); dw must be zeroed by the caller
-extern "C" int fsv_conv2d_wgrad_thin(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, void* stream) {
-    int kind = fsv_conv2d_thin_kind(d);
-    FSV_REQUIRE(kind != 0, "conv2d_wgrad_thin: not a thin layer");
+// thin-output weight gradient (dw only; the bias gradient stays with the column-sum kernel of conv_simt.cu); dw must be
+// zeroed by the caller.  Returns FSV_OK with *handled = 0 when the (taps, Cout) pair has no instantiation.
+extern "C" int fsv_conv2d_wgrad_thin(const fsv_conv_desc* d, const float* x, const float* dy, float* dw, int* handled, void* stream) {
+    *handled = 0;
+    if (fsv_conv2d_thin_kind(d) != 2 || (((uintptr_t)x) & 15) != 0) return FSV_OK;
+    const int taps = d->kh * d->kw;
+    if (taps > 9 && d->Cout > 2) return FSV_OK;
     ThinP p = thin_p(d);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long total = (long long)d->N * d->Ho * d->Wo;
-    const int taps = d->kh * d->kw;
-    long long warps = (long long)fsv_sm_count() * 32;
-    int pix_per_warp = (int)((total + warps - 1) / warps);
-    if (pix_per_warp < 16) pix_per_warp = 16;
-    long long nwarps = (total + pix_per_warp - 1) / pix_per_warp;
-    dim3 block(128);
-    if (kind == 1) {
-        dim3 grid(fsv_cdiv(nwarps, 4), fsv_cdiv(d->Cout, 32));
-        int tc = taps * d->Cin;
-        if (tc <= 16) k_thin_cin_wgrad<16><<<grid, block, 0, st>>>(p, x, dy, dw, pix_per_warp);
-        else if (tc <= 48) k_thin_cin_wgrad<48><<<grid, block, 0, st>>>(p, x, dy, dw, pix_per_warp);
-        else k_thin_cin_wgrad<128><<<grid, block, 0, st>>>(p, x, dy, dw, pix_per_warp);
+    const int lpp = tt_lpp(d->Cin);
+    const int tiles_x = fsv_cdiv(d->Wo, TT_W), tiles_y = fsv_cdiv(d->Ho, TT_H);
+    const long long ntiles = (long long)tiles_x * tiles_y * d->N;
+    const int groups = fsv_cdiv(d->Cin / 4, lpp);
+    long long gx = (2LL * fsv_sm_count() + groups - 1) / groups;
+    if (gx > ntiles) gx = ntiles;
+    dim3 grid((unsigned)gx, groups);
+#define TCO_WGRAD(T, C) k_tco_wgrad<T, C><<<grid, TT_THREADS, 0, st>>>(p, lpp, tiles_x, tiles_y, ntiles, x, dy, dw)
+    if (taps <= 9) {
+        switch (d->Cout) {
+            case 1: TCO_WGRAD(9, 1); break;
+            case 2: TCO_WGRAD(9, 2); break;
+            case 3: TCO_WGRAD(9, 3); break;
+            default: TCO_WGRAD(9, 4); break;
+        }
     } else {
-        dim3 grid(fsv_cdiv(nwarps, 4), fsv_cdiv(d->Cin, 32));
-        if (taps <= 9) k_thin_cout_wgrad<9><<<grid, block, 0, st>>>(p, x, dy, dw, pix_per_warp);
-        else k_thin_cout_wgrad<16><<<grid, block, 0, st>>>(p, x, dy, dw, pix_per_warp);
+        if (d->Cout == 1) TCO_WGRAD(16, 1); else TCO_WGRAD(16, 2);
     }
+#undef TCO_WGRAD
     FSV_CHECK_LAUNCH("conv2d_wgrad_thin");
+    *handled = 1;
     return FSV_OK;
 }
 
+// kind 1: thin dx (Cin <= 8); kind 2: thin dy (Cout <= 4)
 extern "C" int fsv_conv2d_dgrad_thin_ok(const fsv_conv_desc* d) {
-    return d && d->up == 1 && d->w_nstride == 0 && d->Cin <= 8 && d->Cout >= 16 && d->Cout % 4 == 0 && d->y_ld % 4 == 0 &&
-           d->y_coff % 4 == 0 && d->kh * d->kw <= 16 && (long long)d->kh * d->kw * d->Cout * 8 * 4 <= 40 * 1024 &&
-           (long long)d->N * d->H * d->W >= 4096;
+    if (!d) return 0;
+    if (d->up == 1 && d->w_nstride == 0 && d->Cin <= 8 && d->Cout >= 16 && d->Cout % 4 == 0 && d->y_ld % 4 == 0 &&
+        d->y_coff % 4 == 0 && d->kh * d->kw <= 16 && (long long)d->kh * d->kw * d->Cout * 8 * 4 <= 40 * 1024 &&
+        (long long)d->N * d->H * d->W >= 4096) return 1;
+    if (fsv_conv2d_thin_kind(d) == 2) return 2;
+    return 0;
 }
 extern "C" int fsv_conv2d_dgrad_thin(const fsv_conv_desc* d, const float* dy, const float* w, float* dx, int accumulate, void* stream) {
-    FSV_REQUIRE(fsv_conv2d_dgrad_thin_ok(d), "conv2d_dgrad_thin: not eligible");
-    FSV_REQUIRE((((uintptr_t)dy) & 15) == 0, "conv2d_dgrad_thin: dy must be 16-byte aligned");
+    int kind = fsv_conv2d_dgrad_thin_ok(d);
+    FSV_REQUIRE(kind != 0, "conv2d_dgrad_thin: not eligible");
     ThinP p = thin_p(d);
-    const long long total = (long long)d->N * d->H * d->W;
-    k_thin_cin_dgrad<<<fsv_cdiv(total, 128), 128, (size_t)d->kh * d->kw * d->Cout * 8 * sizeof(float), (cudaStream_t)stream>>>(p, dy, w, dx, accumulate);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kind == 1) {
+        FSV_REQUIRE((((uintptr_t)dy) & 15) == 0, "conv2d_dgrad_thin: dy must be 16-byte aligned");
+        const long long total = (long long)d->N * d->H * d->W;
+        k_thin_cin_dgrad<<<fsv_cdiv(total, 128), 128, (size_t)d->kh * d->kw * d->Cout * 8 * sizeof(float), st>>>(p, dy, w, dx, accumulate);
+    } else {
+        FSV_REQUIRE((((uintptr_t)dx) & 15) == 0 && (((uintptr_t)w) & 15) == 0, "conv2d_dgrad_thin: pointers must be 16-byte aligned");
+        dim3 grid(fsv_cdiv(d->W, TT_W), fsv_cdiv(d->H, TT_H), d->N);
+        size_t sm = (size_t)d->Cout * d->kh * d->kw * d->Cin * sizeof(float);
+        int lpp = tt_lpp(d->Cin);
+        switch (d->Cout) {
+            case 1: k_tco_dgrad<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+            case 2: k_tco_dgrad<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+            case 3: k_tco_dgrad<3><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+            default: k_tco_dgrad<4><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+        }
+    }
     FSV_CHECK_LAUNCH("conv2d_dgrad_thin");
     return FSV_OK;
 }

@@ -64,6 +64,10 @@ CONV_CASES = [
     (2, 48, 48, 32, 1, 3, 1, 1, 1, 3, True, False),
     (4, 40, 40, 64, 2, 3, 1, 1, 1, 0, True, False),
     (16, 18, 18, 512, 1, 4, 1, 2, 1, 0, True, False),
+    (2, 50, 46, 32, 3, 3, 1, 1, 1, 2, True, False),     # ragged 16x8 tiles
+    (2, 66, 70, 16, 4, 4, 2, 1, 1, 0, True, False),     # stride 2, 16 taps x 4 outputs (generic wgrad)
+    (3, 40, 40, 48, 2, 3, 1, 1, 1, 0, False, True),     # Cin/4 = 12: not a power of two
+    (2, 48, 48, 160, 1, 1, 1, 0, 1, 0, True, False),    # 1x1, Cin > 128 (two channel groups in the wgrad)
 ]
 
 
