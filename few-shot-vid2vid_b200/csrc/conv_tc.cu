@@ -24,7 +24,7 @@
 #include "tc_common.cuh"
 
 #define TC_MAX_TAPS 16
-#define TC_STAGES 4
+#define TC_MAX_STAGES 8
 
 struct TcTap { int map, dh, dw, wk; };
 
@@ -39,6 +39,7 @@ struct __align__(64) TcParams {
     int BN;
     int w_per_sample;           // B operand: 3-D tensor map (K, rows, sample); tiles never span samples (TN == 1)
     long long b_nstride;        // per-sample bias stride (floats), 0 = shared
+    int stages;                 // smem ring depth (2..TC_MAX_STAGES)
     int OH, OW, os, oph, opw;   // output buffer dims and pixel stride/offset: pixel (ho,wo) of the GEMM lands at (ho*os+oph, wo*os+opw)
 };
 
@@ -49,10 +50,11 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
     // 1024-byte alignment for SWIZZLE_128B
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BN = p.BN;
+    const int STG = p.stages;
     const int b_bytes = BN * TC_BK * 4;
     const int stage_bytes = TC_A_BYTES + b_bytes;
-    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * stage_bytes);   // full[STAGES], empty[STAGES], tmem_full
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+    uint64_t* bars = (uint64_t*)(smem + STG * stage_bytes);   // full[STAGES], empty[STAGES], tmem_full
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STG + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile coordinates
@@ -66,11 +68,11 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
     const int num_k = p.ntaps * kblocks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < STG; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[TC_STAGES + s]), 1);
+            mbar_init(smem_u32(&bars[STG + s]), 1);
         }
-        mbar_init(smem_u32(&bars[2 * TC_STAGES]), 1);
+        mbar_init(smem_u32(&bars[2 * STG]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -89,9 +91,9 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
         if (lane == 0) {
             // ===== TMA producer
             for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
-                mbar_wait(smem_u32(&bars[TC_STAGES + s]), ph ^ 1);          // slot free
+                const int s = kb % STG;
+                const uint32_t ph = (kb / STG) & 1;
+                mbar_wait(smem_u32(&bars[STG + s]), ph ^ 1);          // slot free
                 const int t = kb / kblocks, cb = kb - t * kblocks;
                 const TcTap tap = p.taps[t];
                 const uint32_t full = smem_u32(&bars[s]);
@@ -106,8 +108,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
             // ===== MMA issuer
             const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
             for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
+                const int s = kb % STG;
+                const uint32_t ph = (kb / STG) & 1;
                 mbar_wait(smem_u32(&bars[s]), ph);                           // operands landed
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -118,15 +120,15 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
                     // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
                     tc_mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                 }
-                tc_commit(smem_u32(&bars[TC_STAGES + s]));                   // frees the smem slot when the MMAs retire
+                tc_commit(smem_u32(&bars[STG + s]));                   // frees the smem slot when the MMAs retire
             }
-            tc_commit(smem_u32(&bars[2 * TC_STAGES]));                       // accumulator complete
+            tc_commit(smem_u32(&bars[2 * STG]));                       // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5 -> TMEM lane quadrant (warp % 4)
         const int q = warp & 3;
         const int row = q * 32 + lane;                // GEMM row = pixel inside the tile
-        mbar_wait(smem_u32(&bars[2 * TC_STAGES]), 0);
+        mbar_wait(smem_u32(&bars[2 * STG]), 0);
         tc_fence_after();
         const int tw = row % p.TW;
         const int r2 = row / p.TW;
@@ -246,11 +248,39 @@ static int encode_weight_map(CUtensorMap* m, const float* w, long long kdim, int
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// Ring depth.  The kernel is latency-bound on the L2 -> smem operand stream (ncu: lts throughput 10-40 %, tensor pipe
+// 12-20 %), so bytes in flight per SM are what counts: either a deep ring with one CTA per SM or a shallower ring that
+// lets two CTAs share the SM (the second CTA's main loop then also hides the first one's epilogue).
+static int tc_env_stages() {
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("FSV_TC_STAGES");
+        v = e ? atoi(e) : -1;
+    }
+    return v;
+}
+static int pick_stages(int stage_bytes, int num_k) {
+    int st = tc_env_stages();
+    if (st <= 0) {
+        const int budget = 96 * 1024;                       // two CTAs per SM
+        st = budget / stage_bytes;
+        if (st < 3) st = 3;
+    }
+    const int max_fit = (200 * 1024) / stage_bytes;
+    if (st > max_fit) st = max_fit;
+    if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
+    if (st > num_k) st = num_k;
+    if (st < 2) st = 2;
+    return st;
+}
+
 static int launch_tc(TcParams& p, int tiles_n, const float* bias, const float* residual, float* y, cudaStream_t st, const char* who) {
-    const int smem_bytes = TC_STAGES * (TC_A_BYTES + p.BN * TC_BK * 4) + (2 * TC_STAGES + 1) * 8 + 16 + 1024;
+    const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 4;
+    p.stages = pick_stages(stage_bytes, p.ntaps * (p.Cin / TC_BK));
+    const int smem_bytes = p.stages * stage_bytes + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {
-        FSV_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FSV_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured = true;
     }
     dim3 grid(p.tiles_w * p.tiles_h * tiles_n, p.Cout / p.BN);

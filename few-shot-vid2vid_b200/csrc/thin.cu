@@ -112,7 +112,7 @@ __device__ __forceinline__ float4 lrelu4(float4 v) {
 
 // forward: grid (x tiles, y tiles, N); weights [co][tap][ci] (= OHWI as stored) in shared memory
 template <int COUT>
-__global__ void __launch_bounds__(TT_THREADS) k_tco_fwd(ThinP p, int lpp, const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(TT_THREADS) k_tco_fwd(ThinP p, int lpp, int tw, int th, const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const float* __restrict__ residual,
                                                         float* __restrict__ y) {
     extern __shared__ __align__(16) float ws[];
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(TT_THREADS) k_tco_fwd(ThinP p, int lpp, const 
     __syncthreads();
     const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
     const long long n = blockIdx.z;
-    const int h0 = blockIdx.y * TT_H, w0 = blockIdx.x * TT_W;
-    for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
-        const int ho = h0 + pidx / TT_W, wo = w0 + (pidx % TT_W);
+    const int h0 = blockIdx.y * th, w0 = blockIdx.x * tw;
+    for (int pidx = slot; pidx < tw * th; pidx += slots) {
+        const int ho = h0 + pidx / tw, wo = w0 + (pidx % tw);
         const bool valid = ho < p.Ho && wo < p.Wo;
         float acc[COUT];
 #pragma unroll
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(TT_THREADS) k_tco_fwd(ThinP p, int lpp, const 
 
 // data gradient: dx[n,h,w,ci] = sum_{r,s,co} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,co] * w[co][r][s][ci]; tiles over (H, W)
 template <int COUT>
-__global__ void __launch_bounds__(TT_THREADS) k_tco_dgrad(ThinP p, int lpp, const float* __restrict__ dy, const float* __restrict__ w,
+__global__ void __launch_bounds__(TT_THREADS) k_tco_dgrad(ThinP p, int lpp, int tw, int th, const float* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, int accumulate) {
     extern __shared__ __align__(16) float ws[];
     const int taps = p.kh * p.kw, cin4 = p.Cin >> 2;
@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(TT_THREADS) k_tco_dgrad(ThinP p, int lpp, cons
     __syncthreads();
     const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
     const long long n = blockIdx.z;
-    const int h0 = blockIdx.y * TT_H, w0 = blockIdx.x * TT_W;
-    for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
-        const int hq = h0 + pidx / TT_W, wq = w0 + (pidx % TT_W);
+    const int h0 = blockIdx.y * th, w0 = blockIdx.x * tw;
+    for (int pidx = slot; pidx < tw * th; pidx += slots) {
+        const int hq = h0 + pidx / tw, wq = w0 + (pidx % tw);
         if (hq >= p.H || wq >= p.W) continue;
         for (int c4 = sub; c4 < cin4; c4 += lpp) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(TT_THREADS) k_tco_dgrad(ThinP p, int lpp, cons
 // keeps taps x COUT float4 accumulators for its 4 channels; one warp-shuffle + shared-memory reduction per block, then
 // taps*COUT*Cin global atomics per block.  grid.y = channel groups of lpp*4 (only > 1 when Cin > 128).
 template <int TAPS, int COUT>
-__global__ void __launch_bounds__(TT_THREADS) k_tco_wgrad(ThinP p, int lpp, int tiles_x, int tiles_y, long long ntiles,
+__global__ void __launch_bounds__(TT_THREADS) k_tco_wgrad(ThinP p, int lpp, int tw, int th, int tiles_x, int tiles_y, long long ntiles,
                                                           const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw) {
     __shared__ float red[TAPS * COUT * 128];
     const int taps = p.kh * p.kw, cin4 = p.Cin >> 2;
@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(TT_THREADS) k_tco_wgrad(ThinP p, int lpp, int 
         const long long q = tile / tiles_x;
         const int ty = (int)(q % tiles_y);
         const long long n = q / tiles_y;
-        for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
-            const int ho = ty * TT_H + pidx / TT_W, wo = tx * TT_W + (pidx % TT_W);
+        for (int pidx = slot; pidx < tw * th; pidx += slots) {
+            const int ho = ty * th + pidx / tw, wo = tx * tw + (pidx % tw);
             if (!cvalid || ho >= p.Ho || wo >= p.Wo) continue;
             const float* dp = dy + ((n * p.Ho + ho) * p.Wo + wo) * p.y_ld + p.y_coff;
             float dv[COUT];
@@ -360,6 +360,18 @@ extern "C" int fsv_conv2d_thin_kind(const fsv_conv_desc* d) {
         (long long)d->Cout * d->kh * d->kw * d->Cin * 4 <= 40 * 1024) return 2;         // thin output
     return 0;
 }
+// tile: 16x8 pixels, shrunk (16x4, 8x4) while the grid would not fill the GPU twice over; always a multiple of the
+// block's pixel slots so every lane of a warp runs the same number of passes
+static void tt_tile(int lpp, long long n, int hh, int ww, int* tw, int* th) {
+    const int slots = TT_THREADS / lpp;
+    *tw = TT_W; *th = TT_H;
+    const long long want = 2LL * fsv_sm_count();
+    while (n * fsv_cdiv(ww, *tw) * fsv_cdiv(hh, *th) < want) {
+        if (*th > 4 && (*tw) * (*th / 2) >= slots) *th /= 2;
+        else if (*tw > 8 && (*tw / 2) * (*th) >= slots) *tw /= 2;
+        else break;
+    }
+}
 static int tt_lpp(int cin) {
     int l = 1;
     while (l * 2 <= cin / 4 && l < 32) l *= 2;
@@ -379,14 +391,15 @@ extern "C" int fsv_conv2d_fwd_thin(const fsv_conv_desc* d, const float* x, const
         k_thin_cin_fwd<<<grid, 128, taps * d->Cin * 32 * sizeof(float), st>>>(p, x, w, bias, residual, y);
     } else {
         FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w) & 15) == 0, "conv2d_fwd_thin: pointers must be 16-byte aligned");
-        dim3 grid(fsv_cdiv(d->Wo, TT_W), fsv_cdiv(d->Ho, TT_H), d->N);
         size_t sm = (size_t)d->Cout * taps * d->Cin * sizeof(float);
-        int lpp = tt_lpp(d->Cin);
+        int lpp = tt_lpp(d->Cin), tw, th;
+        tt_tile(lpp, d->N, d->Ho, d->Wo, &tw, &th);
+        dim3 grid(fsv_cdiv(d->Wo, tw), fsv_cdiv(d->Ho, th), d->N);
         switch (d->Cout) {
-            case 1: k_tco_fwd<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); break;
-            case 2: k_tco_fwd<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); break;
-            case 3: k_tco_fwd<3><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); break;
-            default: k_tco_fwd<4><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); break;
+            case 1: k_tco_fwd<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, x, w, bias, residual, y); break;
+            case 2: k_tco_fwd<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, x, w, bias, residual, y); break;
+            case 3: k_tco_fwd<3><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, x, w, bias, residual, y); break;
+            default: k_tco_fwd<4><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, x, w, bias, residual, y); break;
         }
     }
     FSV_CHECK_LAUNCH("conv2d_fwd_thin");
@@ -403,13 +416,15 @@ extern "C" int fsv_conv2d_wgrad_thin(const fsv_conv_desc* d, const float* x, con
     ThinP p = thin_p(d);
     cudaStream_t st = (cudaStream_t)stream;
     const int lpp = tt_lpp(d->Cin);
-    const int tiles_x = fsv_cdiv(d->Wo, TT_W), tiles_y = fsv_cdiv(d->Ho, TT_H);
+    int tw, th;
+    tt_tile(lpp, d->N, d->Ho, d->Wo, &tw, &th);
+    const int tiles_x = fsv_cdiv(d->Wo, tw), tiles_y = fsv_cdiv(d->Ho, th);
     const long long ntiles = (long long)tiles_x * tiles_y * d->N;
     const int groups = fsv_cdiv(d->Cin / 4, lpp);
     long long gx = (2LL * fsv_sm_count() + groups - 1) / groups;
     if (gx > ntiles) gx = ntiles;
     dim3 grid((unsigned)gx, groups);
-#define TCO_WGRAD(T, C) k_tco_wgrad<T, C><<<grid, TT_THREADS, 0, st>>>(p, lpp, tiles_x, tiles_y, ntiles, x, dy, dw)
+#define TCO_WGRAD(T, C) k_tco_wgrad<T, C><<<grid, TT_THREADS, 0, st>>>(p, lpp, tw, th, tiles_x, tiles_y, ntiles, x, dy, dw)
     if (taps <= 9) {
         switch (d->Cout) {
             case 1: TCO_WGRAD(9, 1); break;
@@ -446,14 +461,15 @@ extern "C" int fsv_conv2d_dgrad_thin(const fsv_conv_desc* d, const float* dy, co
         k_thin_cin_dgrad<<<fsv_cdiv(total, 128), 128, (size_t)d->kh * d->kw * d->Cout * 8 * sizeof(float), st>>>(p, dy, w, dx, accumulate);
     } else {
         FSV_REQUIRE((((uintptr_t)dx) & 15) == 0 && (((uintptr_t)w) & 15) == 0, "conv2d_dgrad_thin: pointers must be 16-byte aligned");
-        dim3 grid(fsv_cdiv(d->W, TT_W), fsv_cdiv(d->H, TT_H), d->N);
         size_t sm = (size_t)d->Cout * d->kh * d->kw * d->Cin * sizeof(float);
-        int lpp = tt_lpp(d->Cin);
+        int lpp = tt_lpp(d->Cin), tw, th;
+        tt_tile(lpp, d->N, d->H, d->W, &tw, &th);
+        dim3 grid(fsv_cdiv(d->W, tw), fsv_cdiv(d->H, th), d->N);
         switch (d->Cout) {
-            case 1: k_tco_dgrad<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
-            case 2: k_tco_dgrad<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
-            case 3: k_tco_dgrad<3><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
-            default: k_tco_dgrad<4><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+            case 1: k_tco_dgrad<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, dy, w, dx, accumulate); break;
+            case 2: k_tco_dgrad<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, dy, w, dx, accumulate); break;
+            case 3: k_tco_dgrad<3><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, dy, w, dx, accumulate); break;
+            default: k_tco_dgrad<4><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, dy, w, dx, accumulate); break;
         }
     }
     FSV_CHECK_LAUNCH("conv2d_dgrad_thin");

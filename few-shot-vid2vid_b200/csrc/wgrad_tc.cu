@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #define WG_STAGES 4
+#define WG_MAX_STAGES 8
 #define WG_MAX_TAPS 16
 
 struct WgTap { int plane, dh, dw; };
@@ -167,6 +168,7 @@ struct __align__(64) WgMnParams {
     int role, BN, mtiles, ntiles, kb_per_split;
     int per_sample, KBs, spn;          // per-sample weights: K blocks per sample, splits per sample (grid.x = N * spn)
     long long dw_nstride;
+    int stages;                         // smem ring depth (2..WG_MAX_STAGES)
     int lbo16, sbo16, kstep16, ltype;   // descriptor fields in 16-byte units (tunable while bringing the layout up)
 };
 
@@ -184,10 +186,11 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BN = p.BN;
+    const int STG = p.stages;
     const int a_bytes = 4 * WGMN_BLOCK_BYTES, b_bytes = (BN / 32) * WGMN_BLOCK_BYTES;
     const int stage_bytes = a_bytes + b_bytes;
-    uint64_t* bars = (uint64_t*)(smem + WG_STAGES * stage_bytes);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WG_STAGES + 1);
+    uint64_t* bars = (uint64_t*)(smem + STG * stage_bytes);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STG + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tap_i = blockIdx.y;
     const WgTap tap = p.taps[tap_i];
@@ -206,11 +209,11 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ 
     if (num_k <= 0) return;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < WG_STAGES; ++s) {
+        for (int s = 0; s < STG; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[WG_STAGES + s]), 1);
+            mbar_init(smem_u32(&bars[STG + s]), 1);
         }
-        mbar_init(smem_u32(&bars[2 * WG_STAGES]), 1);
+        mbar_init(smem_u32(&bars[2 * STG]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -232,9 +235,9 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ 
             const int a_dh = p.role == 0 ? 0 : tap.dh, a_dw = p.role == 0 ? 0 : tap.dw;
             const int b_dh = p.role == 0 ? tap.dh : 0, b_dw = p.role == 0 ? tap.dw : 0;
             for (int i = 0; i < num_k; ++i) {
-                const int s = i % WG_STAGES;
-                const uint32_t ph = (i / WG_STAGES) & 1;
-                mbar_wait(smem_u32(&bars[WG_STAGES + s]), ph ^ 1);
+                const int s = i % STG;
+                const uint32_t ph = (i / STG) & 1;
+                mbar_wait(smem_u32(&bars[STG + s]), ph ^ 1);
                 int kb = kb0 + i;
                 const int wb = kb % p.nWB; kb /= p.nWB;
                 const int hb = kb % p.nHB; kb /= p.nHB;
@@ -252,8 +255,8 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ 
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_BM, BN) | (1u << 15) | (1u << 16);   // A and B MN-major
             for (int i = 0; i < num_k; ++i) {
-                const int s = i % WG_STAGES;
-                const uint32_t ph = (i / WG_STAGES) & 1;
+                const int s = i % STG;
+                const uint32_t ph = (i / STG) & 1;
                 mbar_wait(smem_u32(&bars[s]), ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -262,14 +265,14 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ 
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k)     // 8 pixels = 8 rows of 128 B = +1024 B = +64 in (addr >> 4)
                     tc_mma_tf32(tmem_base, adesc + (uint64_t)(k * p.kstep16), bdesc + (uint64_t)(k * p.kstep16), idesc, (i | k) != 0);
-                tc_commit(smem_u32(&bars[WG_STAGES + s]));
+                tc_commit(smem_u32(&bars[STG + s]));
             }
-            tc_commit(smem_u32(&bars[2 * WG_STAGES]));
+            tc_commit(smem_u32(&bars[2 * STG]));
         }
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        mbar_wait(smem_u32(&bars[2 * WG_STAGES]), 0);
+        mbar_wait(smem_u32(&bars[2 * STG]), 0);
         tc_fence_after();
         const int Mdim = p.role == 0 ? p.Cout : p.Cin;
         const int Ndim = p.role == 0 ? p.Cin : p.Cout;
@@ -516,7 +519,19 @@ static int wgrad_tc_mn(const fsv_conv_desc* d, const float* x, const float* dy, 
         p.spn = (int)((p.KBs + p.kb_per_split - 1) / p.kb_per_split);
         splits = (long long)d->N * p.spn;
     }
-    const int smem_bytes = WG_STAGES * (4 * WGMN_BLOCK_BYTES + (p.BN / 32) * WGMN_BLOCK_BYTES) + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
+    {
+        // ring depth: see conv_tc.cu pick_stages (latency-bound operand stream: two CTAs per SM by default)
+        static int env_st = -2;
+        if (env_st == -2) { const char* e = getenv("FSV_WG_STAGES"); env_st = e ? atoi(e) : -1; }
+        const int stage_bytes = 4 * WGMN_BLOCK_BYTES + (p.BN / 32) * WGMN_BLOCK_BYTES;
+        int stg = env_st > 0 ? env_st : (96 * 1024) / stage_bytes;
+        if (stg < 3 && env_st <= 0) stg = 3;
+        if (stg > (200 * 1024) / stage_bytes) stg = (200 * 1024) / stage_bytes;
+        if (stg > WG_MAX_STAGES) stg = WG_MAX_STAGES;
+        if (stg < 2) stg = 2;
+        p.stages = stg;
+    }
+    const int smem_bytes = p.stages * (4 * WGMN_BLOCK_BYTES + (p.BN / 32) * WGMN_BLOCK_BYTES) + (2 * WG_MAX_STAGES + 1) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {
         FSV_CUDA(cudaFuncSetAttribute(k_wgrad_tc_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
