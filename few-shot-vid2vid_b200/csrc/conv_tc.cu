@@ -126,11 +126,6 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
         }
     } else {
         // ===== epilogue: warps 2..5 -> TMEM lane quadrant (warp % 4)
-        // tcgen05.ld hands every thread one GEMM row (pixel) x 32 columns.  Storing that directly makes each 16-byte
-        // store of a warp hit 32 different lines (the epilogue then costs more LSU cycles than the main loop of the
-        // short-K layers), so the 32x32 block is transposed through shared memory (the operand ring is idle once
-        // the accumulator barrier has fired): 8 lanes then cover 128 contiguous bytes of one pixel, a warp
-        // instruction writes 4 full lines, and bias / residual are read the same coalesced way.
         const int q = warp & 3;
         const int row = q * 32 + lane;                // GEMM row = pixel inside the tile
         mbar_wait(smem_u32(&bars[2 * STG]), 0);
@@ -142,43 +137,33 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
         const int n = n0 + tn, ho = h0 + th, wo = w0 + tw;
         const bool valid = (n < p.N) && (ho < p.Ho) && (wo < p.Wo);
         const long long pix = ((long long)n * p.OH + (ho * p.os + p.oph)) * p.OW + (wo * p.os + p.opw);
-        const long long my_yoff = valid ? pix * p.y_ld + p.y_coff + co0 : -1;
-        const long long my_roff = pix * p.res_ld + p.res_coff + co0;
-        const long long my_boff = (long long)n * p.b_nstride + co0;
-        float* stg = reinterpret_cast<float*>(smem) + q * (32 * 36);
-        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        float* yrow = y + pix * p.y_ld + p.y_coff + co0;
+        const float* rrow = residual ? residual + pix * p.res_ld + p.res_coff + co0 : nullptr;
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (valid) {
+                const int ncol = min(32, BN - c);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(stg + lane * 36 + j * 4) =
-                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                __uint_as_float(v[4 * j + 3]));
-            __syncwarp();
-            const bool col_ok = c + c4 < BN;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = i * 4 + rsub;
-                const long long yo = __shfl_sync(0xffffffffu, my_yoff, r);
-                const long long ro = __shfl_sync(0xffffffffu, my_roff, r);
-                const long long bo = __shfl_sync(0xffffffffu, my_boff, r);
-                if (col_ok && yo >= 0) {
-                    float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-                    if (bias) {
-                        const float4 bv = *reinterpret_cast<const float4*>(bias + bo + c + c4);
-                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncol) {
+                        float4 o;
+                        o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
+                        o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+                        if (bias) {
+                            float4 b = *reinterpret_cast<const float4*>(bias + (long long)n * p.b_nstride + co0 + c + j);
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        if (rrow) {
+                            float4 r = *reinterpret_cast<const float4*>(rrow + c + j);
+                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                        }
+                        o.x = fsv_act(o.x, p.act) * p.out_scale; o.y = fsv_act(o.y, p.act) * p.out_scale;
+                        o.z = fsv_act(o.z, p.act) * p.out_scale; o.w = fsv_act(o.w, p.act) * p.out_scale;
+                        *reinterpret_cast<float4*>(yrow + c + j) = o;
                     }
-                    if (residual) {
-                        const float4 rv = *reinterpret_cast<const float4*>(residual + ro + c + c4);
-                        o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-                    }
-                    o.x = fsv_act(o.x, p.act) * p.out_scale; o.y = fsv_act(o.y, p.act) * p.out_scale;
-                    o.z = fsv_act(o.z, p.act) * p.out_scale; o.w = fsv_act(o.w, p.act) * p.out_scale;
-                    *reinterpret_cast<float4*>(y + yo + c + c4) = o;
                 }
             }
-            __syncwarp();
         }
     }
     tc_fence_before();
