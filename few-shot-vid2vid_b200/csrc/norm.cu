@@ -12,51 +12,116 @@
 
 #define RED_TX 32
 #define RED_TY 8
-#define RED_ROWS_PER_BLOCK 256
+#define RED_MAX_TICKETS 8192
 
-// Generic two-value per-(group, channel) reduction over the rows of an NHWC slice.
-// f(row, c) -> float2; results are atomically added (fp64) into a[g*C+c], b[g*C+c].
-template <class F>
-__global__ void k_chan_reduce2(F f, long long rows_per_group, int C, double* __restrict__ a, double* __restrict__ b) {
-    int c = blockIdx.y * RED_TX + threadIdx.x;
-    int g = blockIdx.z;
-    long long r0 = (long long)blockIdx.x * RED_ROWS_PER_BLOCK;
-    long long r1 = r0 + RED_ROWS_PER_BLOCK;
+__device__ unsigned int g_red_ticket[RED_MAX_TICKETS];
+
+// Generic two-value per-(group, channel) reduction over the rows of an NHWC slice: f(row, c) -> float2.
+// grid (row blocks, 32-channel blocks, groups), block 32 x 8.  Every block leaves its fp64 partials in `part`; the last
+// block to finish for a (group, channel block) -- one ticket each, reset by that block -- adds the partials in a fixed
+// order and hands the totals to the epilogue functor e(g, c, a, b).  No memsets, no float atomics: one launch, and the
+// result does not depend on block scheduling.
+template <class F, class E>
+__global__ void __launch_bounds__(RED_TX * RED_TY) k_chan_reduce2(F f, E e, long long rows_per_group, long long rows_per_block, int C,
+                                                                  double* part) {
+    __shared__ double s_a[RED_TY][RED_TX], s_b[RED_TY][RED_TX];
+    __shared__ int s_last;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c = blockIdx.y * RED_TX + tx;
+    const int g = blockIdx.z;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
     if (r1 > rows_per_group) r1 = rows_per_group;
-    float sa = 0.f, sb = 0.f;
+    float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f, sa2 = 0.f, sb2 = 0.f, sa3 = 0.f, sb3 = 0.f;
     if (c < C) {
-        for (long long r = r0 + threadIdx.y; r < r1; r += RED_TY) {
-            float2 v = f(g * rows_per_group + r, c);
-            sa += v.x;
-            sb += v.y;
+        const long long base = g * rows_per_group;
+        long long r = r0 + ty;
+        for (; r + 3 * RED_TY < r1; r += 4 * RED_TY) {
+            float2 v0 = f(base + r, c), v1 = f(base + r + RED_TY, c), v2 = f(base + r + 2 * RED_TY, c), v3 = f(base + r + 3 * RED_TY, c);
+            sa0 += v0.x; sb0 += v0.y; sa1 += v1.x; sb1 += v1.y; sa2 += v2.x; sb2 += v2.y; sa3 += v3.x; sb3 += v3.y;
+        }
+        for (; r < r1; r += RED_TY) {
+            float2 v = f(base + r, c);
+            sa0 += v.x; sb0 += v.y;
         }
     }
-    __shared__ double s_a[RED_TY][RED_TX], s_b[RED_TY][RED_TX];
-    s_a[threadIdx.y][threadIdx.x] = (double)sa;
-    s_b[threadIdx.y][threadIdx.x] = (double)sb;
+    s_a[ty][tx] = ((double)sa0 + (double)sa1) + ((double)sa2 + (double)sa3);
+    s_b[ty][tx] = ((double)sb0 + (double)sb1) + ((double)sb2 + (double)sb3);
     __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
+    const long long slot = ((long long)g * gridDim.y + blockIdx.y) * gridDim.x;       // first row block of this (g, channel block)
+    if (ty == 0) {
         double ta = 0.0, tb = 0.0;
 #pragma unroll
-        for (int i = 0; i < RED_TY; ++i) {
-            ta += s_a[i][threadIdx.x];
-            tb += s_b[i][threadIdx.x];
-        }
-        atomicAdd(&a[(long long)g * C + c], ta);
-        atomicAdd(&b[(long long)g * C + c], tb);
+        for (int i = 0; i < RED_TY; ++i) { ta += s_a[i][tx]; tb += s_b[i][tx]; }
+        double* pp = part + ((slot + blockIdx.x) * RED_TX + tx) * 2;
+        pp[0] = ta; pp[1] = tb;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tx == 0 && ty == 0) {
+        unsigned int* tk = &g_red_ticket[g * gridDim.y + blockIdx.y];
+        unsigned int t = atomicAdd(tk, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *tk = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile double* vp = part;
+    double ta = 0.0, tb = 0.0;
+    for (int rb = ty; rb < (int)gridDim.x; rb += RED_TY) {
+        const long long o = ((slot + rb) * RED_TX + tx) * 2;
+        ta += vp[o]; tb += vp[o + 1];
+    }
+    s_a[ty][tx] = ta; s_b[ty][tx] = tb;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        ta = 0.0; tb = 0.0;
+#pragma unroll
+        for (int i = 0; i < RED_TY; ++i) { ta += s_a[i][tx]; tb += s_b[i][tx]; }
+        e(g, c, ta, tb);
     }
 }
 
-template <class F>
-static int launch_reduce2(F f, int groups, long long rows_per_group, int C, double* a, double* b, cudaStream_t st, const char* name) {
-    FSV_CUDA(cudaMemsetAsync(a, 0, sizeof(double) * (size_t)groups * C, st));
-    FSV_CUDA(cudaMemsetAsync(b, 0, sizeof(double) * (size_t)groups * C, st));
-    dim3 grid(fsv_cdiv(rows_per_group, RED_ROWS_PER_BLOCK), fsv_cdiv(C, RED_TX), groups);
+static void reduce_geometry(int groups, long long rows_per_group, int C, int* row_blocks, long long* rows_per_block) {
+    const int cb = fsv_cdiv(C, RED_TX);
+    long long want = (4LL * fsv_sm_count() + (long long)cb * groups - 1) / ((long long)cb * groups);
+    long long max_rb = (rows_per_group + 63) / 64;
+    if (want > max_rb) want = max_rb;
+    if (want < 1) want = 1;
+    long long rpb = (rows_per_group + want - 1) / want;
+    rpb = ((rpb + RED_TY - 1) / RED_TY) * RED_TY;
+    *rows_per_block = rpb;
+    *row_blocks = (int)((rows_per_group + rpb - 1) / rpb);
+}
+// doubles of workspace a reduction over (groups, rows_per_group, C) needs
+extern "C" long long fsv_norm_work_doubles(int groups, int C, long long rows_per_group) {
+    int rb; long long rpb;
+    reduce_geometry(groups, rows_per_group, C, &rb, &rpb);
+    return (long long)groups * fsv_cdiv(C, RED_TX) * rb * RED_TX * 2;
+}
+
+template <class F, class E>
+static int launch_reduce2(F f, E e, int groups, long long rows_per_group, int C, double* work, cudaStream_t st, const char* name) {
+    FSV_REQUIRE(work != nullptr, "%s: null workspace", name);
+    FSV_REQUIRE((long long)groups * fsv_cdiv(C, RED_TX) <= RED_MAX_TICKETS && groups <= 65535, "%s: too many (group, channel-block) pairs", name);
+    int rb; long long rpb;
+    reduce_geometry(groups, rows_per_group, C, &rb, &rpb);
+    dim3 grid(rb, fsv_cdiv(C, RED_TX), groups);
     dim3 block(RED_TX, RED_TY);
-    k_chan_reduce2<<<grid, block, 0, st>>>(f, rows_per_group, C, a, b);
+    k_chan_reduce2<<<grid, block, 0, st>>>(f, e, rows_per_group, rpb, C, work);
     FSV_CHECK_LAUNCH(name);
     return FSV_OK;
 }
+
+struct StoreE {   // totals -> a[g*C+c], b[g*C+c]
+    double *a, *b;
+    int C;
+    __device__ void operator()(int g, int c, double ta, double tb) const {
+        a[(long long)g * C + c] = ta;
+        b[(long long)g * C + c] = tb;
+    }
+};
 
 struct StatsF {
     const float* x;
@@ -67,12 +132,47 @@ struct StatsF {
     }
 };
 
-extern "C" int fsv_norm_stats(const float* x, int N, int HW, int C, int ld, int coff, int mode, double* sum, double* sumsq, void* stream) {
+extern "C" int fsv_norm_stats(const float* x, int N, int HW, int C, int ld, int coff, int mode, double* sum, double* sumsq, double* work,
+                              void* stream) {
     FSV_REQUIRE(N > 0 && HW > 0 && C > 0 && ld >= coff + C, "norm_stats: bad dims");
     int groups = mode == FSV_NORM_INSTANCE ? N : 1;
     long long rpg = mode == FSV_NORM_INSTANCE ? HW : (long long)N * HW;
     StatsF f{x, ld, coff};
-    return launch_reduce2(f, groups, rpg, C, sum, sumsq, (cudaStream_t)stream, "norm_stats");
+    StoreE e{sum, sumsq, C};
+    return launch_reduce2(f, e, groups, rpg, C, work, (cudaStream_t)stream, "norm_stats");
+}
+
+// statistics and their finalisation in ONE launch (the training-mode forward of every BatchNorm / InstanceNorm / SPADE)
+struct FinalizeE {
+    double count, ucount;
+    float eps, momentum;
+    float *running_mean, *running_var;
+    int update_running, C;
+    float *mean, *rstd;
+    __device__ void operator()(int g, int c, double sum, double sumsq) const {
+        const long long i = (long long)g * C + c;
+        double m = sum / count;
+        double var = sumsq / count - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[i] = (float)m;
+        rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+        if (update_running) {   // batch mode: one group
+            double unbiased = ucount > 1.0 ? var * (ucount / (ucount - 1.0)) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    }
+};
+extern "C" int fsv_norm_stats_finalize(const float* x, int N, int HW, int C, int ld, int coff, int mode, double unbias_mul, float eps,
+                                       float momentum, float* running_mean, float* running_var, int update_running, float* mean,
+                                       float* rstd, double* work, void* stream) {
+    FSV_REQUIRE(N > 0 && HW > 0 && C > 0 && ld >= coff + C && mean && rstd, "norm_stats_finalize: bad args");
+    int groups = mode == FSV_NORM_INSTANCE ? N : 1;
+    FSV_REQUIRE(!update_running || (groups == 1 && running_mean && running_var), "norm_stats_finalize: running update needs batch mode");
+    long long rpg = mode == FSV_NORM_INSTANCE ? HW : (long long)N * HW;
+    StatsF f{x, ld, coff};
+    FinalizeE e{(double)rpg, (double)rpg * unbias_mul, eps, momentum, running_mean, running_var, update_running, C, mean, rstd};
+    return launch_reduce2(f, e, groups, rpg, C, work, (cudaStream_t)stream, "norm_stats_finalize");
 }
 
 __global__ void k_norm_finalize(const double* __restrict__ sum, const double* __restrict__ sumsq, int total, int C, double count,
@@ -201,6 +301,42 @@ __global__ void k_norm_apply_bwd(const float* __restrict__ x, const float* __res
         dx[i] = r * w * v;
     }
 }
+// float4 variant (C % 4 == 0): the scalar kernel above spends its time on 64-bit index arithmetic, not on memory
+__global__ void k_norm_apply_bwd4(const float4* __restrict__ x, const float4* __restrict__ y, const float4* __restrict__ dy,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ weight,
+                                  const double* __restrict__ A, const double* __restrict__ B, float4* __restrict__ dx,
+                                  long long total4, int C, long long HWC, int instance, int act, int batch_stats, float inv_cnt) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 4;
+        const int c = (int)(e % C);
+        const int s = instance ? (int)(e / HWC) * C + c : c;
+        const float4 r = *reinterpret_cast<const float4*>(rstd + s);
+        const float4 d4 = dy[i], y4 = y[i];
+        float g[4] = {d4.x * fsv_act_grad(y4.x, act), d4.y * fsv_act_grad(y4.y, act), d4.z * fsv_act_grad(y4.z, act),
+                      d4.w * fsv_act_grad(y4.w, act)};
+        float w[4] = {1.f, 1.f, 1.f, 1.f};
+        if (weight) {
+            const float4 w4 = *reinterpret_cast<const float4*>(weight + c);
+            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+        }
+        const float rr[4] = {r.x, r.y, r.z, r.w};
+        float o[4];
+        if (batch_stats) {
+            const float4 m = *reinterpret_cast<const float4*>(mean + s);
+            const float4 x4 = x[i];
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (xv[j] - mm[j]) * rr[j];
+                o[j] = rr[j] * w[j] * (g[j] - (float)A[s + j] * inv_cnt - xh * (float)B[s + j] * inv_cnt);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = rr[j] * w[j] * g[j];
+        }
+        dx[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
 __global__ void k_norm_param_grads(const double* __restrict__ A, const double* __restrict__ B, int groups, int C,
                                    float* __restrict__ dweight, float* __restrict__ dbias) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,7 +360,8 @@ extern "C" int fsv_norm_apply_bwd(const float* x, const float* y, const float* d
     double* A = scratch;
     double* B = scratch + (size_t)groups * C;
     NormBwdF f{x, y, dy, mean, rstd, C, act, inst, (long long)HW};
-    int rc = launch_reduce2(f, groups, rpg, C, A, B, st, "norm_bwd_reduce");
+    StoreE e{A, B, C};
+    int rc = launch_reduce2(f, e, groups, rpg, C, B + (size_t)groups * C, st, "norm_bwd_reduce");
     if (rc) return rc;
     if (weight) {
         FSV_REQUIRE(dweight && dbias, "norm_apply_bwd: affine needs dweight/dbias");
@@ -232,8 +369,13 @@ extern "C" int fsv_norm_apply_bwd(const float* x, const float* y, const float* d
         FSV_CHECK_LAUNCH("norm_param_grads");
     }
     long long total = (long long)N * HW * C;
-    k_norm_apply_bwd<<<ew_grid(total), 256, 0, st>>>(x, y, dy, mean, rstd, weight, A, B, dx, total, C, HW, inst, act, batch_stats,
-                                                      (float)(1.0 / (double)rpg));
+    if (C % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0)
+        k_norm_apply_bwd4<<<ew_grid(total / 4), 256, 0, st>>>((const float4*)x, (const float4*)y, (const float4*)dy, mean, rstd, weight, A, B,
+                                                              (float4*)dx, total / 4, C, (long long)HW * C, inst, act, batch_stats,
+                                                              (float)(1.0 / (double)rpg));
+    else
+        k_norm_apply_bwd<<<ew_grid(total), 256, 0, st>>>(x, y, dy, mean, rstd, weight, A, B, dx, total, C, HW, inst, act, batch_stats,
+                                                          (float)(1.0 / (double)rpg));
     FSV_CHECK_LAUNCH("norm_apply_bwd");
     return FSV_OK;
 }
@@ -282,6 +424,42 @@ __global__ void k_spade_norm_bwd(const float* __restrict__ x, const float* __res
         dx[i] = r * v;
     }
 }
+// float4 variant (C % 4 == 0)
+__global__ void k_spade_norm_bwd4(const float4* __restrict__ x, const float4* __restrict__ g, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const double* __restrict__ A, const double* __restrict__ B,
+                                  float4* __restrict__ dx, int N, int Hs, int Ws, int C, int up, int instance, int batch_stats, float inv_cnt) {
+    const int C4 = C >> 2;
+    const long long total4 = (long long)N * Hs * Ws * C4;
+    const int W = Ws * up;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const long long p = i / C4;
+        const int ws = (int)(p % Ws);
+        const long long q = p / Ws;
+        const int hs = (int)(q % Hs);
+        const long long n = q / Hs;
+        const int c = c4 * 4;
+        const int s = instance ? (int)n * C + c : c;
+        float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int a = 0; a < up; ++a)
+            for (int b = 0; b < up; ++b) {
+                const float4 t = g[(((n * Hs * up + hs * up + a) * W) + ws * up + b) * C4 + c4];
+                gs.x += t.x; gs.y += t.y; gs.z += t.z; gs.w += t.w;
+            }
+        const float4 r = *reinterpret_cast<const float4*>(rstd + s);
+        float4 v = gs;
+        if (batch_stats) {
+            const float k = (float)(up * up) * inv_cnt;
+            const float4 m = *reinterpret_cast<const float4*>(mean + s);
+            const float4 xv = x[i];
+            v.x = gs.x - k * (float)A[s + 0] - k * (xv.x - m.x) * r.x * (float)B[s + 0];
+            v.y = gs.y - k * (float)A[s + 1] - k * (xv.y - m.y) * r.y * (float)B[s + 1];
+            v.z = gs.z - k * (float)A[s + 2] - k * (xv.z - m.z) * r.z * (float)B[s + 2];
+            v.w = gs.w - k * (float)A[s + 3] - k * (xv.w - m.w) * r.w * (float)B[s + 3];
+        }
+        dx[i] = make_float4(r.x * v.x, r.y * v.y, r.z * v.z, r.w * v.w);
+    }
+}
 extern "C" int fsv_spade_norm_bwd(const float* x, const float* dxhat, const float* mean, const float* rstd, float* dx,
                                   double* scratch, int N, int H, int W, int C, int up, int mode, int batch_stats, void* stream) {
     FSV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (up == 1 || up == 2) && H % up == 0 && W % up == 0, "spade_norm_bwd: bad dims");
@@ -293,12 +471,17 @@ extern "C" int fsv_spade_norm_bwd(const float* x, const float* dxhat, const floa
     double* B = scratch + (size_t)groups * C;
     if (batch_stats) {
         SpadeNormBwdF f{x, dxhat, mean, rstd, C, H, W, up, inst};
-        int rc = launch_reduce2(f, groups, rpg, C, A, B, st, "spade_norm_bwd_reduce");
+        StoreE e{A, B, C};
+        int rc = launch_reduce2(f, e, groups, rpg, C, B + (size_t)groups * C, st, "spade_norm_bwd_reduce");
         if (rc) return rc;
     }
     long long total = (long long)N * (H / up) * (W / up) * C;
-    k_spade_norm_bwd<<<ew_grid(total), 256, 0, st>>>(x, dxhat, mean, rstd, A, B, dx, N, H / up, W / up, C, up, inst, batch_stats,
-                                                      (float)(1.0 / (double)rpg));
+    if (C % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)dxhat) | ((uintptr_t)dx)) & 15) == 0)
+        k_spade_norm_bwd4<<<ew_grid(total / 4), 256, 0, st>>>((const float4*)x, (const float4*)dxhat, mean, rstd, A, B, (float4*)dx, N, H / up,
+                                                              W / up, C, up, inst, batch_stats, (float)(1.0 / (double)rpg));
+    else
+        k_spade_norm_bwd<<<ew_grid(total), 256, 0, st>>>(x, dxhat, mean, rstd, A, B, dx, N, H / up, W / up, C, up, inst, batch_stats,
+                                                          (float)(1.0 / (double)rpg));
     FSV_CHECK_LAUNCH("spade_norm_bwd");
     return FSV_OK;
 }

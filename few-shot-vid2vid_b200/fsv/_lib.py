@@ -57,7 +57,9 @@ SIGNATURES = {
     'fsv_conv2d_wgrad_tc_eligible': [_CD],
     'fsv_conv2d_wgrad_tc_workspace': [_CD],
     'fsv_conv2d_wgrad_tc': [_CD, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
-    'fsv_norm_stats': [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    'fsv_norm_work_doubles': [c_int, c_int, c_ll],
+    'fsv_norm_stats': [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    'fsv_norm_stats_finalize': [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_float, c_float, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
     'fsv_norm_finalize': [c_vp, c_vp, c_int, c_int, c_double, c_double, c_float, c_float, c_vp, c_vp, c_int, c_vp, c_vp, c_vp],
     'fsv_norm_from_running': [c_vp, c_vp, c_int, c_float, c_vp, c_vp, c_vp],
     'fsv_norm_apply_fwd': [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
@@ -89,6 +91,7 @@ def _load():
         fn.restype = c_int
     lib.fsv_conv2d_wgrad_tc_workspace.restype = c_ll
     lib.fsv_spectral_workspace.restype = c_ll
+    lib.fsv_norm_work_doubles.restype = c_ll
     lib.fsv_last_error.argtypes = []
     lib.fsv_last_error.restype = ctypes.c_char_p
     return lib

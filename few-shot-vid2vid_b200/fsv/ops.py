@@ -420,12 +420,11 @@ def _stats(x, n, hw, c, mode, training, running_mean, running_var, eps, momentum
     rstd = torch.empty(groups * c, device=dev, dtype=torch.float32)
     st = stream()
     if training or mode == NORM_INSTANCE:
-        sums = torch.empty(2 * groups * c, device=dev, dtype=torch.float64)
-        _call(lib.fsv_norm_stats, ptr(x), n, hw, c, c, 0, mode, ptr(sums), _off(sums, 2 * groups * c), st)
-        count = float(hw if mode == NORM_INSTANCE else n * hw)
+        rpg = hw if mode == NORM_INSTANCE else n * hw
+        work = torch.empty(int(lib.fsv_norm_work_doubles(groups, c, rpg)), device=dev, dtype=torch.float64)
         upd = 1 if (mode == NORM_BATCH and running_mean is not None) else 0
-        _call(lib.fsv_norm_finalize, ptr(sums), _off(sums, 2 * groups * c), groups, c, count, count * unbias_mul, eps, momentum,
-              ptr(running_mean) if upd else None, ptr(running_var) if upd else None, upd, ptr(mean), ptr(rstd), st)
+        _call(lib.fsv_norm_stats_finalize, ptr(x), n, hw, c, c, 0, mode, float(unbias_mul), eps, momentum,
+              ptr(running_mean) if upd else None, ptr(running_var) if upd else None, upd, ptr(mean), ptr(rstd), ptr(work), st)
     else:
         _call(lib.fsv_norm_from_running, ptr(running_mean), ptr(running_var), c, eps, ptr(mean), ptr(rstd), st)
     return mean, rstd
@@ -459,7 +458,8 @@ class NormActFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dwt = torch.empty(c, device=x.device, dtype=torch.float32) if weight is not None else None
         dbs = torch.empty(c, device=x.device, dtype=torch.float32) if weight is not None else None
-        scratch = torch.empty(2 * groups * c, device=x.device, dtype=torch.float64)
+        rpg = h * w if mode == NORM_INSTANCE else n * h * w
+        scratch = torch.empty(2 * groups * c + int(lib.fsv_norm_work_doubles(groups, c, rpg)), device=x.device, dtype=torch.float64)
         _call(lib.fsv_norm_apply_bwd, ptr(x), ptr(y), ptr(dy), ptr(mean), ptr(rstd), ptr(weight), ptr(dx), ptr(dwt), ptr(dbs),
               ptr(scratch), n, h * w, c, mode, cfg.get('act', ACT_NONE), batch_stats, stream())
         return dx, dwt, dbs, None, None, None
@@ -567,7 +567,8 @@ class SpadeFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            scratch = torch.empty(2 * groups * c, device=dev, dtype=torch.float64)
+            rpg = h * w if mode == NORM_INSTANCE else n * h * w
+            scratch = torch.empty(2 * groups * c + int(lib.fsv_norm_work_doubles(groups, c, rpg)), device=dev, dtype=torch.float64)
             _call(lib.fsv_spade_norm_bwd, ptr(x), ptr(dxhat), ptr(mean), ptr(rstd), ptr(dx), ptr(scratch), n, h, w, c,
                   cfg['up'], mode, batch_stats, st)
         grads = [None] * len(tensors)

@@ -120,9 +120,19 @@ int fsv_conv2d_wgrad_tc(const fsv_conv_desc* d, const float* x, const float* dy,
                         int accumulate, void* stream);
 
 /* ------------------------------------------------------------------ normalisation */
+/* Per-channel reductions run as ONE launch: blocks leave fp64 partials in a workspace, the last block of each
+ * (group, 32-channel block) adds them in a fixed order (deterministic; no memsets, no float atomics).
+ * fsv_norm_work_doubles: doubles of workspace such a reduction needs (rows_per_group = N*HW for batch, HW for instance). */
+long long fsv_norm_work_doubles(int groups, int C, long long rows_per_group);
 /* per-(group, channel) sum and sum of squares of an NHWC slice; groups = 1 (batch) or N (instance).
- * Outputs are DOUBLE [groups*C] (zeroed by the call). */
-int fsv_norm_stats(const float* x, int N, int HW, int C, int ld, int coff, int mode, double* sum, double* sumsq, void* stream);
+ * Outputs are DOUBLE [groups*C]; work: fsv_norm_work_doubles(groups, C, rows_per_group) doubles. */
+int fsv_norm_stats(const float* x, int N, int HW, int C, int ld, int coff, int mode, double* sum, double* sumsq, double* work,
+                   void* stream);
+/* fsv_norm_stats + fsv_norm_finalize fused (the training-mode forward of every BatchNorm / InstanceNorm / SPADE,
+ * normalization.py:32-35,42,78-82): count = rows per group, unbias_count = count * unbias_mul. */
+int fsv_norm_stats_finalize(const float* x, int N, int HW, int C, int ld, int coff, int mode, double unbias_mul, float eps,
+                            float momentum, float* running_mean, float* running_var, int update_running, float* mean,
+                            float* rstd, double* work, void* stream);
 /* mean/rstd from the sums; for mode batch + training also the running-stat update of
  * F.batch_norm (momentum, unbiased variance).  count = elements per channel that were summed;
  * unbias_count = elements per channel as seen by the reference (4x count when the reference
@@ -139,8 +149,8 @@ int fsv_norm_apply_fwd(const float* x, const float* mean, const float* rstd, con
                        float* y, int N, int HW, int C, int mode, int act, void* stream);
 /* backward of the above given y (for the activation mask) and dy:
  *   g = dy*act'(y)*weight;  dx = rstd*(g - S1/cnt - xhat*S2/cnt)  (batch_stats!=0)  or  rstd*g  (eval)
- *   dweight += sum dy'*xhat, dbias += sum dy'  (when weight != NULL; buffers are zeroed by the call)
- * scratch: double[2*groups*C]. */
+ *   dweight = sum dy'*xhat, dbias = sum dy'  (when weight != NULL)
+ * scratch: double[2*groups*C + fsv_norm_work_doubles(groups, C, rows_per_group)]. */
 int fsv_norm_apply_bwd(const float* x, const float* y, const float* dy, const float* mean, const float* rstd,
                        const float* weight, float* dx, float* dweight, float* dbias, double* scratch,
                        int N, int HW, int C, int mode, int act, int batch_stats, void* stream);
@@ -184,7 +194,7 @@ int fsv_spade_bwd(const fsv_spade_desc* d, const float* x, const float* mean, co
                   const float* const* wb, const float* const* bb, const float* dout,
                   float* dxhat, float* const* dgamma, float* const* dbeta, void* stream);
 /* dx (N,H/up,W/up,C) from dxhat: batch_stats!=0: rstd*(sum_children(g) - k*S1/cnt - k*xhat*S2/cnt), else rstd*sum(g).
- * scratch: double[2*groups*C]. */
+ * scratch: double[2*groups*C + fsv_norm_work_doubles(groups, C, rows_per_group)] (rows at full resolution H*W). */
 int fsv_spade_norm_bwd(const float* x, const float* dxhat, const float* mean, const float* rstd, float* dx,
                        double* scratch, int N, int H, int W, int C, int up, int mode, int batch_stats, void* stream);
 

@@ -35,6 +35,12 @@ def to_nchw(t):
 G = torch.Generator().manual_seed(7)
 
 
+@pytest.fixture(autouse=True)
+def _reseed():
+    """every test draws the same data whatever ran before it (test selection / order must not matter)"""
+    G.manual_seed(7)
+
+
 def rnd(*shape, scale=1.0):
     return torch.randn(*shape, generator=G, dtype=torch.float64) * scale
 

@@ -14,6 +14,12 @@ TOL_TF32 = 3e-3
 G = torch.Generator().manual_seed(21)
 
 
+@pytest.fixture(autouse=True)
+def _reseed():
+    """every test draws the same data whatever ran before it (test selection / order must not matter)"""
+    G.manual_seed(21)
+
+
 def rnd(*shape, scale=1.0):
     return torch.randn(*shape, generator=G, dtype=torch.float64) * scale
 
