@@ -170,8 +170,11 @@ def test_conv_tc_wgrad(case):
     ('batch', 64, 16, 2, [32, 32], True, 2), ('batch', 128, 16, 1, [64], False, 2), ('batch', 64, 8, 1, [32], False, 4),
     ('instance', 64, 24, 1, [32, 64, 32], True, 1), ('batch', 192, 20, 1, [32, 32], True, 2),
     ('batch', 32, 32, 1, [32, 32], True, 2), ('batch', 96, 16, 2, [32], False, 2)])
-def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N):
-    """fused SPADE on tcgen05 (TF32 gamma/beta GEMM in TMEM) vs the float64 oracle; backward runs the exact-fp32 kernels."""
+@pytest.mark.parametrize('act', [0, 1])
+def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N, act):
+    """fused SPADE on tcgen05 (TF32 gamma/beta GEMMs in TMEM, forward and backward) vs the float64 oracle.
+    act=0 (no LeakyReLU after the SPADE): everything is smooth, gradients are held to the TF32 tolerance.
+    act=1 (the LeakyReLU the reference applies, architecture.py:96-97): see the kink note below."""
     from fsv import ops
     from fsv.networks.layers import SPADE
     old = ops.CONV_USE_TC
@@ -196,7 +199,9 @@ def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N):
             n_gb = C * K0 + C
             flat = rnd(N, 2 * n_gb, scale=0.2).requires_grad_(True)
             wts = O.slice_gamma_beta(flat, [C, K0, 1, 1])
-        y = O.lrelu(O.spade(O.up2(x) if up == 2 else x, maps, sd, 's', kind, True, wts))
+        y = O.spade(O.up2(x) if up == 2 else x, maps, sd, 's', kind, True, wts)
+        if act:
+            y = O.lrelu(y)
         go = rnd(*y.shape)
         (y * go).sum().backward()
         xg = to_nhwc(x.detach().float().cuda()).requires_grad_(True)
@@ -205,14 +210,16 @@ def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N):
             fg = flat.detach().float().cuda().requires_grad_(True)
             wloc = (fg, 0, C * Ks[0], C * Ks[0] + C, 2 * C * Ks[0] + C)
         n0 = ops.LAUNCHES[0]
-        yg = mod(xg, mg, wloc, up=up, act=ops.ACT_LRELU)
+        yg = mod(xg, mg, wloc, up=up, act=ops.ACT_LRELU if act else ops.ACT_NONE)
         assert rel_err(yg.permute(0, 3, 1, 2), y) < TOL_TF32
         (yg * to_nhwc(go.float().cuda())).sum().backward()
         # Gradients: TF32 rounding of gamma/beta (~5e-4) flips the LeakyReLU slope of the ~0.1% of elements whose
         # pre-activation is that close to zero; each flip changes that element's gradient by 80%, i.e. an L2 error of
-        # ~sqrt(1e-3) ~ 1-3% on random inputs.  (The exact-fp32 kernels are held to 1e-4 in test_gpu_ops.py.)
+        # ~sqrt(1e-3) ~ 1-3% on random inputs, up to ~4% on the smallest case here (16K elements: the flip count is
+        # noisy).  The act=0 variant has no kink and pins the same kernels to 5e-3.  (The exact-fp32 kernels are held to
+        # 1e-4 in test_gpu_ops.py.)
         from util import l2_err
-        GT = 3e-2
+        GT = 5e-2 if act else 5e-3
         assert l2_err(xg.grad.permute(0, 3, 1, 2), x.grad) < GT
         for a, b in zip(mg, maps):
             assert l2_err(a.grad.permute(0, 3, 1, 2), b.grad) < GT
