@@ -295,6 +295,198 @@ __global__ void __launch_bounds__(TT_THREADS) k_tco_wgrad(ThinP p, int lpp, int 
     }
 }
 
+// ------------------------------------------------------------------ Cout <= 4, 3x3 / stride 1 / pad 1 fast paths
+// The generic kernels above are instruction-issue bound (ncu: 85 % issue-active, ~950 instructions per (pixel, lane):
+// run-time tap loops, 64-bit addressing and divisions per tap).  All full-resolution thin-output layers are 3x3 s1 p1
+// (conv_img / conv_flow / conv_mask), so these variants unroll the nine taps at compile time, form the pixel address
+// once and reach the taps through 32-bit offsets; the weight gradient additionally spreads the three tap rows over
+// blockIdx.y, which cuts its accumulators from 27 to 9 float4 per output (145 -> ~64 registers, 4x the occupancy).
+template <int COUT, bool INACT>
+__global__ void __launch_bounds__(TT_THREADS) k_tco_fwd_k3(ThinP p, int lpp, const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ residual,
+                                                           float* __restrict__ y) {
+    extern __shared__ __align__(16) float ws[];   // [co][9][ci]
+    const int cin4 = p.Cin >> 2;
+    for (int i = threadIdx.x; i < COUT * 9 * p.Cin; i += TT_THREADS) ws[i] = w[i];
+    __syncthreads();
+    const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
+    const long long n = blockIdx.z;
+    const int h0 = blockIdx.y * TT_H, w0 = blockIdx.x * TT_W;
+    const int rowp = p.W * p.x_ld;
+    for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
+        const int ho = h0 + (pidx >> 4), wo = w0 + (pidx & 15);
+        const bool valid = ho < p.Ho && wo < p.Wo;
+        float acc[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+        if (valid) {
+            const float* xb = x + ((n * p.H + ho) * p.W + wo) * p.x_ld + p.x_coff;
+            const bool vr0 = ho > 0, vr2 = ho + 1 < p.H, vc0 = wo > 0, vc2 = wo + 1 < p.W;
+            for (int c4 = sub; c4 < cin4; c4 += lpp) {
+                const float* xc = xb + c4 * 4;
+                const float* wc = ws + c4 * 4;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const bool vr = r == 0 ? vr0 : (r == 2 ? vr2 : true);
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        const bool vc = s == 0 ? vc0 : (s == 2 ? vc2 : true);
+                        if (vr && vc) {
+                            float4 xv = *reinterpret_cast<const float4*>(xc + (r - 1) * rowp + (s - 1) * p.x_ld);
+                            if (INACT) xv = lrelu4(xv);
+#pragma unroll
+                            for (int co = 0; co < COUT; ++co) {
+                                const float4 wv = *reinterpret_cast<const float4*>(wc + (co * 9 + r * 3 + s) * p.Cin);
+                                acc[co] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        for (int o = lpp >> 1; o > 0; o >>= 1)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+        if (valid && sub == 0) {
+            const long long pix = (n * p.Ho + ho) * p.Wo + wo;
+            float* yp = y + pix * p.y_ld + p.y_coff;
+            const float* rp = residual ? residual + pix * p.res_ld + p.res_coff : nullptr;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                float t = acc[co];
+                if (bias) t += bias[co];
+                if (rp) t += rp[co];
+                yp[co] = fsv_act(t, p.act) * p.out_scale;
+            }
+        }
+    }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(TT_THREADS) k_tco_dgrad_k3(ThinP p, int lpp, const float* __restrict__ dy, const float* __restrict__ w,
+                                                             float* __restrict__ dx, int accumulate) {
+    extern __shared__ __align__(16) float ws[];
+    const int cin4 = p.Cin >> 2;
+    for (int i = threadIdx.x; i < COUT * 9 * p.Cin; i += TT_THREADS) ws[i] = w[i];
+    __syncthreads();
+    const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
+    const long long n = blockIdx.z;
+    const int h0 = blockIdx.y * TT_H, w0 = blockIdx.x * TT_W;
+    const int rowp = p.Wo * p.y_ld;
+    for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
+        const int hq = h0 + (pidx >> 4), wq = w0 + (pidx & 15);
+        if (hq >= p.H || wq >= p.W) continue;
+        // tap (r, s) reads dy at (hq + 1 - r, wq + 1 - s)
+        const float* db = dy + ((n * p.Ho + hq) * p.Wo + wq) * p.y_ld + p.y_coff;
+        const bool vr0 = hq + 1 < p.Ho, vr2 = hq > 0, vc0 = wq + 1 < p.Wo, vc2 = wq > 0;
+        float dv[9][COUT];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const bool vr = r == 0 ? vr0 : (r == 2 ? vr2 : true);
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const bool vc = s == 0 ? vc0 : (s == 2 ? vc2 : true);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) dv[r * 3 + s][co] = (vr && vc) ? db[(1 - r) * rowp + (1 - s) * p.y_ld + co] : 0.f;
+            }
+        }
+        for (int c4 = sub; c4 < cin4; c4 += lpp) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* wc = ws + c4 * 4;
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wc + (co * 9 + t) * p.Cin);
+                    acc.x += dv[t][co] * wv.x; acc.y += dv[t][co] * wv.y; acc.z += dv[t][co] * wv.z; acc.w += dv[t][co] * wv.w;
+                }
+            float4* xp = reinterpret_cast<float4*>(dx + ((n * p.H + hq) * p.W + wq) * p.x_ld + p.x_coff) + c4;
+            if (accumulate) {
+                const float4 o = *xp;
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            *xp = acc;
+        }
+    }
+}
+
+// grid (persistent tile walkers, 3 tap rows x channel groups)
+template <int COUT, bool INACT>
+__global__ void __launch_bounds__(TT_THREADS) k_tco_wgrad_k3(ThinP p, int lpp, int tiles_x, int tiles_y, long long ntiles,
+                                                             const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw) {
+    __shared__ float red[3 * COUT * 128];
+    const int cin4 = p.Cin >> 2;
+    const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
+    const int tr = blockIdx.y % 3, cg = blockIdx.y / 3;
+    const int c4 = cg * lpp + sub;
+    const bool cvalid = c4 < cin4;
+    float4 acc[3][COUT];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[s][co] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long q = tile / tiles_x;
+        const int ty = (int)(q % tiles_y);
+        const long long n = q / tiles_y;
+        for (int pidx = slot; pidx < TT_W * TT_H; pidx += slots) {
+            const int ho = ty * TT_H + (pidx >> 4), wo = tx * TT_W + (pidx & 15);
+            const int ih = ho + tr - 1;
+            if (!cvalid || ho >= p.Ho || wo >= p.Wo || ih < 0 || ih >= p.H) continue;
+            const float* dp = dy + ((n * p.Ho + ho) * p.Wo + wo) * p.y_ld + p.y_coff;
+            float dv[COUT];
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) dv[co] = dp[co];
+            const float* xr = x + ((n * p.H + ih) * p.W + wo) * p.x_ld + p.x_coff + c4 * 4;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int iw = wo + s - 1;
+                if (iw >= 0 && iw < p.W) {
+                    float4 xv = *reinterpret_cast<const float4*>(xr + (s - 1) * p.x_ld);
+                    if (INACT) xv = lrelu4(xv);
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) {
+                        acc[s][co].x += dv[co] * xv.x; acc[s][co].y += dv[co] * xv.y;
+                        acc[s][co].z += dv[co] * xv.z; acc[s][co].w += dv[co] * xv.w;
+                    }
+                }
+            }
+        }
+    }
+    for (int o = lpp; o < 32; o <<= 1) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                acc[s][co].x += __shfl_xor_sync(0xffffffffu, acc[s][co].x, o);
+                acc[s][co].y += __shfl_xor_sync(0xffffffffu, acc[s][co].y, o);
+                acc[s][co].z += __shfl_xor_sync(0xffffffffu, acc[s][co].z, o);
+                acc[s][co].w += __shfl_xor_sync(0xffffffffu, acc[s][co].w, o);
+            }
+    }
+    const int row = lpp * 4;
+    for (int i = threadIdx.x; i < 3 * COUT * row; i += TT_THREADS) red[i] = 0.f;
+    __syncthreads();
+    if ((threadIdx.x & 31) < lpp && cvalid) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                float* rp = red + (s * COUT + co) * row + sub * 4;
+                atomicAdd(rp + 0, acc[s][co].x); atomicAdd(rp + 1, acc[s][co].y);
+                atomicAdd(rp + 2, acc[s][co].z); atomicAdd(rp + 3, acc[s][co].w);
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * COUT * row; i += TT_THREADS) {
+        const int cc = i % row, sc = i / row;
+        const int co = sc % COUT, s = sc / COUT;
+        const int ci = cg * row + cc;
+        if (ci < p.Cin) atomicAdd(dw + ((long long)co * 9 + tr * 3 + s) * p.Cin + ci, red[i]);
+    }
+}
+
 // ------------------------------------------------------------------ Cin <= 8 data gradient (thin OUTPUT dx, wide dy)
 // dx[n,h,w,ci] = sum_{r,s,co} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,co] * w[co][r][s][ci]; one thread per dx pixel.
 // Needed for the discriminator's first conv (8 -> 32, k4 s2): its input carries the generated image.
@@ -372,6 +564,12 @@ static void tt_tile(int lpp, long long n, int hh, int ww, int* tw, int* th) {
         else break;
     }
 }
+// 3x3 / stride 1 / pad 1 on full 16x8 tiles with 32-bit tap offsets: the unrolled fast paths apply
+static bool tco_k3(const fsv_conv_desc* d, int tw, int th) {
+    return d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && tw == TT_W && th == TT_H &&
+           (long long)d->W * d->x_ld < (1 << 28) && (long long)d->Wo * d->y_ld < (1 << 28) &&
+           (d->in_act == FSV_ACT_NONE || d->in_act == FSV_ACT_LRELU);
+}
 static int tt_lpp(int cin) {
     int l = 1;
     while (l * 2 <= cin / 4 && l < 32) l *= 2;
@@ -395,6 +593,19 @@ extern "C" int fsv_conv2d_fwd_thin(const fsv_conv_desc* d, const float* x, const
         int lpp = tt_lpp(d->Cin), tw, th;
         tt_tile(lpp, d->N, d->Ho, d->Wo, &tw, &th);
         dim3 grid(fsv_cdiv(d->Wo, tw), fsv_cdiv(d->Ho, th), d->N);
+        if (tco_k3(d, tw, th)) {
+#define TCO_FWD3(C) do { if (d->in_act == FSV_ACT_LRELU) k_tco_fwd_k3<C, true><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); \
+                         else k_tco_fwd_k3<C, false><<<grid, TT_THREADS, sm, st>>>(p, lpp, x, w, bias, residual, y); } while (0)
+            switch (d->Cout) {
+                case 1: TCO_FWD3(1); break;
+                case 2: TCO_FWD3(2); break;
+                case 3: TCO_FWD3(3); break;
+                default: TCO_FWD3(4); break;
+            }
+#undef TCO_FWD3
+            FSV_CHECK_LAUNCH("conv2d_fwd_thin_k3");
+            return FSV_OK;
+        }
         switch (d->Cout) {
             case 1: k_tco_fwd<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, x, w, bias, residual, y); break;
             case 2: k_tco_fwd<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, x, w, bias, residual, y); break;
@@ -423,6 +634,23 @@ extern "C" int fsv_conv2d_wgrad_thin(const fsv_conv_desc* d, const float* x, con
     const int groups = fsv_cdiv(d->Cin / 4, lpp);
     long long gx = (2LL * fsv_sm_count() + groups - 1) / groups;
     if (gx > ntiles) gx = ntiles;
+    if (tco_k3(d, tw, th)) {
+        long long g3 = (4LL * fsv_sm_count() + 3 * groups - 1) / (3 * groups);
+        if (g3 > ntiles) g3 = ntiles;
+        dim3 grid3((unsigned)g3, 3 * groups);
+#define TCO_WG3(C) do { if (d->in_act == FSV_ACT_LRELU) k_tco_wgrad_k3<C, true><<<grid3, TT_THREADS, 0, st>>>(p, lpp, tiles_x, tiles_y, ntiles, x, dy, dw); \
+                        else k_tco_wgrad_k3<C, false><<<grid3, TT_THREADS, 0, st>>>(p, lpp, tiles_x, tiles_y, ntiles, x, dy, dw); } while (0)
+        switch (d->Cout) {
+            case 1: TCO_WG3(1); break;
+            case 2: TCO_WG3(2); break;
+            case 3: TCO_WG3(3); break;
+            default: TCO_WG3(4); break;
+        }
+#undef TCO_WG3
+        FSV_CHECK_LAUNCH("conv2d_wgrad_thin_k3");
+        *handled = 1;
+        return FSV_OK;
+    }
     dim3 grid((unsigned)gx, groups);
 #define TCO_WGRAD(T, C) k_tco_wgrad<T, C><<<grid, TT_THREADS, 0, st>>>(p, lpp, tw, th, tiles_x, tiles_y, ntiles, x, dy, dw)
     if (taps <= 9) {
@@ -465,6 +693,16 @@ extern "C" int fsv_conv2d_dgrad_thin(const fsv_conv_desc* d, const float* dy, co
         int lpp = tt_lpp(d->Cin), tw, th;
         tt_tile(lpp, d->N, d->H, d->W, &tw, &th);
         dim3 grid(fsv_cdiv(d->W, tw), fsv_cdiv(d->H, th), d->N);
+        if (tco_k3(d, tw, th)) {
+            switch (d->Cout) {
+                case 1: k_tco_dgrad_k3<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+                case 2: k_tco_dgrad_k3<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+                case 3: k_tco_dgrad_k3<3><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+                default: k_tco_dgrad_k3<4><<<grid, TT_THREADS, sm, st>>>(p, lpp, dy, w, dx, accumulate); break;
+            }
+            FSV_CHECK_LAUNCH("conv2d_dgrad_thin_k3");
+            return FSV_OK;
+        }
         switch (d->Cout) {
             case 1: k_tco_dgrad<1><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, dy, w, dx, accumulate); break;
             case 2: k_tco_dgrad<2><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, dy, w, dx, accumulate); break;
