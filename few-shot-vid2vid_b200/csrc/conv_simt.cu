@@ -415,6 +415,106 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_flat(ConvP p, const float* _
     }
 }
 
+// Second version of the thin-input weight gradient: a 32 (co) x BNJ (tap,ci) tile instead of 64 x 64 -- the layers it
+// serves have 32 output channels and 9..128 (tap,ci) columns, so the square tile ran at 7-50 % utilisation.  The 256
+// threads are (BNJ/4 column quads) x (8 co quads) x KS pixel slices; every slice owns BK/KS of the chunk's pixels and
+// the slices meet in the final atomics.  BNJ = 16 (taps*Cin <= 16, e.g. the 1-channel label conv) or 64.
+template <int BNJ>
+__global__ void __launch_bounds__(256) k_conv_wgrad_flat2(ConvP p, const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dw, int j_tiles, int chunks_per_sample, int pix_per_chunk) {
+    constexpr int QJ = BNJ / 4;              // column quads
+    constexpr int KS = 256 / (QJ * 8);       // pixel slices: 2 (BNJ 64) or 8 (BNJ 16)
+    constexpr int KPS = BK / KS;             // pixels per slice per chunk
+    constexpr int BPT = BK * BNJ / 256;      // gathered x values per thread per chunk: 4 or 1
+    __shared__ __align__(16) float As[BK][32 + PADM];    // dy tile  [pixel][co]
+    __shared__ __align__(16) float Bs[BK][BNJ + PADM];   // x gather [pixel][j]
+    const int tid = threadIdx.x;
+    const int tx = tid % QJ, ty = (tid / QJ) & 7, kz = tid / (QJ * 8);
+    const int co0 = (blockIdx.x / j_tiles) * 32;
+    const int j0 = (blockIdx.x % j_tiles) * BNJ;
+    const int n = blockIdx.z / chunks_per_sample;
+    const int chunk = blockIdx.z - n * chunks_per_sample;
+    const int MP = p.Ho * p.Wo;
+    const int px0 = chunk * pix_per_chunk;
+    const int px1 = min(px0 + pix_per_chunk, MP);
+    const int taps = p.kh * p.kw, tc = taps * p.Cin;
+    const float* dyn = dy + (long long)n * MP * p.y_ld + p.y_coff;
+    const float* xn = x + (long long)n * p.H * p.W * p.x_ld + p.x_coff;
+    const bool a_vec = ((p.y_ld & 3) == 0) && ((p.y_coff & 3) == 0) && ((p.Cout & 3) == 0) && ((((uintptr_t)dy) & 15) == 0);
+    // loader roles: B -- thread owns BPT consecutive columns of pixel row kb; A -- threads < 128 own one float4 of dy
+    const int kb = tid / (BNJ / BPT), cb = (tid % (BNJ / BPT)) * BPT;
+    const int ka = tid >> 3, ca = (tid & 7) * 4;
+    int jr[BPT], js[BPT], jc[BPT];
+#pragma unroll
+    for (int e = 0; e < BPT; ++e) {
+        int j = j0 + cb + e;
+        int tap = j < tc ? j / p.Cin : 0;
+        jc[e] = j < tc ? j - tap * p.Cin : -1;
+        jr[e] = tap / p.kw;
+        js[e] = tap - jr[e] * p.kw;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int p0 = px0; p0 < px1; p0 += BK) {
+        if (tid < 128) {
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            const int px = p0 + ka, co = co0 + ca;
+            if (px < px1 && co < p.Cout) {
+                const float* ptr = dyn + (long long)px * p.y_ld + co;
+                if (a_vec) { float4 t = *reinterpret_cast<const float4*>(ptr); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+                else { a[0] = ptr[0]; if (co + 1 < p.Cout) a[1] = ptr[1]; if (co + 2 < p.Cout) a[2] = ptr[2]; if (co + 3 < p.Cout) a[3] = ptr[3]; }
+            }
+            *reinterpret_cast<float4*>(&As[ka][ca]) = make_float4(a[0], a[1], a[2], a[3]);
+        }
+        {
+            float b[BPT];
+#pragma unroll
+            for (int e = 0; e < BPT; ++e) b[e] = 0.f;
+            const int px = p0 + kb;
+            if (px < px1) {
+                const int ho = px / p.Wo, wo = px - ho * p.Wo;
+#pragma unroll
+                for (int e = 0; e < BPT; ++e) {
+                    if (jc[e] >= 0) {
+                        const int ih = ho * p.stride + jr[e] - p.pad, iw = wo * p.stride + js[e] - p.pad;
+                        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                            float v = xn[((long long)ih * p.W + iw) * p.x_ld + jc[e]];
+                            b[e] = p.in_act == FSV_ACT_LRELU ? fsv_act(v, FSV_ACT_LRELU) : v;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < BPT; ++e) Bs[kb][cb + e] = b[e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < KPS; ++kk) {
+            const int k = kz * KPS + kk;
+            float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            acc[0][0] += av.x * bv.x; acc[0][1] += av.x * bv.y; acc[0][2] += av.x * bv.z; acc[0][3] += av.x * bv.w;
+            acc[1][0] += av.y * bv.x; acc[1][1] += av.y * bv.y; acc[1][2] += av.y * bv.z; acc[1][3] += av.y * bv.w;
+            acc[2][0] += av.z * bv.x; acc[2][1] += av.z * bv.y; acc[2][2] += av.z * bv.z; acc[2][3] += av.z * bv.w;
+            acc[3][0] += av.w * bv.x; acc[3][1] += av.w * bv.y; acc[3][2] += av.w * bv.z; acc[3][3] += av.w * bv.w;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int co = co0 + ty * 4 + i;
+        if (co >= p.Cout) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int j = j0 + tx * 4 + e;
+            if (j < tc) atomicAdd(dw + (long long)co * tc + j, acc[i][e]);
+        }
+    }
+}
+
 // per-(sample-group, channel) column sums of dy -> dbias (fp32 atomics into a zeroed buffer)
 __global__ void k_colsum(const float* __restrict__ dy, int ld, int coff, long long rows_per_group, int C, long long out_gstride,
                          float* __restrict__ out) {
@@ -460,7 +560,11 @@ extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const fl
         if (d->Cin <= 8 && d->up == 1 && d->w_nstride == 0) {
             // thin input: flatten (tap, ci) into the GEMM column axis
             const int tc = taps * d->Cin;
-            int co_tiles = fsv_cdiv(d->Cout, BM), j_tiles = fsv_cdiv(tc, BN);
+            static int flat_v1 = -1;
+            if (flat_v1 < 0) { const char* e = getenv("FSV_WGRAD_FLAT_V1"); flat_v1 = (e && atoi(e)) ? 1 : 0; }
+            const int bm = flat_v1 ? BM : 32;
+            const int bnj = flat_v1 ? BN : (tc <= 16 ? 16 : 64);
+            int co_tiles = fsv_cdiv(d->Cout, bm), j_tiles = fsv_cdiv(tc, bnj);
             long long base = (long long)co_tiles * j_tiles;
             long long want = ((long long)fsv_sm_count() * 8 + base - 1) / base;
             long long per_sample = (want + d->N - 1) / d->N;
@@ -472,7 +576,9 @@ extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const fl
             int chunks_per_sample = fsv_cdiv(MP, pix_per_chunk);
             dim3 grid(co_tiles * j_tiles, 1, d->N * chunks_per_sample);
             FSV_REQUIRE(grid.z <= 65535, "conv2d_wgrad: grid too large");
-            k_conv_wgrad_flat<<<grid, 256, 0, st>>>(p, x, dy, dw, j_tiles, chunks_per_sample, pix_per_chunk);
+            if (flat_v1) k_conv_wgrad_flat<<<grid, 256, 0, st>>>(p, x, dy, dw, j_tiles, chunks_per_sample, pix_per_chunk);
+            else if (bnj == 16) k_conv_wgrad_flat2<16><<<grid, 256, 0, st>>>(p, x, dy, dw, j_tiles, chunks_per_sample, pix_per_chunk);
+            else k_conv_wgrad_flat2<64><<<grid, 256, 0, st>>>(p, x, dy, dw, j_tiles, chunks_per_sample, pix_per_chunk);
             FSV_CHECK_LAUNCH("conv2d_wgrad_flat");
             goto bias_part;
         }

@@ -192,6 +192,37 @@ __global__ void __launch_bounds__(SN_CI) k_sn_scale(const float* __restrict__ W,
         for (int t = 0; t < taps; ++t) out[r * K + (size_t)t * Cin + ci0 + threadIdx.x] = sm[threadIdx.x * tp + t];
 }
 
+// phase 3, two-output variant: besides W_sn (R, taps, Cin) also emit wt (Cin, taps, R) = the same weight with its
+// channel axes swapped, which is the B operand of the tcgen05 data gradient (conv_tc.cu) -- otherwise a strided torch
+// copy per conv per step.  Block = (RB rows) x (32 input channels) x all taps, staged in shared memory with odd pitches
+// so that both output orders are written in full 128-byte (64-byte for RB = 16) segments without bank conflicts.
+__global__ void __launch_bounds__(SN_THREADS) k_sn_scale_t(const float* __restrict__ W, const float* __restrict__ sigma, int R, int Cin,
+                                                           int taps, int RB, float* __restrict__ out, float* __restrict__ wt) {
+    extern __shared__ float smt[];                 // [(row * 33 + j) * tp + t]
+    const float inv = 1.f / *sigma;
+    const int tp = taps | 1;
+    const int r0 = blockIdx.y * RB, ci0 = blockIdx.x * 32;
+    const int nr = min(RB, R - r0), nj = min(32, Cin - ci0);
+    const size_t K = (size_t)Cin * taps;
+    const int run = nj * taps;                     // contiguous floats per row in the source
+    for (int e = threadIdx.x; e < nr * run; e += SN_THREADS) {
+        const int row = e / run, off = e - row * run;
+        const int j = off / taps, t = off - j * taps;
+        smt[(row * 33 + j) * tp + t] = W[(size_t)(r0 + row) * K + (size_t)ci0 * taps + off] * inv;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * taps * 32; e += SN_THREADS) {        // W_sn[r][t][ci]
+        const int j = e & 31, rt = e >> 5;
+        const int t = rt % taps, row = rt / taps;
+        if (j < nj) out[(size_t)(r0 + row) * K + (size_t)t * Cin + ci0 + j] = smt[(row * 33 + j) * tp + t];
+    }
+    for (int e = threadIdx.x; e < nj * taps * RB; e += SN_THREADS) {        // wt[ci][t][r]
+        const int row = e % RB, jt = e / RB;
+        const int t = jt % taps, j = jt / taps;
+        if (row < nr) wt[((size_t)(ci0 + j) * taps + t) * R + r0 + row] = smt[(row * 33 + j) * tp + t];
+    }
+}
+
 // backward phase 1: c = sum dW_sn * W_sn  (both OHWI, contiguous)
 __global__ void __launch_bounds__(SN_THREADS) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, long long total,
                                                        float* part, float* __restrict__ c_out) {
@@ -259,7 +290,7 @@ extern "C" long long fsv_spectral_workspace(int R, int K) {
 }
 
 extern "C" int fsv_spectral_fwd(const float* w_orig, float* u, float* v, int R, int Cin, int taps, int power, float eps,
-                                float* w_out, float* uvs, float* work, void* stream) {
+                                float* w_out, float* wt_out, float* uvs, float* work, void* stream) {
     FSV_REQUIRE(R > 0 && R <= 65535 && Cin > 0 && taps > 0 && taps <= SN_MAXTAPS, "spectral_fwd: bad dims (R %d Cin %d taps %d)", R, Cin, taps);
     FSV_REQUIRE(w_orig && u && v && w_out && uvs && work, "spectral_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -282,6 +313,15 @@ extern "C" int fsv_spectral_fwd(const float* w_orig, float* u, float* v, int R, 
     k_sn_wv<<<fsv_cdiv(R, SN_THREADS / 32), SN_THREADS, 0, st>>>(w_orig, power ? part : v, nrm_part, nchunks, R, K, power, eps, s, u, u_save,
                                                                  v, v_save, sigma);
     FSV_CHECK_LAUNCH("spectral_wv");
+    if (wt_out) {
+        const int RB = taps <= 9 ? 32 : 16;
+        const size_t sm = (size_t)RB * 33 * (taps | 1) * sizeof(float);
+        dim3 gt(fsv_cdiv(Cin, 32), fsv_cdiv(R, RB));
+        FSV_REQUIRE(gt.y <= 65535, "spectral_fwd: too many rows");
+        k_sn_scale_t<<<gt, SN_THREADS, sm, st>>>(w_orig, sigma, R, Cin, taps, RB, w_out, wt_out);
+        FSV_CHECK_LAUNCH("spectral_scale_t");
+        return FSV_OK;
+    }
     dim3 g3(fsv_cdiv(Cin, SN_CI), R);
     k_sn_scale<<<g3, SN_CI, 0, st>>>(w_orig, sigma, Cin, taps, w_out);
     FSV_CHECK_LAUNCH("spectral_scale");

@@ -75,7 +75,7 @@ SIGNATURES = {
     'fsv_softmax_rows_fwd': [c_vp, c_vp, c_ll, c_int, c_vp],
     'fsv_softmax_rows_bwd': [c_vp, c_vp, c_vp, c_ll, c_int, c_vp],
     'fsv_spectral_workspace': [c_int, c_int],
-    'fsv_spectral_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp],
+    'fsv_spectral_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     'fsv_spectral_bwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
 }
 

@@ -27,14 +27,20 @@ class Conv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
         nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
 
-    def ohwi(self):
+    def ohwi(self, want_wt=False):
+        """OHWI weight [and its channel-swapped copy for the tcgen05 data gradient, or None]."""
         if getattr(self, 'fsv_spectral', False):
-            return ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v, self.training, self.fsv_spectral_eps)
-        return self.weight.permute(0, 2, 3, 1).contiguous()
+            return ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v, self.training, self.fsv_spectral_eps,
+                                       want_wt=want_wt)
+        w = self.weight.permute(0, 2, 3, 1).contiguous()
+        return (w, None) if want_wt else w
 
     def forward(self, x, up=1, act=ACT_NONE, residual=None, out_scale=1.0, in_act=ACT_NONE):
-        return ops.conv2d(x, self.ohwi(), self.bias, stride=self.stride, pad=self.padding, up=up, act=act,
-                          out_scale=out_scale, residual=residual, in_act=in_act)
+        # the swapped copy only pays off where the tensor-core data gradient will run (conv_tc.cu eligibility)
+        want = self.in_channels % 16 == 0 and self.out_channels % 32 == 0 and x.requires_grad
+        w, wt = self.ohwi(want_wt=True) if want else (self.ohwi(), None)
+        return ops.conv2d(x, w, self.bias, stride=self.stride, pad=self.padding, up=up, act=act,
+                          out_scale=out_scale, residual=residual, in_act=in_act, wt=wt)
 
 
 class Linear(nn.Module):
@@ -48,11 +54,15 @@ class Linear(nn.Module):
         nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
 
     def forward(self, x, act=ACT_NONE):
+        wt = None
         if getattr(self, 'fsv_spectral', False):
-            w = ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v, self.training, self.fsv_spectral_eps)
+            want = self.in_features % 16 == 0 and self.out_features % 32 == 0 and x.requires_grad
+            w, wt = ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v, self.training, self.fsv_spectral_eps,
+                                        want_wt=True) if want else (ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v,
+                                                                                        self.training, self.fsv_spectral_eps), None)
         else:
             w = self.weight
-        return ops.linear(x, w, self.bias, act=act)
+        return ops.linear(x, w, self.bias, act=act, wt=wt)
 
 
 def spectral(module):

@@ -311,7 +311,9 @@ class Conv2dFn(torch.autograd.Function):
                 dd.up = 1
                 if lib.fsv_conv2d_dgrad_tc_eligible(ctypes.byref(dd)):
                     # tcgen05 data gradient: the kernel wants the weight with its channel axes swapped, wt[ci][r][s][co]
-                    wt = wbase.reshape(d.Cout, d.kh, d.kw, d.Cin).permute(3, 1, 2, 0).contiguous()
+                    wt = cfg.get('wt')
+                    if wt is None or wt.numel() != wbase.numel():
+                        wt = wbase.reshape(d.Cout, d.kh, d.kw, d.Cin).permute(3, 1, 2, 0).contiguous()
                     _call(lib.fsv_conv2d_dgrad_tc, ctypes.byref(dd), ptr(g), ptr(wt), ptr(dfull), st)
                     done = True
             if not done:
@@ -351,10 +353,12 @@ class Conv2dFn(torch.autograd.Function):
 
 
 def conv2d(x, w_ohwi, bias=None, stride=1, pad=0, up=1, act=ACT_NONE, out_scale=1.0, residual=None, use_tc=None,
-           in_act=ACT_NONE):
+           in_act=ACT_NONE, wt=None):
+    """``wt``: optional (Cin, kh, kw, Cout) copy of the weight with swapped channel axes (spectral_weight(want_wt=True));
+    saves the transposing copy the tcgen05 data gradient would otherwise make."""
     cout, kh, kw, _ = w_ohwi.shape
     cfg = dict(cout=cout, kh=kh, kw=kw, stride=stride, pad=pad, up=up, act=act, out_scale=out_scale, use_tc=use_tc,
-               in_act=in_act)
+               in_act=in_act, wt=wt)
     return Conv2dFn.apply(x, w_ohwi, bias, residual, cfg)
 
 
@@ -366,49 +370,64 @@ def batch_conv1x1(x, flat, cout, cin, w_off, b_off, act=ACT_NONE):
     return Conv2dFn.apply(x, flat, flat, None, cfg)
 
 
-def linear(x2d, w, bias, act=ACT_NONE):
+def linear(x2d, w, bias, act=ACT_NONE, wt=None):
     """F.linear on (rows, K) with w (out, K): a 1x1 conv over a rows x 1 'image'."""
     rows, k = x2d.shape
     wcols = 32 if rows % 32 == 0 else 1      # a 1x1 conv does not care how the rows are arranged as an image; 32-wide rows
-    y = conv2d(x2d.reshape(1, rows // wcols, wcols, k), w.reshape(w.shape[0], 1, 1, k), bias, act=act)   # suit the TMA boxes
+    y = conv2d(x2d.reshape(1, rows // wcols, wcols, k), w.reshape(w.shape[0], 1, 1, k), bias, act=act, wt=wt)   # suit the TMA boxes
     return y.reshape(rows, w.shape[0])
 
 
 # --------------------------------------------------------------------------- spectral normalisation of weights
 
+# emit the channel-swapped copy of a spectral weight for the tcgen05 data gradient from the spectral kernel itself
+SPECTRAL_EMIT_WT = True
+
+
 class SpectralWeightFn(torch.autograd.Function):
     """torch.nn.utils.spectral_norm's weight computation (one power iteration in training mode, ``weight_u/_v`` advanced
-    in place) fused with the OIHW -> OHWI repack: weight_orig (R, Cin[, kh, kw]) -> W / sigma as (R[, kh, kw], Cin)."""
+    in place) fused with the OIHW -> OHWI repack: weight_orig (R, Cin[, kh, kw]) -> W / sigma as (R[, kh, kw], Cin).
+    With ``want_wt`` a second, non-differentiable output holds the same weight as (Cin[, kh, kw], R)."""
 
     @staticmethod
-    def forward(ctx, w_orig, u, v, training, eps):
+    def forward(ctx, w_orig, u, v, training, eps, want_wt):
         w = _c(w_orig)
         _lib.require_cuda(u, v)
         R, cin = w.shape[0], w.shape[1]
         taps = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
         K = cin * taps
         out = torch.empty((R, w.shape[2], w.shape[3], cin) if w.dim() == 4 else (R, cin), device=w.device, dtype=torch.float32)
+        wt = None
+        if want_wt:
+            wt = torch.empty((cin, w.shape[2], w.shape[3], R) if w.dim() == 4 else (cin, R), device=w.device, dtype=torch.float32)
         uvs = torch.empty(K + R + 1, device=w.device, dtype=torch.float32)
         work = torch.empty(lib.fsv_spectral_workspace(R, K) // 4, device=w.device, dtype=torch.float32)
-        _call(lib.fsv_spectral_fwd, ptr(w), ptr(u), ptr(v), R, cin, taps, 1 if training else 0, float(eps), ptr(out), ptr(uvs),
-              ptr(work), stream())
+        _call(lib.fsv_spectral_fwd, ptr(w), ptr(u), ptr(v), R, cin, taps, 1 if training else 0, float(eps), ptr(out), ptr(wt),
+              ptr(uvs), ptr(work), stream())
         ctx.save_for_backward(out, uvs)
         ctx.dims = (R, cin, taps, tuple(w_orig.shape))
+        if want_wt:
+            ctx.mark_non_differentiable(wt)
+            return out, wt
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, *unused):
         out, uvs = ctx.saved_tensors
         R, cin, taps, shape = ctx.dims
         dout = _c(dout)
         dw = torch.empty(shape, device=dout.device, dtype=torch.float32)
         work = torch.empty(lib.fsv_spectral_workspace(R, cin * taps) // 4, device=dout.device, dtype=torch.float32)
         _call(lib.fsv_spectral_bwd, ptr(dout), ptr(out), ptr(uvs), R, cin, taps, ptr(dw), ptr(work), stream())
-        return dw, None, None, None, None
+        return dw, None, None, None, None, None
 
 
-def spectral_weight(w_orig, u, v, training, eps=1e-12):
-    return SpectralWeightFn.apply(w_orig, u, v, training, eps)
+def spectral_weight(w_orig, u, v, training, eps=1e-12, want_wt=False):
+    """-> W_sn (OHWI), or (W_sn, wt) with ``want_wt`` (wt = None when SPECTRAL_EMIT_WT is off)."""
+    if want_wt and SPECTRAL_EMIT_WT and torch.is_grad_enabled():
+        return SpectralWeightFn.apply(w_orig, u, v, training, eps, True)
+    out = SpectralWeightFn.apply(w_orig, u, v, training, eps, False)
+    return (out, None) if want_wt else out
 
 
 # --------------------------------------------------------------------------- normalisation (+ activation)

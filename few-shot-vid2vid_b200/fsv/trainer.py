@@ -88,6 +88,9 @@ def generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_imag
     return losses, fake
 
 
+FUSED_ADAM = True
+
+
 def make_optimizers(opt, netG, netD, capturable=False):
     """base_model.py:39-48 Adam with TTUR.  ``capturable`` keeps the step counters on the device so the whole
     iteration can be recorded into a CUDA graph (same arithmetic)."""
@@ -95,8 +98,13 @@ def make_optimizers(opt, netG, netD, capturable=False):
         beta1, beta2, g_lr, d_lr = opt.beta1, 0.999, opt.lr, opt.lr
     else:
         beta1, beta2, g_lr, d_lr = 0.0, opt.beta2, opt.lr / 2, opt.lr * 2
-    return (torch.optim.Adam(netG.parameters(), lr=g_lr, betas=(beta1, beta2), capturable=capturable),
-            torch.optim.Adam(netD.parameters(), lr=d_lr, betas=(beta1, beta2), capturable=capturable))
+    # fused=True: torch's single-kernel multi-tensor Adam (same update rule; ~7 instead of ~30 passes over the 98 M generator
+    # parameters and their moments) -- the optimizer is parameter-side plumbing, as in the reference (base_model.py:39-48)
+    def adam(net, lr):
+        params = list(net.parameters())
+        fused = FUSED_ADAM and all(p.is_cuda for p in params)
+        return torch.optim.Adam(params, lr=lr, betas=(beta1, beta2), capturable=capturable, fused=True if fused else None)
+    return adam(netG, g_lr), adam(netD, d_lr)
 
 
 class GraphedStep:

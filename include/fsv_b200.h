@@ -219,12 +219,13 @@ int fsv_softmax_rows_bwd(const float* y, const float* dy, float* dx, long long r
  * (architecture.py:60,81-84, generator.py:106-109, normalization.py:64-65, discriminator.py:69-88).
  * w_orig: weight_orig, (R, Cin, taps) contiguous (OIHW, taps = kh*kw; 1 for nn.Linear); u: weight_u (R), v: weight_v
  * (K = Cin*taps).  power=1 (training): one power iteration, u and v advance IN PLACE; power=0 (eval): none.
- * w_out: (R, taps, Cin) = w_orig / sigma repacked OHWI for fsv_conv2d_*; uvs: (K + R + 1) floats = [v | u | sigma] as
- * used for this call (the backward needs them after the buffers moved on).  work: fsv_spectral_workspace(R, K) bytes.
+ * w_out: (R, taps, Cin) = w_orig / sigma repacked OHWI for fsv_conv2d_*; wt_out: NULL or (Cin, taps, R), the same
+ * weight with the channel axes swapped (the B operand fsv_conv2d_dgrad_tc wants); uvs: (K + R + 1) floats = [v | u | sigma]
+ * as used for this call (the backward needs them after the buffers moved on).  work: fsv_spectral_workspace(R, K) bytes.
  * Backward, u and v constants:  dw_orig (R, Cin, taps) = (dw_ohwi - (sum dw_ohwi * w_sn_ohwi) u v^T) / sigma. */
 long long fsv_spectral_workspace(int R, int K);
 int fsv_spectral_fwd(const float* w_orig, float* u, float* v, int R, int Cin, int taps, int power, float eps, float* w_out,
-                     float* uvs, float* work, void* stream);
+                     float* wt_out, float* uvs, float* work, void* stream);
 int fsv_spectral_bwd(const float* dw_ohwi, const float* w_sn_ohwi, const float* uvs, int R, int Cin, int taps, float* dw_orig,
                      float* work, void* stream);
 

@@ -420,3 +420,7 @@ def test_spectral_weight_vs_oracle(R, cin, k, training):
     assert rel_err(gc1, gr1) < 1e-4 and rel_err(gc2, gr2) < 1e-4
     if not training:
         assert torch.equal(uc.cpu(), u) and torch.equal(vc.cpu(), v)
+    # two-output variant: the channel-swapped copy the tcgen05 data gradient consumes
+    o3, wt = ops.spectral_weight(wc, uc.clone(), vc.clone(), False, want_wt=True)
+    assert wt is not None and torch.equal(wt, (o3.permute(3, 1, 2, 0) if k > 1 else o3.t()).contiguous())
+    assert rel_err(o3, o2 if not training else o3) < tol
