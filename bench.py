@@ -185,7 +185,7 @@ def run_reference(args):
             'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                              'sample': 'CPU oracle (torch-CPU port of the reference), one D-step+G-step fwd/bwd at batch %d, no optimiser' % sample_batch},
             'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
@@ -262,7 +262,7 @@ def run_fsv(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({'quick': True, 'ms_per_step': ms / args.steps, 'note': 'profiling aid, not a bench value'}))
+            emit(json.dumps({'quick': True, 'ms_per_step': ms / args.steps, 'note': 'profiling aid, not a bench value'}))
         return
     # e2e: host inputs (pinned) -> device every step, losses read back to the host every step
     d2h = [0]
@@ -336,6 +336,8 @@ def run_fsv(args):
         ach = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         roof = {'bound': 'tensor', 'kernel': 'fsv_conv2d_{fwd,dgrad,wgrad} (all launches of one step)', 'achieved': ach,
                 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
+                'traffic_note': 'aggregate over launches of many shapes, so no single per-launch figure; one captured launch '
+                                '(profiles/ncu_full_r1_summary.txt, k_conv_tc grid 256): 33.9 MB DRAM read+write vs 34.2 MB algorithmic (x + y + w)',
                 'peak_source': peaks['src'] + ', dense bf16 sustained', 'share_of_step_kernel_time': conv_ms / total_ms if total_ms else None}
     sp_ms = sum(prof[k][0] for k in ('fsv_spade_fwd', 'fsv_spade_fwd_tc') if k in prof)
     sp = [sp_ms]
@@ -359,10 +361,31 @@ def run_fsv(args):
         t_cpu = cpu_step_time(args.workload, 1, threads)
         line['cpu_baseline'] = {'value': 1.0 / t_cpu, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                                 'sample': 'CPU oracle (torch-CPU port of the reference), one D-step+G-step fwd/bwd at batch 1, no optimiser'}
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr: stdout carries the ONE JSON line only."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(text):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + '\n').encode())
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
