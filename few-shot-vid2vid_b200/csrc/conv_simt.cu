@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_flat(ConvP p, const float* _
 // Second version of the thin-input weight gradient: a 32 (co) x BNJ (tap,ci) tile instead of 64 x 64 -- the layers it
 // serves have 32 output channels and 9..128 (tap,ci) columns, so the square tile ran at 7-50 % utilisation.  The 256
 // threads are (BNJ/4 column quads) x (8 co quads) x KS pixel slices; every slice owns BK/KS of the chunk's pixels and
-// the slices meet in the final atomics.  BNJ = 16 (taps*Cin <= 16, e.g. the 1-channel label conv) or 64.
+// the slices meet in the final atomics.  Used with BNJ = 64 when taps*Cin > 64 (see the dispatch in fsv_conv2d_wgrad).
 template <int BNJ>
 __global__ void __launch_bounds__(256) k_conv_wgrad_flat2(ConvP p, const float* __restrict__ x, const float* __restrict__ dy,
                                                           float* __restrict__ dw, int j_tiles, int chunks_per_sample, int pix_per_chunk) {
@@ -560,10 +560,12 @@ extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const fl
         if (d->Cin <= 8 && d->up == 1 && d->w_nstride == 0) {
             // thin input: flatten (tap, ci) into the GEMM column axis
             const int tc = taps * d->Cin;
-            static int flat_v1 = -1;
-            if (flat_v1 < 0) { const char* e = getenv("FSV_WGRAD_FLAT_V1"); flat_v1 = (e && atoi(e)) ? 1 : 0; }
+            // measured on the B200 (profiles/breakdown_r1_cuda_events.txt history): the 32 x 64 tile wins only when there is
+            // more than one 64-column tile (8 ch x 4x4 taps: 0.39 -> 0.32 ms); for taps*Cin <= 64 the 64 x 64 kernel is as
+            // fast, and a 32 x 16 tile (tried for the 1-channel label conv) was 2.8x slower (sync-bound), so it is gone.
+            const int flat_v1 = tc <= 64 ? 1 : 0;
             const int bm = flat_v1 ? BM : 32;
-            const int bnj = flat_v1 ? BN : (tc <= 16 ? 16 : 64);
+            const int bnj = 64;
             int co_tiles = fsv_cdiv(d->Cout, bm), j_tiles = fsv_cdiv(tc, bnj);
             long long base = (long long)co_tiles * j_tiles;
             long long want = ((long long)fsv_sm_count() * 8 + base - 1) / base;
@@ -577,7 +579,6 @@ extern "C" int fsv_conv2d_wgrad(const fsv_conv_desc* d, const float* x, const fl
             dim3 grid(co_tiles * j_tiles, 1, d->N * chunks_per_sample);
             FSV_REQUIRE(grid.z <= 65535, "conv2d_wgrad: grid too large");
             if (flat_v1) k_conv_wgrad_flat<<<grid, 256, 0, st>>>(p, x, dy, dw, j_tiles, chunks_per_sample, pix_per_chunk);
-            else if (bnj == 16) k_conv_wgrad_flat2<16><<<grid, 256, 0, st>>>(p, x, dy, dw, j_tiles, chunks_per_sample, pix_per_chunk);
             else k_conv_wgrad_flat2<64><<<grid, 256, 0, st>>>(p, x, dy, dw, j_tiles, chunks_per_sample, pix_per_chunk);
             FSV_CHECK_LAUNCH("conv2d_wgrad_flat");
             goto bias_part;
