@@ -311,5 +311,57 @@ def main():
     save('ops.npz', **arrays)
 
 
+def variants():
+    """Two more dataset geometries of BASELINE.json (structure only, tiny widths), written to g_variants_tiny.npz:
+    'pose'  : 6-channel label, portrait frames H = 2W (fewshot_pose_dataset.py:23-25), warp_ref + spade_combine;
+    'street': wide frames W = 2H, 5-channel one-hot-like label, --adaptive_spade only (no warp, no spade_combine)."""
+    install_shims()
+    import models.networks as networks
+    import models.networks.generator as refgen
+    import models.loss_collector as reflc
+    refgen.resample = resample_any_device
+    reflc.resample = resample_any_device
+    small = dict(TINY, n_downsample_G=3, n_adaptive_layers=2, n_downsample_F=2, n_blocks_F=1)
+    cfgs = {
+        'pose': (dict(small, input_nc=6, aspect_ratio=0.5, fineSize=32, dataset_mode='fewshot_pose'), 64, 32),
+        'street': (dict(small, input_nc=5, aspect_ratio=2, fineSize=64, warp_ref=False, spade_combine=False,
+                        dataset_mode='fewshot_street'), 32, 64),
+    }
+    arrays = {}
+    gen = torch.Generator().manual_seed(4321)
+    for name, (cfg, H, W) in cfgs.items():
+        torch.manual_seed(7)
+        opt = Namespace(**cfg)
+        G = networks.define_G(opt)
+        G.train()
+        B, C = 2, cfg['input_nc']
+        label = torch.rand(B, C, H, W, generator=gen) * 2 - 1
+        lref = torch.rand(B, 1, C, H, W, generator=gen) * 2 - 1
+        iref = torch.rand(B, 1, 3, H, W, generator=gen) * 2 - 1
+        sd0 = {k: v.clone() for k, v in G.state_dict().items()}
+        label.requires_grad_(True)
+        out = G(label, lref, iref)
+        r1 = torch.randn(out[0].shape, generator=gen)
+        loss = (out[0] * r1).sum()
+        if out[1][0] is not None:
+            loss = loss + 0.05 * out[1][0].sum() + out[2][0].sum()
+        loss.backward()
+        pre = name + '.'
+        arrays.update({pre + 'opt': json.dumps(cfg), pre + 'label': label.detach().numpy(), pre + 'lref': lref.numpy(),
+                       pre + 'iref': iref.numpy(), pre + 'r1': r1.numpy(), pre + 'out_img': out[0].detach().numpy(),
+                       pre + 'loss': np.float64(loss.item()), pre + 'grad_label': label.grad.numpy(),
+                       pre + 'has_flow': np.int64(out[1][0] is not None)})
+        if out[1][0] is not None:
+            arrays.update({pre + 'out_flow': out[1][0].detach().numpy(), pre + 'out_mask': out[2][0].detach().numpy()})
+        params = dict(G.named_parameters())
+        for n in ['conv_img.weight', 'up_0.conv_0.weight_orig', 'fc_spade_0_0.0.weight_orig', 'label_embedding.conv_first.0.weight']:
+            arrays[pre + 'grad.' + n] = params[n].grad.numpy()
+        arrays.update(npz_state(pre + 'sd.', sd0))
+    save('g_variants_tiny.npz', **arrays)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'variants':
+        variants()
+    else:
+        main()

@@ -53,6 +53,23 @@ def test_state_dict_names_match_reference():
     assert any('fc' in k for k in keys) and any('conv_img' in k for k in keys) and any(k.startswith('up_') for k in keys)
 
 
+@pytest.mark.parametrize('name', ['pose', 'street'])
+def test_state_dict_names_match_reference_other_geometries(name):
+    """Same check on the pose-like (6-channel, H = 2W, warp + spade_combine) and street-like (W = 2H, no flow branch)
+    configurations: the drop-in modules build the reference's parameter / buffer set key for key."""
+    import json
+    from argparse import Namespace
+    from fsv import networks
+    z = load_npz('g_variants_tiny.npz')
+    opt = Namespace(**json.loads(str(z[name + '.opt'])))
+    G = networks.define_G(opt)
+    ref = state_from(z, name + '.sd.')
+    mine = G.state_dict()
+    assert list(mine.keys()) == list(ref.keys())
+    assert all(tuple(mine[k].shape) == tuple(ref[k].shape) for k in ref)
+    G.load_state_dict(ref)
+
+
 def test_init_matches_reference_statistics():
     from fsv import networks
     z = load_npz('g_face_tiny.npz')

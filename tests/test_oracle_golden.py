@@ -166,3 +166,35 @@ def test_train_step_losses():
     for k in z.files:
         if k.startswith('gradG.'):
             assert grad_err(sdG[k[6:]].grad, T(z[k])) < 3e-4, k
+
+
+@pytest.mark.parametrize('name', ['pose', 'street'])
+def test_generator_other_dataset_geometries(name):
+    """Oracle vs the reference on two more BASELINE geometries (tests/golden/make_golden.py variants): 'pose' = 6-channel
+    label, portrait H = 2W, warp_ref + spade_combine; 'street' = wide W = 2H, --adaptive_spade only (no flow branch)."""
+    import json
+    from argparse import Namespace
+    z = load_npz('g_variants_tiny.npz')
+    pre = name + '.'
+    opt = Namespace(**json.loads(str(z[pre + 'opt'])))
+    sd = state_from(z, pre + 'sd.')
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(('running_mean', 'running_var', 'weight_u', 'weight_v')):
+            v.requires_grad_(True)
+    label = T(z[pre + 'label']).requires_grad_(True)
+    out = nets.generator_forward(sd, opt, label, T(z[pre + 'lref']), T(z[pre + 'iref']), training=True)
+    assert rel_err(out[0], T(z[pre + 'out_img'])) < TOL
+    loss = (out[0] * T(z[pre + 'r1'])).sum()
+    if int(z[pre + 'has_flow']):
+        assert rel_err(out[1][0], T(z[pre + 'out_flow'])) < TOL
+        assert rel_err(out[2][0], T(z[pre + 'out_mask'])) < TOL
+        loss = loss + 0.05 * out[1][0].sum() + out[2][0].sum()
+    else:
+        assert out[1][0] is None and out[2][0] is None
+    assert abs(float(loss.detach()) - float(z[pre + 'loss'])) < 1e-3 * max(1.0, abs(float(z[pre + 'loss'])))
+    loss.backward()
+    assert grad_err(label.grad, T(z[pre + 'grad_label'])) < 1e-3
+    for k in z.files:
+        if k.startswith(pre + 'grad.') and k != pre + 'grad_label':
+            n = k[len(pre) + 5:]
+            assert grad_err(sd[n].grad, T(z[k])) < 1e-3, n
