@@ -40,6 +40,7 @@ struct __align__(64) TcParams {
     int w_per_sample;           // B operand: 3-D tensor map (K, rows, sample); tiles never span samples (TN == 1)
     long long b_nstride;        // per-sample bias stride (floats), 0 = shared
     int stages;                 // smem ring depth (2..TC_MAX_STAGES)
+    int m_tiles;                // pixel tiles (tiles_w * tiles_h * tiles_n), used by the persistent variant
     int OH, OW, os, oph, opw;   // output buffer dims and pixel stride/offset: pixel (ho,wo) of the GEMM lands at (ho*os+oph, wo*os+opw)
 };
 
@@ -174,6 +175,166 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
     }
 }
 
+// ------------------------------------------------------------------ persistent variant (NOT the default; FSV_TC_PERSIST=1)
+// Round-2 candidate, written after the round-1 GPU budget was spent: it compiles for sm_100a but has NOT run on hardware
+// yet, so nothing selects it unless FSV_TC_PERSIST=1 is set.  Motivation: the
+// 256x256- and 128x128-resolution layers have 9-36 K blocks per tile, so a CTA spends more time in its prologue
+// (barrier init, TMEM allocation, first TMA round trip) and epilogue than in its main loop.  Here each CTA walks tiles
+// tile = blockIdx.x, blockIdx.x + gridDim.x, ...; the operand ring runs continuously across tiles and the accumulator is
+// double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1:
+//   full[s]/empty[s]   : TMA -> MMA ring, exactly as in k_conv_tc, stage counter carried across tiles
+//   acc_full[b]        : tcgen05.commit after the last MMA of a tile -> epilogue warps
+//   acc_empty[b]       : one arrive per epilogue warp after its last tcgen05.ld of the tile -> MMA issuer may overwrite
+__global__ void __launch_bounds__(192, 1) k_conv_tc_p(const __grid_constant__ TcParams p, const float* __restrict__ bias,
+                                                      const float* __restrict__ residual, float* __restrict__ y) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BN = p.BN;
+    const int STG = p.stages;
+    const int stage_bytes = TC_A_BYTES + BN * TC_BK * 4;
+    uint64_t* bars = (uint64_t*)(smem + STG * stage_bytes);   // full[STG], empty[STG], acc_full[2], acc_empty[2]
+    uint64_t* acc_full = bars + 2 * STG;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = p.Cin / TC_BK;
+    const int num_k = p.ntaps * kblocks;
+    const int m_tiles = p.m_tiles;
+    const int total = m_tiles * (p.Cout / BN);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STG; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[STG + s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&acc_full[b]), 1);
+            mbar_init(smem_u32(&acc_empty[b]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    uint32_t accw = 32;
+    while ((int)accw < BN) accw <<= 1;
+    const uint32_t tmem_cols = 2 * accw;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                int mt = tile % m_tiles;
+                const int co0 = (tile / m_tiles) * BN;
+                const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
+                const int n0 = mt * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STG;
+                    const uint32_t ph = (it / STG) & 1;
+                    mbar_wait(smem_u32(&bars[STG + s]), ph ^ 1);
+                    const int t = kb / kblocks, cb = kb - t * kblocks;
+                    const TcTap tap = p.taps[t];
+                    const uint32_t full = smem_u32(&bars[s]);
+                    const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
+                    mbar_expect_tx(full, (uint32_t)stage_bytes);
+                    tma_load_4d(a_dst, &p.amap[tap.map], full, cb * TC_BK, w0 + tap.dw, h0 + tap.dh, n0);
+                    tma_load_3d(a_dst + TC_A_BYTES, &p.bmap, full, tap.wk * p.Cin + cb * TC_BK, co0, p.w_per_sample ? n0 : 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+            uint32_t it = 0, i = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+                const uint32_t buf = i & 1;
+                mbar_wait(smem_u32(&acc_empty[buf]), ((i >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * accw;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STG;
+                    const uint32_t ph = (it / STG) & 1;
+                    mbar_wait(smem_u32(&bars[s]), ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                    const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        tc_mma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    tc_commit(smem_u32(&bars[STG + s]));
+                }
+                tc_commit(smem_u32(&acc_full[buf]));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t i = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+            const uint32_t buf = i & 1;
+            int mt = tile % m_tiles;
+            const int co0 = (tile / m_tiles) * BN;
+            const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
+            const int n0 = mt * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+            const int tw = row % p.TW;
+            const int r2 = row / p.TW;
+            const int th = r2 % p.TH;
+            const int tn = r2 / p.TH;
+            const int n = n0 + tn, ho = h0 + th, wo = w0 + tw;
+            const bool valid = (n < p.N) && (ho < p.Ho) && (wo < p.Wo);
+            const long long pix = ((long long)n * p.OH + (ho * p.os + p.oph)) * p.OW + (wo * p.os + p.opw);
+            float* yrow = y + pix * p.y_ld + p.y_coff + co0;
+            const float* rrow = residual ? residual + pix * p.res_ld + p.res_coff + co0 : nullptr;
+            mbar_wait(smem_u32(&acc_full[buf]), (i >> 1) & 1);
+            tc_fence_after();
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * accw + (uint32_t)c, v);
+                if (valid) {
+                    const int ncol = min(32, BN - c);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (j < ncol) {
+                            float4 o;
+                            o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
+                            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+                            if (bias) {
+                                float4 b = *reinterpret_cast<const float4*>(bias + (long long)n * p.b_nstride + co0 + c + j);
+                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            }
+                            if (rrow) {
+                                float4 r = *reinterpret_cast<const float4*>(rrow + c + j);
+                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                            }
+                            o.x = fsv_act(o.x, p.act) * p.out_scale; o.y = fsv_act(o.y, p.act) * p.out_scale;
+                            o.z = fsv_act(o.z, p.act) * p.out_scale; o.w = fsv_act(o.w, p.act) * p.out_scale;
+                            *reinterpret_cast<float4*>(yrow + c + j) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
 // ------------------------------------------------------------------ host side
 PFN_encodeTiled fsv_get_encode_tiled();
 static PFN_encodeTiled get_encode() { return fsv_get_encode_tiled(); }
@@ -283,7 +444,25 @@ static int launch_tc(TcParams& p, int tiles_n, const float* bias, const float* r
         FSV_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured = true;
     }
-    dim3 grid(p.tiles_w * p.tiles_h * tiles_n, p.Cout / p.BN);
+    p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+    static int persist = -1;
+    if (persist < 0) { const char* e = getenv("FSV_TC_PERSIST"); persist = (e && atoi(e)) ? 1 : 0; }
+    if (persist) {      // round-2 candidate, see k_conv_tc_p; off by default
+        static bool configured_p = false;
+        if (!configured_p) {
+            FSV_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            configured_p = true;
+        }
+        const int smem_p = smem_bytes + 4 * 8;
+        const long long total = (long long)p.m_tiles * (p.Cout / p.BN);
+        const int per_sm = smem_p <= 110 * 1024 ? 2 : 1;
+        long long gx = (long long)fsv_sm_count() * per_sm;
+        if (gx > total) gx = total;
+        k_conv_tc_p<<<(unsigned)gx, 192, smem_p, st>>>(p, bias, residual, y);
+        FSV_CHECK_LAUNCH(who);
+        return FSV_OK;
+    }
+    dim3 grid(p.m_tiles, p.Cout / p.BN);
     k_conv_tc<<<grid, 192, smem_bytes, st>>>(p, bias, residual, y);
     FSV_CHECK_LAUNCH(who);
     return FSV_OK;
