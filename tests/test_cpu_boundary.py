@@ -104,3 +104,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(d, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, os.path.join(d, f)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm: the oracle port on host threads) keeps the driver's output contract: exactly
+    one JSON line on stdout with the metric keys; the fsv arm refuses to run without a CUDA device (no CPU fallback)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                        '--workload', 'tiny'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'dtype', 'data', 'config', 'e2e', 'cpu_baseline'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port'
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    if not torch.cuda.is_available():
+        r2 = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1', '--warmup', '0'],
+                            capture_output=True, text=True, timeout=600)
+        assert r2.returncode != 0 and 'no CPU fallback' in (r2.stderr + r2.stdout)
