@@ -23,3 +23,44 @@ def test_persistent_conv_kernel_matches_default_path():
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_tc.py'), '-m', 'gpu', '-q', '-x',
                         '--timeout', '120', '-p', 'no:cacheprovider'], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize('name', ['pose', 'street'])
+def test_generator_other_geometries_vs_reference_golden(name):
+    """The drop-in generator in the pose-like (6-channel, portrait H = 2W, warp + spade_combine) and street-like (wide
+    W = 2H, no flow branch) configurations against the reference's own outputs (tests/golden/g_variants_tiny.npz, pinned
+    for the oracle on CPU in test_oracle_golden.py).  Written without GPU access at the end of round 1."""
+    import json
+    from argparse import Namespace
+    import torch
+    from fsv import networks, ops
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import load_npz, state_from, T, rel_err, l2_err
+    z = load_npz('g_variants_tiny.npz')
+    pre = name + '.'
+    opt = Namespace(**json.loads(str(z[pre + 'opt'])))
+    opt.gpu_ids = [0]
+    old = ops.CONV_USE_TC
+    ops.CONV_USE_TC = 0
+    try:
+        G = networks.define_G(opt)
+        G.load_state_dict(state_from(z, pre + 'sd.'))
+        G.train()
+        label = T(z[pre + 'label']).cuda().requires_grad_(True)
+        out = G(label, T(z[pre + 'lref']).cuda(), T(z[pre + 'iref']).cuda())
+        assert rel_err(out[0], T(z[pre + 'out_img'])) < 1e-3
+        loss = (out[0] * T(z[pre + 'r1']).cuda()).sum()
+        if int(z[pre + 'has_flow']):
+            assert rel_err(out[1][0], T(z[pre + 'out_flow'])) < 1e-3
+            assert rel_err(out[2][0], T(z[pre + 'out_mask'])) < 1e-3
+            loss = loss + 0.05 * out[1][0].sum() + out[2][0].sum()
+        else:
+            assert out[1][0] is None and out[2][0] is None
+        loss.backward()
+        assert l2_err(label.grad, T(z[pre + 'grad_label'])) < 1e-2
+        params = dict(G.named_parameters())
+        for k in z.files:
+            if k.startswith(pre + 'grad.') and k != pre + 'grad_label':
+                assert l2_err(params[k[len(pre) + 5:]].grad, T(z[k])) < 1e-2, k
+    finally:
+        ops.CONV_USE_TC = old
