@@ -32,8 +32,8 @@ def channels(opt):
 def check_scope(opt):
     if getattr(opt, 'adaptive_conv', False) or getattr(opt, 'res_for_ref', False):
         raise NotImplementedError('adaptive_conv / res_for_ref are outside the hot-path scope')
-    if getattr(opt, 'lambda_kld', 0) > 0 or getattr(opt, 'n_shot', 1) > 1:
-        raise NotImplementedError('kld / K>1 attention are outside the round-1 scope')
+    if getattr(opt, 'lambda_kld', 0) > 0:
+        raise NotImplementedError('the kld bottleneck is outside the hot-path scope')
     if 'mul' not in opt.use_label_ref:
         raise NotImplementedError("only use_label_ref='mul' is in scope")
 
@@ -133,20 +133,64 @@ def hyper_mlp(sd, prefix, x, n_fc_layers, training):
     return F.linear(x, get_weight(sd, p, training), sd[p + '.bias'])
 
 
-def reference_encoding(sd, opt, img_ref, label_ref, training):
-    """generator.py:341-393 (K=1, use_label_ref='mul')."""
+def attention_encode(sd, opt, x, name, training):
+    """generator.py:292-296: first conv + n_downsample_A stride-2 convs (spectral conv + BN + LReLU each)."""
+    x = sn_conv_bn_lrelu(sd, name + '_first', x, 1, training)
+    for i in range(opt.n_downsample_A):
+        x = sn_conv_bn_lrelu(sd, '%s_%d' % (name, i), x, 2, training)
+    return x
+
+
+def attention_module(sd, opt, x, label, label_ref, training, attention=None):
+    """generator.py:298-316: combine the features of the n = n_shot reference images.  x: (b*n, c, h, w).
+    attention (b, n*h*w, h*w) = softmax over the reference positions of key^T query; out = x_flat @ attention."""
+    bn, c, h, w = x.shape
+    n = opt.n_shot
+    b = bn // n
+    if attention is None:
+        key = attention_encode(sd, opt, label_ref, 'atn_key', training)          # (b*n, c, h, w)
+        query = attention_encode(sd, opt, label, 'atn_query', training)          # (b, c, h, w)
+        key = key.reshape(b, n, c, -1).permute(0, 1, 3, 2).reshape(b, -1, c)     # b x nhw x c
+        query = query.reshape(b, c, -1)                                          # b x c x hw
+        attention = torch.softmax(torch.bmm(key, query), dim=1)                  # b x nhw x hw
+    xf = x.reshape(b, n, c, h * w).permute(0, 2, 1, 3).reshape(b, c, -1)         # b x c x nhw
+    out = torch.bmm(xf, attention).reshape(b, c, h, w)
+    atn_vis = attention.reshape(b, n, h * w, h * w).sum(2).reshape(b, n, h, w)
+    return out, attention, atn_vis[-1:, 0:1]
+
+
+def reference_encoding(sd, opt, img_ref, label_ref, training, label=None, n=1):
+    """generator.py:341-393 (use_label_ref='mul').  With n = n_shot > 1 the (b*n) reference features are merged
+    into b by the attention module after down-sampling level n_downsample_A - 1 (:359-366); returns additionally
+    (atn, atn_vis, ref_idx) -- ref_idx = the reference with the largest total attention, used to pick the image
+    that gets warped (flow_generation, :425)."""
     nd = opt.n_downsample_G
     x = sn_conv_bn_lrelu(sd, 'ref_img_first', img_ref, 1, training)
     xl = sn_conv_bn_lrelu(sd, 'ref_label_first', label_ref, 1, training)
+    atn = atn_vis = ref_idx = None
     for i in range(nd):
         x = sn_conv_bn_lrelu(sd, 'ref_img_down_%d' % i, x, 2, training)
         xl = sn_conv_bn_lrelu(sd, 'ref_label_down_%d' % i, xl, 2, training)
+        if n > 1 and i == opt.n_downsample_A - 1:
+            x, atn, atn_vis = attention_module(sd, opt, x, label, label_ref, training)
+            xl, _, _ = attention_module(sd, opt, xl, None, None, training, atn)
+            ref_idx = torch.argmax(atn.reshape(label.shape[0], n, -1).sum(2), dim=1)
     enc_img, enc_lab = [x], [xl]
     for i in reversed(range(nd)):
         enc_img.append(sn_conv_bn_lrelu(sd, 'ref_img_up_%d' % i, enc_img[-1], 1, training))
         enc_lab.append(sn_conv_bn_lrelu(sd, 'ref_label_up_%d' % i, enc_lab[-1], 1, training))
     encoded = [ops.ref_outer_product(a, b) for a, b in zip(enc_img, enc_lab)]
+    if n > 1:
+        return x, encoded[::-1], atn, atn_vis, ref_idx
     return x, encoded[::-1]
+
+
+def pick_ref(refs, ref_idx):
+    """base_network.py:40-47: refs (b, n, c, h, w) -> (b, c, h, w): reference 0, or the one ref_idx names."""
+    if ref_idx is None:
+        return refs[:, 0]
+    idx = ref_idx.long().view(-1, 1, 1, 1, 1).expand(-1, 1, *refs.shape[2:])
+    return refs.gather(1, idx)[:, 0]
 
 
 def spade_hyper_weights(sd, opt, feat, i, training):
@@ -187,8 +231,13 @@ def generator_forward(sd, opt, label, label_refs, img_refs, prev=(None, None), t
     label_ref = label_refs.reshape(b * n, -1, h, w)
 
     # ---- weight generation (generator.py:396-422)
+    atn_vis = ref_idx = None
     if cached_weights is None:
-        x, encoded_ref = reference_encoding(sd, opt, img_ref, label_ref, training)
+        if n > 1:
+            assert n == opt.n_shot, 'n_shot must equal the number of reference images'
+            x, encoded_ref, _atn, atn_vis, ref_idx = reference_encoding(sd, opt, img_ref, label_ref, training, label, n)
+        else:
+            x, encoded_ref = reference_encoding(sd, opt, img_ref, label_ref, training)
         emb_w, norm_w = [], []
         for i in range(opt.n_adaptive_layers):
             feat = encoded_ref[min(len(encoded_ref) - 1, i + 1)]
@@ -210,7 +259,7 @@ def generator_forward(sd, opt, label, label_refs, img_refs, prev=(None, None), t
 
     # ---- flow + warp (generator.py:424-445)
     flow, mask, warp, ds = [None, None], [None, None], [None, None], [None, None]
-    lref, iref = label_refs[:, 0], img_refs[:, 0]
+    lref, iref = pick_ref(label_refs, ref_idx), pick_ref(img_refs, ref_idx)     # generator.py:425
     warp_ref = opt.warp_ref and not opt.for_face
     if warp_ref:
         flow[0], mask[0] = flow_generator(sd, 'flow_network_ref', opt, label, lref, iref, training)
@@ -261,7 +310,7 @@ def generator_forward(sd, opt, label, label_refs, img_refs, prev=(None, None), t
     else:
         img_final = img_raw
         img_raw = None
-    out = (img_final, flow, mask, img_raw, warp, None, None, None, None)
+    out = (img_final, flow, mask, img_raw, warp, None, None, atn_vis, ref_idx)
     if return_internals:
         internals.update(enc_label=enc_label, norm_w=norm_w, emb_w=emb_w)
         return out, internals

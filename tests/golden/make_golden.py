@@ -360,8 +360,44 @@ def variants():
     save('g_variants_tiny.npz', **arrays)
 
 
+def kshot():
+    """K = 2 reference images: the attention module merges the two references' features
+    (generator.py:298-316,359-366) and ref_idx picks the one that is warped.  -> g_kshot_tiny.npz"""
+    install_shims()
+    import models.networks as networks
+    import models.networks.generator as refgen
+    import models.loss_collector as reflc
+    refgen.resample = resample_any_device
+    reflc.resample = resample_any_device
+    cfg = dict(TINY, n_downsample_G=3, n_adaptive_layers=2, n_downsample_F=2, n_blocks_F=1, n_shot=2, n_downsample_A=2)
+    torch.manual_seed(11)
+    gen = torch.Generator().manual_seed(99)
+    G = networks.define_G(Namespace(**cfg))
+    G.train()
+    B, H, W, K = 2, 32, 32, 2
+    label, lref, iref, _ = synth_face_inputs(gen, B, H, W, K=K)
+    sd0 = {k: v.clone() for k, v in G.state_dict().items()}
+    label.requires_grad_(True)
+    out = G(label, lref, iref)
+    r1 = torch.randn(out[0].shape, generator=gen)
+    loss = (out[0] * r1).sum() + 0.05 * out[1][0].sum() + out[2][0].sum()
+    loss.backward()
+    params = dict(G.named_parameters())
+    arrays = dict(opt=json.dumps(cfg), label=label.detach().numpy(), lref=lref.numpy(), iref=iref.numpy(), r1=r1.numpy(),
+                  out_img=out[0].detach().numpy(), out_flow=out[1][0].detach().numpy(), out_mask=out[2][0].detach().numpy(),
+                  out_warp=out[4][0].detach().numpy(), atn_vis=out[7].detach().numpy(), ref_idx=out[8].numpy(),
+                  loss=np.float64(loss.item()), grad_label=label.grad.numpy())
+    for n in ['atn_key_first.conv.weight_orig', 'atn_query_1.conv.weight_orig', 'up_0.conv_0.weight_orig',
+              'fc_spade_0_0.0.weight_orig', 'ref_img_down_2.conv.weight_orig']:
+        arrays['grad.' + n] = params[n].grad.numpy()
+    arrays.update(npz_state('sd.', sd0))
+    save('g_kshot_tiny.npz', **arrays)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'variants':
+    if len(sys.argv) > 1 and sys.argv[1] == 'kshot':
+        kshot()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'variants':
         variants()
     else:
         main()

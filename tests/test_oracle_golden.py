@@ -198,3 +198,29 @@ def test_generator_other_dataset_geometries(name):
         if k.startswith(pre + 'grad.') and k != pre + 'grad_label':
             n = k[len(pre) + 5:]
             assert grad_err(sd[n].grad, T(z[k])) < 1e-3, n
+
+
+def test_generator_two_reference_images_attention():
+    """K = 2: the oracle's attention module / ref_idx / pick_ref against the reference
+    (tests/golden/g_kshot_tiny.npz): frames, flow, mask, warp, the attention visualisation, the picked reference and
+    gradients -- including those of the attention key / query encoders."""
+    z = load_npz('g_kshot_tiny.npz')
+    opt = opt_from(z)
+    sd = state_from(z, 'sd.')
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(('running_mean', 'running_var', 'weight_u', 'weight_v')):
+            v.requires_grad_(True)
+    label = T(z['label']).requires_grad_(True)
+    out = nets.generator_forward(sd, opt, label, T(z['lref']), T(z['iref']), training=True)
+    assert rel_err(out[0], T(z['out_img'])) < TOL
+    assert rel_err(out[1][0], T(z['out_flow'])) < TOL
+    assert rel_err(out[2][0], T(z['out_mask'])) < TOL
+    assert rel_err(out[4][0], T(z['out_warp'])) < TOL
+    assert rel_err(out[7], T(z['atn_vis'])) < TOL
+    assert torch.equal(out[8], torch.from_numpy(np.array(z['ref_idx'])))
+    loss = (out[0] * T(z['r1'])).sum() + 0.05 * out[1][0].sum() + out[2][0].sum()
+    loss.backward()
+    assert grad_err(label.grad, T(z['grad_label'])) < 1e-3
+    for k in z.files:
+        if k.startswith('grad.'):
+            assert grad_err(sd[k[5:]].grad, T(z[k])) < 1e-3, k
