@@ -158,8 +158,7 @@ class FewShotGenerator(BaseNetwork):
             raise NotImplementedError('adaptive_conv / res_for_ref are outside the hot-path scope (SURVEY.md section 8)')
         if getattr(opt, 'lambda_kld', 0) > 0:
             raise NotImplementedError('lambda_kld > 0 is outside the hot-path scope')
-        if getattr(opt, 'n_shot', 1) > 1:
-            raise NotImplementedError('K>1 attention is a "next" row of SURVEY.md section 8(f)')
+        self.n_shot = getattr(opt, 'n_shot', 1)          # K > 1: attention module, see attention_module
         if 'mul' not in opt.use_label_ref:
             raise NotImplementedError("only use_label_ref='mul' is in scope")
         self.n_downsample_G = nd = opt.n_downsample_G
@@ -216,6 +215,14 @@ class FewShotGenerator(BaseNetwork):
             setattr(self, 'up_%d' % i, SPADEResnetBlock(ch[i + 1], ch[i], norm=norm, hidden_nc=self.ch_hidden[i],
                                                         norm_params_free=(self.adap_spade and i < self.n_adaptive_layers)))
         self.conv_img = Conv2d(nf, 3, 3, padding=1)
+
+        if self.n_shot > 1:                              # generator.py:127-134
+            self.n_downsample_A = opt.n_downsample_A
+            self.atn_query_first = ConvNormAct(input_nc, nf)
+            self.atn_key_first = ConvNormAct(input_nc, nf)
+            for i in range(self.n_downsample_A):
+                setattr(self, 'atn_key_%d' % i, ConvNormAct(ch[i], ch[i + 1], stride=2))
+                setattr(self, 'atn_query_%d' % i, ConvNormAct(ch[i], ch[i + 1], stride=2))
 
         self.warp_prev = False
         self.warp_ref = opt.warp_ref and not opt.for_face
@@ -279,13 +286,43 @@ class FewShotGenerator(BaseNetwork):
         return emb, [gb(fc_0, ch_out), gb(fc_1, ch_in), gb(fc_s, ch_out)]
 
     # ------------------------------------------------------------------ reference encoder (generator.py:341-393)
-    def reference_encoding(self, img_ref, label_ref, need_weights):
+    def attention_encode(self, x, name):
+        """generator.py:292-296."""
+        x = getattr(self, name + '_first')(x)
+        for i in range(self.n_downsample_A):
+            x = getattr(self, '%s_%d' % (name, i))(x)
+        return x
+
+    def attention_module(self, x, label, label_ref, attention=None):
+        """generator.py:298-316 on NHWC: x (b*n, h, w, c) -> (b, h, w, c).  attention is kept as (b, h, w, n*h*w) =
+        the reference's (b, n*h*w, h*w) transposed, so that the softmax over the reference positions is a channel softmax
+        and both GEMMs are per-sample 1x1 convs of the C ABI (no torch.bmm on the path)."""
+        bn, h, w, c = x.shape
+        n = self.n_shot
+        b = bn // n
+        if attention is None:
+            key = self.attention_encode(label_ref, 'atn_key')                       # (b*n, h, w, c)
+            query = self.attention_encode(label, 'atn_query')                       # (b, h, w, c)
+            energy = ops.per_sample_matmul(query, key.reshape(b, n * h * w * c), n * h * w, c)
+            attention = ops.softmax_channels(energy)                                # softmax over the n*h*w reference positions
+        xt = x.reshape(b, n * h * w, c).transpose(1, 2).contiguous().reshape(b, c * n * h * w)
+        out = ops.per_sample_matmul(attention, xt, c, n * h * w)
+        atn_vis = attention.reshape(b, h * w, n, h * w).sum(3).permute(0, 2, 1).reshape(b, n, h, w)
+        return out, attention, atn_vis[-1:, 0:1]
+
+    def reference_encoding(self, img_ref, label_ref, need_weights, label=None, n=1):
         nd = self.n_downsample_G
         x = self.ref_img_first(img_ref)
         xl = self.ref_label_first(label_ref)
+        atn_vis = ref_idx = None
         for i in range(nd):
             x = getattr(self, 'ref_img_down_%d' % i)(x)
             xl = getattr(self, 'ref_label_down_%d' % i)(xl)
+            if n > 1 and i == self.n_downsample_A - 1:                               # generator.py:359-366
+                x, atn, atn_vis = self.attention_module(x, label, label_ref)
+                xl, _, _ = self.attention_module(xl, None, None, atn)
+                b, h, w = atn.shape[0], atn.shape[1], atn.shape[2]
+                ref_idx = torch.argmax(atn.detach().reshape(b, h * w, n, -1).sum((1, 3)), dim=1)
         encoded = None
         if need_weights:
             enc_img, enc_lab = [x], [xl]
@@ -297,11 +334,17 @@ class FewShotGenerator(BaseNetwork):
             # discards) levels 0 and nd -- a pure function of the features, skipped here with identical results.
             used = set(min(nd, i + 1) for i in range(self.n_adaptive_layers)) if self.adap_spade else set()
             encoded = [ops.softmax_outer(enc_img[j], enc_lab[j]) if j in used else None for j in range(nd + 1)]
+        if n > 1:
+            return x, encoded, atn_vis, ref_idx
         return x, encoded
 
-    def weight_generation(self, img_ref, label_ref, label, t=0):
-        need = self.opt.isTrain or t == 0
-        x, encoded = self.reference_encoding(img_ref, label_ref, need)
+    def weight_generation(self, img_ref, label_ref, label, t=0, n=1):
+        need = self.opt.isTrain or t == 0 or n > 1                                  # generator.py:403
+        atn_vis = ref_idx = None
+        if n > 1:
+            x, encoded, atn_vis, ref_idx = self.reference_encoding(img_ref, label_ref, need, label=label, n=n)
+        else:
+            x, encoded = self.reference_encoding(img_ref, label_ref, need)
         if need:
             emb_w, norm_w = [], []
             for i in range(self.n_adaptive_layers):
@@ -314,6 +357,8 @@ class FewShotGenerator(BaseNetwork):
         else:
             emb_w, norm_w = self.embedding_weights, self.norm_weights        # generator.py:418
         enc_label = self.label_embedding(label, weights=(emb_w if self.adap_embed else None))
+        if n > 1:
+            return x, enc_label, norm_w, atn_vis, ref_idx
         return x, enc_label, norm_w
 
     # ------------------------------------------------------------------ forward (generator.py:181-229)
@@ -321,21 +366,33 @@ class FewShotGenerator(BaseNetwork):
         if img_coarse is not None:
             raise NotImplementedError('forward_face (--refine_face) is a "next" row of SURVEY.md section 8(f)')
         b, n = img_refs.shape[0], img_refs.shape[1]
-        if n != 1:
-            raise NotImplementedError('K>1 reference images need the attention module (SURVEY.md section 8f)')
+        if n != 1 and n != self.n_shot:
+            raise ValueError('got %d reference images but the network was built with n_shot=%d' % (n, self.n_shot))
         nd = self.n_downsample_G
         label_n = ops.to_nhwc(label)
-        lref_n = ops.to_nhwc(label_refs[:, 0])
-        iref_n = ops.to_nhwc(img_refs[:, 0])
-
-        x, enc_label, norm_w = self.weight_generation(iref_n, lref_n, label_n, t=t)
+        atn_vis = ref_idx = None
+        if n == 1:
+            lref_pick, iref_pick = label_refs[:, 0], img_refs[:, 0]
+            lref_n = ops.to_nhwc(lref_pick)
+            iref_n = ops.to_nhwc(iref_pick)
+            x, enc_label, norm_w = self.weight_generation(iref_n, lref_n, label_n, t=t)
+        else:
+            # K reference images: encode all b*n, merge by attention, warp the most-attended one (generator.py:396-400,425)
+            hh, ww = img_refs.shape[3], img_refs.shape[4]
+            lref_all = ops.to_nhwc(label_refs.reshape(b * n, -1, hh, ww))
+            iref_all = ops.to_nhwc(img_refs.reshape(b * n, -1, hh, ww))
+            x, enc_label, norm_w, atn_vis, ref_idx = self.weight_generation(iref_all, lref_all, label_n, t=t, n=n)
+            idx = ref_idx.view(-1, 1, 1, 1, 1)
+            lref_pick = label_refs.gather(1, idx.expand(-1, 1, *label_refs.shape[2:]))[:, 0]      # base_network.py:40-47
+            iref_pick = img_refs.gather(1, idx.expand(-1, 1, *img_refs.shape[2:]))[:, 0]
+            iref_n = ops.to_nhwc(iref_pick)
 
         # ---- flow estimation + warp (generator.py:424-445)
         flow, fmask, warp, ds = [None, None], [None, None], [None, None], [None, None]
         label_prev, img_prev = prev
         has_prev = label_prev is not None
         if self.warp_ref:
-            f, m = self.flow_network_ref(ops.pack_nhwc(label, label_refs[:, 0], img_refs[:, 0]))
+            f, m = self.flow_network_ref(ops.pack_nhwc(label, lref_pick, iref_pick))
             flow[0], fmask[0] = f, m
             if self.spade_combine:
                 ds[0] = ops.warp_concat(iref_n, f, m)           # [warp(3), mask(1)] in one kernel
@@ -385,4 +442,4 @@ class FewShotGenerator(BaseNetwork):
         out_mask = [V(m) if m is not None else None for m in fmask]
         out_warp = [V(w) if w is not None else None for w in warp]
         return (V(img_final), out_flow, out_mask, V(img_raw) if img_raw is not None else None, out_warp,
-                None, None, None, None)
+                None, None, atn_vis, ref_idx)

@@ -749,3 +749,37 @@ class SoftmaxOuterFn(torch.autograd.Function):
 
 def softmax_outer(img_feat, lab_feat):
     return SoftmaxOuterFn.apply(img_feat, lab_feat)
+
+
+# --------------------------------------------------------------------------- K-shot attention helpers (generator.py:298-316)
+
+class SoftmaxChannelsFn(torch.autograd.Function):
+    """softmax over the channel (last NHWC) axis: fsv_softmax_rows_fwd/bwd."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        _call(lib.fsv_softmax_rows_fwd, ptr(x), ptr(y), x.numel() // x.shape[-1], x.shape[-1], stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(y)
+        _call(lib.fsv_softmax_rows_bwd, ptr(y), ptr(dy), ptr(dx), y.numel() // y.shape[-1], y.shape[-1], stream())
+        return dx
+
+
+def softmax_channels(x):
+    return SoftmaxChannelsFn.apply(x)
+
+
+def per_sample_matmul(x, flat, cout, cin):
+    """y[b, h, w, :] = W_b @ x[b, h, w, :] with W_b = flat[b].view(cout, cin): a per-sample 1x1 conv without bias (the two
+    GEMMs of the attention module: key^T query and x_ref @ attention).  Gradients flow to both x and flat."""
+    assert x.shape[3] == cin and flat.shape[1] == cout * cin
+    cfg = dict(cout=cout, kh=1, kw=1, stride=1, pad=0, up=1, act=ACT_NONE, w_off=0, w_nstride=cout * cin, use_tc=0)
+    return Conv2dFn.apply(x, flat, None, None, cfg)

@@ -70,6 +70,19 @@ def test_state_dict_names_match_reference_other_geometries(name):
     G.load_state_dict(ref)
 
 
+def test_state_dict_names_match_reference_kshot():
+    """n_shot = 2: the attention key / query encoders are built with the reference's names, in its registration order."""
+    from fsv import networks
+    z = load_npz('g_kshot_tiny.npz')
+    G = networks.define_G(opt_from(z))
+    ref = state_from(z, 'sd.')
+    mine = G.state_dict()
+    assert list(mine.keys()) == list(ref.keys())
+    assert all(tuple(mine[k].shape) == tuple(ref[k].shape) for k in ref)
+    assert any(k.startswith('atn_key_first.') for k in mine) and any(k.startswith('atn_query_1.') for k in mine)
+    G.load_state_dict(ref)
+
+
 def test_init_matches_reference_statistics():
     from fsv import networks
     z = load_npz('g_face_tiny.npz')

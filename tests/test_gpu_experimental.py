@@ -64,3 +64,39 @@ def test_generator_other_geometries_vs_reference_golden(name):
                 assert l2_err(params[k[len(pre) + 5:]].grad, T(z[k])) < 1e-2, k
     finally:
         ops.CONV_USE_TC = old
+
+
+def test_generator_two_reference_images_vs_reference_golden():
+    """K = 2 attention path of the drop-in generator (attention GEMMs as per-sample 1x1 convs + channel softmax of the
+    C ABI) against the reference (tests/golden/g_kshot_tiny.npz; the oracle is pinned to the same file on CPU).
+    Written without GPU access at the end of round 1."""
+    import torch
+    from fsv import networks, ops
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import load_npz, state_from, opt_from, T, rel_err, l2_err
+    z = load_npz('g_kshot_tiny.npz')
+    opt = opt_from(z)
+    opt.gpu_ids = [0]
+    old = ops.CONV_USE_TC
+    ops.CONV_USE_TC = 0
+    try:
+        G = networks.define_G(opt)
+        G.load_state_dict(state_from(z, 'sd.'))
+        G.train()
+        label = T(z['label']).cuda().requires_grad_(True)
+        out = G(label, T(z['lref']).cuda(), T(z['iref']).cuda())
+        assert rel_err(out[0], T(z['out_img'])) < 1e-3
+        assert rel_err(out[1][0], T(z['out_flow'])) < 1e-3
+        assert rel_err(out[2][0], T(z['out_mask'])) < 1e-3
+        assert rel_err(out[4][0], T(z['out_warp'])) < 1e-3
+        assert rel_err(out[7], T(z['atn_vis'])) < 1e-3
+        assert torch.equal(out[8].cpu(), torch.from_numpy(z['ref_idx']))
+        loss = (out[0] * T(z['r1']).cuda()).sum() + 0.05 * out[1][0].sum() + out[2][0].sum()
+        loss.backward()
+        assert l2_err(label.grad, T(z['grad_label'])) < 1e-2
+        params = dict(G.named_parameters())
+        for k in z.files:
+            if k.startswith('grad.'):
+                assert l2_err(params[k[5:]].grad, T(z[k])) < 1e-2, k
+    finally:
+        ops.CONV_USE_TC = old
