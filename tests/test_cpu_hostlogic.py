@@ -156,3 +156,36 @@ def test_generator_two_reference_images(nets):
     for k in z.files:
         if k.startswith('grad.'):
             assert grad_err(params[k[5:]].grad, T(z[k])) < GTOL, k
+
+
+def test_train_step_losses(nets, monkeypatch):
+    """one D-step + G-step through fsv.trainer (the mirror of vid2vid_model.py:62-128 + loss_collector.py) on the
+    emulated op layer: loss values, the generated frame and parameter gradients against the reference's LossCollector."""
+    from fsv import trainer
+    monkeypatch.setattr(trainer, 'ops', mock_ops)
+    z = load_npz('step_face_tiny.npz')
+    zg = load_npz('g_face_tiny.npz')
+    opt = opt_from(zg)
+    G = _build(nets, opt, state_from(zg, 'sd.'))
+    D = nets.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, 1, True, gpu_ids=[])
+    D.load_state_dict(state_from(z, 'sdD.'))
+    D.train()
+    label, lref, iref, tgt = T(z['label']), T(z['lref']), T(z['iref']), T(z['tgt'])
+    dl = trainer.discriminator_losses(opt, G, D, label, tgt, lref, iref)
+    assert rel_err(dl['D_real'].reshape(-1), T(z['D_real']).reshape(-1)) < TOL
+    assert rel_err(dl['D_fake'].reshape(-1), T(z['D_fake']).reshape(-1)) < TOL
+    sum(v.mean() for v in dl.values()).backward()
+    pd = dict(D.named_parameters())
+    for k in z.files:
+        if k.startswith('gradD.'):
+            assert grad_err(pd[k[6:]].grad, T(z[k])) < GTOL, k
+    D.zero_grad()
+    gl, fake = trainer.generator_losses(opt, G, D, label, tgt, lref, iref)
+    assert rel_err(fake, T(z['fake'])) < TOL
+    for n in ('G_GAN', 'G_GAN_Feat', 'F_Warp', 'F_Mask'):
+        assert rel_err(gl[n].reshape(-1), T(z[n]).reshape(-1)) < TOL, n
+    sum(v.mean() for v in gl.values()).backward()
+    pg = dict(G.named_parameters())
+    for k in z.files:
+        if k.startswith('gradG.'):
+            assert grad_err(pg[k[6:]].grad, T(z[k])) < GTOL, k
