@@ -34,6 +34,9 @@ WORKLOADS = {
     # name: (H, W, per-GPU batch, option overrides)
     'face256': dict(H=256, W=256, batch=8, opt=dict()),
     'face512': dict(H=512, W=512, batch=2, opt=dict(fineSize=512)),
+    # temporal phase (warp_prev: second flow pass, previous-frame embedding, 3-map SPADEs).  Parity of this
+    # path is golden-tested on the GPU; this bench workload itself was added after the round-1 GPU budget was spent (not yet timed).
+    'face256t': dict(H=256, W=256, batch=8, opt=dict(), temporal=True),
     'tiny': dict(H=64, W=64, batch=2, opt=dict(ngf=8, nff=8, ndf=8, n_downsample_G=4, n_adaptive_layers=3, n_blocks_F=2, fineSize=64)),
 }
 
@@ -52,7 +55,7 @@ BASE_OPT = dict(
     lr=0.0004, beta1=0.5, beta2=0.999, no_TTUR=False)
 
 # forward MACs per frame at face 256x256 from BASELINE.md section 2 (G 49.21 GMAC, D pair 2.37 GMAC); step = 4 G + 5 D
-FLOP_PER_FRAME = {'face256': 417e9, 'face512': 1645e9}
+FLOP_PER_FRAME = {'face256': 417e9, 'face512': 1645e9, 'face256t': 4 * 149.9e9 + 5 * 4.73e9}
 
 
 def make_opt(workload):
@@ -73,6 +76,8 @@ def synth_inputs(workload, batch, seed, device='cpu', pin=False):
         return torch.nn.functional.max_pool2d(e.view(-1, 1, H, W), 3, 1, 1).view(*shape)
     t = dict(tgt_label=edges(batch, 1, H, W), tgt_image=torch.rand(batch, 3, H, W, generator=g) * 2 - 1,
              ref_labels=edges(batch, 1, 1, H, W), ref_images=torch.rand(batch, 1, 3, H, W, generator=g) * 2 - 1)
+    if wl.get('temporal'):
+        t.update(prev_label=edges(batch, 1, H, W), prev_image=torch.rand(batch, 3, H, W, generator=g) * 2 - 1)
     if pin and torch.cuda.is_available():
         t = {k: v.pin_memory() for k, v in t.items()}
     if device != 'cpu':
@@ -141,7 +146,10 @@ def cpu_step_time(workload, batch, threads, steps=1, warmup=0):
     opt.gpu_ids = []
     from fsv import networks
     torch.manual_seed(0)
-    sdG = {k: v.detach().clone() for k, v in networks.define_G(opt).state_dict().items()}
+    g_cpu = networks.define_G(opt)
+    if WORKLOADS[workload].get('temporal'):
+        g_cpu.init_temporal_network()
+    sdG = {k: v.detach().clone() for k, v in g_cpu.state_dict().items()}
     sdD = {k: v.detach().clone() for k, v in
            networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, opt.num_D, True, gpu_ids=[]).state_dict().items()}
     for sd in (sdG, sdD):
@@ -149,16 +157,19 @@ def cpu_step_time(workload, batch, threads, steps=1, warmup=0):
             if v.is_floating_point() and not k.endswith(('running_mean', 'running_var', 'weight_u', 'weight_v')):
                 v.requires_grad_(True)
     inp = synth_inputs(workload, batch, seed=1234)
+    temporal = bool(WORKLOADS[workload].get('temporal'))
+    prev = (inp['prev_label'], inp['prev_image']) if temporal else (None, None)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         with torch.no_grad():
-            fake = ON.generator_forward(sdG, opt, inp['tgt_label'], inp['ref_labels'], inp['ref_images'], training=True)[0]
+            fake = ON.generator_forward(sdG, opt, inp['tgt_label'], inp['ref_labels'], inp['ref_images'], prev=prev, training=True,
+                                        temporal=temporal)[0]
         dl = ON.discriminator_losses(sdD, inp['tgt_label'], fake, inp['tgt_image'], inp['ref_labels'][:, 0], inp['ref_images'][:, 0],
                                      opt.n_layers_D, opt.num_D)
         sum(v.sum() for v in dl.values()).backward()
         gl, _ = ON.generator_losses(sdG, sdD, opt, inp['tgt_label'], inp['tgt_image'], inp['ref_labels'], inp['ref_images'],
-                                    opt.n_layers_D, opt.num_D)
+                                    opt.n_layers_D, opt.num_D, prev=prev if temporal else None)
         sum(v.sum() for v in gl.values()).backward()
         for sd in (sdG, sdD):
             for v in sd.values():
@@ -202,6 +213,8 @@ def run_fsv(args):
     opt.gpu_ids = [local_rank]
     torch.manual_seed(0)
     netG = networks.define_G(opt)
+    if wl.get('temporal'):
+        netG.init_temporal_network()
     netD = networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, opt.num_D, True, gpu_ids=[local_rank])
     netG.train(), netD.train()
     parallel.broadcast_state(netG), parallel.broadcast_state(netD)
@@ -214,8 +227,9 @@ def run_fsv(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
     def eager_step(inp):
+        prev = [inp['prev_label'], inp['prev_image']] if 'prev_label' in inp else None
         return trainer.train_step(opt, netG, netD, optG, optD, inp['tgt_label'], inp['tgt_image'], inp['ref_labels'], inp['ref_images'],
-                                  sync_G=syncG, sync_D=syncD)
+                                  sync_G=syncG, sync_D=syncD, prev=prev)
     step = eager_step
     n_eager0 = ops.LAUNCHES[0]
     eager_step(devin)

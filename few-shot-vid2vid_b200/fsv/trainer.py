@@ -66,18 +66,20 @@ def _mask_loss(flow_mask, warped, tgt, lambda_mask):
     return (_masked_l1(flow_mask, zero, conf) + _masked_l1(flow_mask, one, 1 - conf)) * lambda_mask
 
 
-def discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images):
-    """vid2vid_model.py:106-128."""
+def discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=None):
+    """vid2vid_model.py:106-128.  ``prev`` = [prev_label, prev_image] in the temporal phase (warp_prev), else None."""
     with torch.no_grad():
-        fake = netG(tgt_label, ref_labels, ref_images)[0]
+        fake = (netG(tgt_label, ref_labels, ref_images) if prev is None else netG(tgt_label, ref_labels, ref_images, prev=prev))[0]
     pred = netD(_d_input(tgt_label, fake.detach(), tgt_image, ref_labels[:, 0], ref_images[:, 0]))
     pf, pr = _split(pred)
     return {'D_real': _gan_loss(pr, True), 'D_fake': _gan_loss(pf, False)}
 
 
-def generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images):
-    """vid2vid_model.py:62-104 (non-zero terms under --no_flow_gt --no_vgg_loss, no foreground mask)."""
-    out = netG(tgt_label, ref_labels, ref_images)
+def generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=None):
+    """vid2vid_model.py:62-104 (non-zero terms under --no_flow_gt --no_vgg_loss, no foreground mask).  With ``prev`` =
+    [prev_label, prev_image] (temporal phase) the warp / mask terms of the previous-frame branch are added
+    (loss_collector.py:132-136,165-168: both entries of flow / flow_mask / warped image contribute)."""
+    out = netG(tgt_label, ref_labels, ref_images) if prev is None else netG(tgt_label, ref_labels, ref_images, prev=prev)
     fake, flow, fmask, warp = out[0], out[1], out[2], out[4]
     pred = netD(_d_input(tgt_label, fake, tgt_image, ref_labels[:, 0], ref_images[:, 0]))
     pf, pr = _split(pred)
@@ -85,6 +87,10 @@ def generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_imag
     if flow[0] is not None:
         losses['F_Warp'] = torch.nn.functional.l1_loss(warp[0], tgt_image) * opt.lambda_flow
         losses['F_Mask'] = _mask_loss(fmask[0], warp[0], tgt_image, opt.lambda_mask)
+    if flow[1] is not None:
+        zero = tgt_image.new_zeros(())
+        losses['F_Warp'] = losses.get('F_Warp', zero) + torch.nn.functional.l1_loss(warp[1], tgt_image) * opt.lambda_flow
+        losses['F_Mask'] = losses.get('F_Mask', zero) + _mask_loss(fmask[1], warp[1], tgt_image, opt.lambda_mask)
     return losses, fake
 
 
@@ -118,8 +124,9 @@ class GraphedStep:
         st = self.static
 
         def run():
+            prev = [st['prev_label'], st['prev_image']] if 'prev_label' in st else None      # temporal phase inputs, if given
             return train_step(opt, netG, netD, optG, optD, st['tgt_label'], st['tgt_image'], st['ref_labels'], st['ref_images'],
-                              sync_G=sync_G, sync_D=sync_D)
+                              sync_G=sync_G, sync_D=sync_D, prev=prev)
         # Capture on the stream the eager iterations already ran on (it must not be the legacy default stream): autograd's
         # AccumulateGrad nodes remember the stream they were created on, and a cross-stream wait would invalidate capture.
         cur = torch.cuda.current_stream()
@@ -150,10 +157,11 @@ def loss_backward(losses, optimizer, grad_sync=None):
     return loss
 
 
-def train_step(opt, netG, netD, optG, optD, tgt_label, tgt_image, ref_labels, ref_images, sync_G=None, sync_D=None):
-    """train.py:58-62: discriminator update, then generator update, for one frame."""
-    d_losses = discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images)
+def train_step(opt, netG, netD, optG, optD, tgt_label, tgt_image, ref_labels, ref_images, sync_G=None, sync_D=None, prev=None):
+    """train.py:58-62: discriminator update, then generator update, for one frame (``prev`` = [prev_label, prev_image] in
+    the temporal phase)."""
+    d_losses = discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=prev)
     ld = loss_backward(d_losses, optD, sync_D)
-    g_losses, fake = generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images)
+    g_losses, fake = generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=prev)
     lg = loss_backward(g_losses, optG, sync_G)
     return ld, lg, fake

@@ -382,11 +382,14 @@ def mask_loss(flow_mask, warped, tgt, lambda_mask):
     return (masked_l1(flow_mask, zero, conf) + masked_l1(flow_mask, one, 1 - conf)) * lambda_mask
 
 
-def generator_losses(sdG, sdD, opt, tgt_label, tgt_image, ref_labels, ref_images, n_layers_D=4, num_D=1):
+def generator_losses(sdG, sdD, opt, tgt_label, tgt_image, ref_labels, ref_images, n_layers_D=4, num_D=1, prev=None):
     """vid2vid_model.py:62-104 forward_generator for the single-frame phase with
     ``--no_flow_gt --no_vgg_loss`` on a non-pose dataset: returns dict of the
     non-zero losses (G_GAN, G_GAN_Feat, F_Warp, F_Mask) and the fake image."""
-    out = generator_forward(sdG, opt, tgt_label, ref_labels, ref_images, training=True)
+    if prev is None:
+        out = generator_forward(sdG, opt, tgt_label, ref_labels, ref_images, training=True)
+    else:       # temporal phase: both branches of flow / mask / warp contribute (loss_collector.py:132-136,165-168)
+        out = generator_forward(sdG, opt, tgt_label, ref_labels, ref_images, prev=prev, training=True, temporal=True)
     fake, flow, fmask, _, warp = out[0], out[1], out[2], out[3], out[4]
     ref_label, ref_image = ref_labels[:, 0], ref_images[:, 0]
     pred = discriminator_forward(sdD, d_input(tgt_label, fake, tgt_image, ref_label, ref_image), n_layers_D, num_D)
@@ -398,6 +401,9 @@ def generator_losses(sdG, sdD, opt, tgt_label, tgt_image, ref_labels, ref_images
     if flow[0] is not None:
         losses['F_Warp'] = (warp[0] - tgt_image).abs().mean() * opt.lambda_flow   # loss_collector.py:154-162
         losses['F_Mask'] = mask_loss(fmask[0], warp[0], tgt_image, opt.lambda_mask)
+    if flow[1] is not None:
+        losses['F_Warp'] = losses.get('F_Warp', 0) + (warp[1] - tgt_image).abs().mean() * opt.lambda_flow
+        losses['F_Mask'] = losses.get('F_Mask', 0) + mask_loss(fmask[1], warp[1], tgt_image, opt.lambda_mask)
     return losses, fake
 
 

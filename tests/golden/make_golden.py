@@ -394,8 +394,59 @@ def kshot():
     save('g_kshot_tiny.npz', **arrays)
 
 
+def temporal_step():
+    """G-step losses of the temporal phase (warp_prev) through the reference LossCollector: the flow / mask terms of BOTH
+    branches (reference image and previous frame).  Reuses state and inputs of g_face_tiny_temporal.npz.  -> step_face_tiny_temporal.npz"""
+    install_shims()
+    import models.networks as networks
+    import models.networks.generator as refgen
+    import models.loss_collector as reflc
+    refgen.resample = resample_any_device
+    reflc.resample = resample_any_device
+    zt = np.load(os.path.join(HERE, 'g_face_tiny_temporal.npz'))
+    opt = Namespace(**TINY)
+    G = networks.define_G(opt)
+    G.init_temporal_network()
+    G.load_state_dict({k[3:]: torch.from_numpy(np.array(zt[k])) for k in zt.files if k.startswith('sd.')})
+    G.train()
+    torch.manual_seed(3)
+    D1 = networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, 1, True, gpu_ids=[])
+    D1.train()
+    sdd = {k: v.clone() for k, v in D1.state_dict().items()}
+    os.makedirs(os.path.join(opt.checkpoints_dir, opt.name), exist_ok=True)
+    lc = reflc.LossCollector()
+    lc.initialize(opt)
+    t = lambda k: torch.from_numpy(np.array(zt[k]))  # noqa: E731
+    label, lref, iref, plabel, pimg = t('label'), t('lref'), t('iref'), t('prev_label'), t('prev_img')
+    gen = torch.Generator().manual_seed(77)
+    tgt = torch.rand(label.shape[0], 3, label.shape[2], label.shape[3], generator=gen) * 2 - 1
+    og = G(label, lref, iref, prev=[plabel, pimg])
+    fake, flow_g, mask_g, warp_g = og[0], og[1], og[2], og[4]
+    tgt_label5, tgt_image5 = label.unsqueeze(1), tgt.unsqueeze(1)
+    nets = (D1, None, None, None)
+    data_list = [tgt_label5, [tgt_image5, tgt_image5 * 1], [fake.unsqueeze(1), None], lref[:, 0], iref[:, 0]]
+    g_gan, g_feat, _, _ = lc.compute_GAN_losses(nets, data_list, for_discriminator=False)
+    rs5 = lambda xs: [x.unsqueeze(1) if x is not None else None for x in xs]  # noqa: E731
+    flow5, mask5, warp5 = rs5(flow_g), rs5(mask_g), rs5(warp_g)
+    l_flow, l_warp, body = lc.compute_flow_losses(lc.reshape(flow5), lc.reshape(warp5), lc.reshape(tgt_image5),
+                                                  [None, None], [None, None], None, tgt_label5, lref[:, 0])
+    l_mask = lc.compute_mask_losses(lc.reshape(mask5), fake.unsqueeze(1), lc.reshape(warp5), tgt_label5,
+                                    lc.reshape(tgt_image5), None, None, None, body)
+    total = g_gan.mean() + g_feat.mean() + l_warp.mean() + l_mask.mean() + l_flow.mean()
+    total.backward()
+    pg = dict(G.named_parameters())
+    arrays = dict(tgt=tgt.numpy(), G_GAN=g_gan.detach().numpy(), G_GAN_Feat=g_feat.detach().numpy(),
+                  F_Warp=l_warp.detach().numpy(), F_Mask=l_mask.detach().numpy(), fake=fake.detach().numpy())
+    arrays.update(npz_state('sdD.', sdd))
+    for n in ['conv_img.weight', 'up_0.bn_0.mlp_gamma3.weight', 'flow_network_ref.conv_mask.0.weight', 'img_prev_embedding.up_1.1.weight']:
+        arrays['gradG.' + n] = pg[n].grad.numpy()
+    save('step_face_tiny_temporal.npz', **arrays)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'kshot':
+    if len(sys.argv) > 1 and sys.argv[1] == 'temporal_step':
+        temporal_step()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'kshot':
         kshot()
     elif len(sys.argv) > 1 and sys.argv[1] == 'variants':
         variants()

@@ -189,3 +189,27 @@ def test_train_step_losses(nets, monkeypatch):
     for k in z.files:
         if k.startswith('gradG.'):
             assert grad_err(pg[k[6:]].grad, T(z[k])) < GTOL, k
+
+
+def test_train_step_losses_temporal_phase(nets, monkeypatch):
+    """G-step losses with a previous frame (warp_prev): warp / mask terms of both branches, against the reference's
+    LossCollector (tests/golden/step_face_tiny_temporal.npz; state and inputs of g_face_tiny_temporal.npz)."""
+    from fsv import trainer
+    monkeypatch.setattr(trainer, 'ops', mock_ops)
+    z = load_npz('step_face_tiny_temporal.npz')
+    zt = load_npz('g_face_tiny_temporal.npz')
+    opt = opt_from(zt)
+    G = _build(nets, opt, state_from(zt, 'sd.'), temporal=True)
+    D = nets.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, 1, True, gpu_ids=[])
+    D.load_state_dict(state_from(z, 'sdD.'))
+    D.train()
+    gl, fake = trainer.generator_losses(opt, G, D, T(zt['label']), T(z['tgt']), T(zt['lref']), T(zt['iref']),
+                                        prev=[T(zt['prev_label']), T(zt['prev_img'])])
+    assert rel_err(fake, T(z['fake'])) < TOL
+    for n in ('G_GAN', 'G_GAN_Feat', 'F_Warp', 'F_Mask'):
+        assert rel_err(gl[n].reshape(-1), T(z[n]).reshape(-1)) < TOL, n
+    sum(v.mean() for v in gl.values()).backward()
+    pg = dict(G.named_parameters())
+    for k in z.files:
+        if k.startswith('gradG.'):
+            assert grad_err(pg[k[6:]].grad, T(z[k])) < GTOL, k

@@ -224,3 +224,15 @@ def test_generator_two_reference_images_attention():
     for k in z.files:
         if k.startswith('grad.'):
             assert grad_err(sd[k[5:]].grad, T(z[k])) < 1e-3, k
+
+
+def test_generator_losses_temporal_phase():
+    """oracle generator_losses with a previous frame against the reference LossCollector (step_face_tiny_temporal.npz)."""
+    z = load_npz('step_face_tiny_temporal.npz')
+    zt = load_npz('g_face_tiny_temporal.npz')
+    opt = opt_from(zt)
+    losses, fake = nets.generator_losses(state_from(zt, 'sd.'), state_from(z, 'sdD.'), opt, T(zt['label']), T(z['tgt']),
+                                         T(zt['lref']), T(zt['iref']), prev=(T(zt['prev_label']), T(zt['prev_img'])))
+    assert rel_err(fake, T(z['fake'])) < TOL
+    for n in ('G_GAN', 'G_GAN_Feat', 'F_Warp', 'F_Mask'):
+        assert rel_err(losses[n].reshape(-1), T(z[n]).reshape(-1)) < TOL, n
