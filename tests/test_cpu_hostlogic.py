@@ -213,3 +213,25 @@ def test_train_step_losses_temporal_phase(nets, monkeypatch):
     for k in z.files:
         if k.startswith('gradG.'):
             assert grad_err(pg[k[6:]].grad, T(z[k])) < GTOL, k
+
+
+@pytest.mark.parametrize('temporal', [False, True])
+def test_train_step_runs_and_updates_parameters(nets, monkeypatch, temporal):
+    """trainer.train_step (what bench.py calls every iteration: D-step + G-step incl. both Adam updates) end to end on the
+    emulated op layer, single-frame and temporal phase: finite losses, parameters of G and D actually move."""
+    from fsv import trainer
+    monkeypatch.setattr(trainer, 'ops', mock_ops)
+    zt = load_npz('g_face_tiny_temporal.npz' if temporal else 'g_face_tiny.npz')
+    opt = opt_from(zt)
+    G = _build(nets, opt, state_from(zt, 'sd.'), temporal=temporal)
+    D = nets.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, 1, True, gpu_ids=[])
+    D.train()
+    optG, optD = trainer.make_optimizers(opt, G, D)
+    w0 = G.conv_img.weight.detach().clone()
+    d0 = next(D.parameters()).detach().clone()
+    g = torch.Generator().manual_seed(5)
+    tgt = torch.rand(T(zt['label']).shape[0], 3, 64, 64, generator=g) * 2 - 1
+    prev = [T(zt['prev_label']), T(zt['prev_img'])] if temporal else None
+    ld, lg, fake = trainer.train_step(opt, G, D, optG, optD, T(zt['label']), tgt, T(zt['lref']), T(zt['iref']), prev=prev)
+    assert torch.isfinite(ld).all() and torch.isfinite(lg).all() and fake.shape == tgt.shape
+    assert not torch.equal(G.conv_img.weight.detach(), w0) and not torch.equal(next(D.parameters()).detach(), d0)
