@@ -77,6 +77,12 @@ SIGNATURES = {
     'fsv_spectral_workspace': [c_int, c_int],
     'fsv_spectral_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     'fsv_spectral_bwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    'fsv_fg_mask': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_float, c_vp],
+    'fsv_face_mask_avg15': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp],
+    'fsv_part_masks': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp],
+    'fsv_face_bbox': [c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    'fsv_crop_resize_fwd': [c_vp, c_ll, c_ll, c_ll, c_ll, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
+    'fsv_crop_resize_bwd': [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
 }
 
 

@@ -85,7 +85,10 @@ class MultiscaleDiscriminator(BaseNetwork):
             setattr(self, 'discriminator_%d' % i, NLayerDiscriminator(input_nc, ndf, n_layers, norm_layer, getIntermFeat, stride))
 
     def forward(self, input, ref=None):
-        x = ops.to_nhwc(input)
+        return self.forward_nhwc(ops.to_nhwc(input))
+
+    def forward_nhwc(self, x):
+        """Same result for an input that is already NHWC (and possibly channel-padded, ops.pad_channels): what fsv.model packs."""
         result = []
         for i in range(self.num_D):
             feats = [ops.nchw_view(f) for f in getattr(self, 'discriminator_%d' % i).forward_nhwc(x)]

@@ -36,9 +36,18 @@ class Conv2d(nn.Module):
         return (w, None) if want_wt else w
 
     def forward(self, x, up=1, act=ACT_NONE, residual=None, out_scale=1.0, in_act=ACT_NONE):
+        cin = x.shape[3]
         # the swapped copy only pays off where the tensor-core data gradient will run (conv_tc.cu eligibility)
-        want = self.in_channels % 16 == 0 and self.out_channels % 32 == 0 and x.requires_grad
+        want = cin % 16 == 0 and self.out_channels % 32 == 0 and x.requires_grad
         w, wt = self.ohwi(want_wt=True) if want else (self.ohwi(), None)
+        if cin != self.in_channels:
+            # network-input buffers are zero-padded to the tcgen05 K block (ops.pad_channels): pad the weight's input-channel axis
+            # with zeros to match -- same values; autograd slices the padded weight gradient back
+            if cin < self.in_channels:
+                raise ValueError('conv input has %d channels, expected %d' % (cin, self.in_channels))
+            w = torch.nn.functional.pad(w, (0, cin - self.in_channels))
+            if wt is not None:
+                wt = torch.nn.functional.pad(wt, (0, 0, 0, 0, 0, 0, 0, cin - self.in_channels))
         return ops.conv2d(x, w, self.bias, stride=self.stride, pad=self.padding, up=up, act=act,
                           out_scale=out_scale, residual=residual, in_act=in_act, wt=wt)
 

@@ -41,23 +41,25 @@ def _call(fn, *args):
 # --------------------------------------------------------------------------- layout
 
 class ToNHWC(torch.autograd.Function):
-    """NCHW (reference boundary layout) -> NHWC."""
+    """NCHW (reference boundary layout) -> NHWC, zero-padded to ``cp`` >= C channels (see pad_channels)."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, cp):
         x = _c(x)
         n, c, h, w = x.shape
-        y = torch.empty((n, h, w, c), device=x.device, dtype=torch.float32)
-        _call(lib.fsv_nchw_to_nhwc, ptr(x), ptr(y), n, c, h, w, c, 0, stream())
+        cp = max(cp or c, c)
+        y = (torch.empty if cp == c else torch.zeros)((n, h, w, cp), device=x.device, dtype=torch.float32)
+        _call(lib.fsv_nchw_to_nhwc, ptr(x), ptr(y), n, c, h, w, cp, 0, stream())
+        ctx.c = c
         return y
 
     @staticmethod
     def backward(ctx, dy):
         dy = _c(dy)
-        n, h, w, c = dy.shape
-        dx = torch.empty((n, c, h, w), device=dy.device, dtype=torch.float32)
-        _call(lib.fsv_nhwc_to_nchw, ptr(dy), ptr(dx), n, c, h, w, c, 0, 0, stream())
-        return dx
+        n, h, w, cp = dy.shape
+        dx = torch.empty((n, ctx.c, h, w), device=dy.device, dtype=torch.float32)
+        _call(lib.fsv_nhwc_to_nchw, ptr(dy), ptr(dx), n, ctx.c, h, w, cp, 0, 0, stream())
+        return dx, None
 
 
 class ToNCHW(torch.autograd.Function):
@@ -90,8 +92,8 @@ class PackNHWC(torch.autograd.Function):
         xs = [_c(x) for x in xs]
         n, _, h, w = xs[0].shape
         cs = [x.shape[1] for x in xs]
-        ct = sum(cs)
-        y = torch.empty((n, h, w, ct), device=xs[0].device, dtype=torch.float32)
+        ct = pad_channels(sum(cs))                                   # zero channels up to the tcgen05 K block, if wide
+        y = (torch.empty if ct == sum(cs) else torch.zeros)((n, h, w, ct), device=xs[0].device, dtype=torch.float32)
         off = 0
         for x, c in zip(xs, cs):
             if tuple(x.shape) != (n, c, h, w):
@@ -121,8 +123,8 @@ def pack_nhwc(*xs):
     return PackNHWC.apply(*xs)
 
 
-def to_nhwc(x):
-    return ToNHWC.apply(x)
+def to_nhwc(x, pad=True):
+    return ToNHWC.apply(x, pad_channels(x.shape[1]) if pad else x.shape[1])
 
 
 def to_nchw(x):
@@ -783,3 +785,129 @@ def per_sample_matmul(x, flat, cout, cin):
     assert x.shape[3] == cin and flat.shape[1] == cout * cin
     cfg = dict(cout=cout, kh=1, kw=1, stride=1, pad=0, up=1, act=ACT_NONE, w_off=0, w_nstride=cout * cin, use_tc=0)
     return Conv2dFn.apply(x, flat, None, None, cfg)
+
+
+# --------------------------------------------------------------------------- pose label preprocessing + face region
+def _plane(label, ch):
+    """device address and batch stride of channel ``ch`` of a contiguous NCHW label."""
+    label = _c(label)
+    b, c, h, w = label.shape
+    return label, c_vp(label.data_ptr() + 4 * (ch % c) * h * w), c * h * w
+
+
+def fg_mask(label, ch=2, thr=-1.0):
+    """get_fg_mask (models/input_process.py:52-61): (MaxPool2d(15,1,7)(label[:, ch]) > thr).float() -> (B, 1, H, W)."""
+    label, p, ns = _plane(label, ch)
+    b, _, h, w = label.shape
+    out = torch.empty((b, 1, h, w), device=label.device, dtype=torch.float32)
+    _call(lib.fsv_fg_mask, p, ns, ptr(out), b, h, w, float(thr), stream())
+    return out
+
+
+def face_mask_avg15(label, ch=2):
+    """AvgPool2d(15,1,7)(get_face_mask(label[:, ch])) (input_process.py:81-93, loss_collector.py:178-179) -> (B, 1, H, W)."""
+    label, p, ns = _plane(label, ch)
+    b, _, h, w = label.shape
+    out = torch.empty((b, 1, h, w), device=label.device, dtype=torch.float32)
+    _call(lib.fsv_face_mask_avg15, p, ns, ptr(out), b, h, w, stream())
+    return out
+
+
+def part_masks(label, ch=2):
+    """get_part_mask (input_process.py:63-79) of label[:, ch] -> NHWC (B, H, W, 9)."""
+    label, p, ns = _plane(label, ch)
+    b, _, h, w = label.shape
+    out = torch.empty((b, h, w, 9), device=label.device, dtype=torch.float32)
+    _call(lib.fsv_part_masks, p, ns, ptr(out), b, h, w, stream())
+    return out
+
+
+def face_bbox(planes, thr, openpose, crop_smaller=0):
+    """get_face_region (models/face_refiner.py:52-83) on the device: ``planes`` = up to three (B, 1|*, H, W)-addressable
+    (tensor, channel) pairs that must all exceed ``thr``.  -> int32 (B, 4) = ys, ye, xs, xe, never copied to the host."""
+    ps = [_plane(t, ch) for t, ch in planes]
+    b, _, h, w = ps[0][0].shape
+    box = torch.empty((b, 4), device=ps[0][0].device, dtype=torch.int32)
+    a = ps + [(None, None, 0)] * (3 - len(ps))
+    _call(lib.fsv_face_bbox, a[0][1], a[1][1], a[2][1], a[0][2], a[1][2], a[2][2], float(thr), b, h, w, 1 if openpose else 0,
+          int(crop_smaller), c_vp(box.data_ptr()), stream())
+    return box
+
+
+class CropResizeFn(torch.autograd.Function):
+    """crop_face_region (face_refiner.py:34-38): image (B, C<=4, H, W) NCHW-shaped (any strides: NCHW tensors and NCHW views
+    of NHWC buffers alike) -> NHWC (B, S, S, C), boxes (B, 4) int32 on the device."""
+
+    @staticmethod
+    def forward(ctx, image, box, size):
+        _lib.require_cuda(image, box)
+        if image.dtype != torch.float32 or box.dtype != torch.int32:
+            raise _lib.FsvError('crop_resize: float32 image and int32 boxes expected')
+        b, c, h, w = image.shape
+        sn, sc, sh, sw = image.stride()
+        out = torch.empty((b, size, size, c), device=image.device, dtype=torch.float32)
+        _call(lib.fsv_crop_resize_fwd, ptr(image), sn, sc, sh, sw, c_vp(box.data_ptr()), ptr(out), b, c, size, c, 0, stream())
+        ctx.save_for_backward(box)
+        ctx.dims = (b, c, h, w, size)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (box,) = ctx.saved_tensors
+        b, c, h, w, size = ctx.dims
+        dout = _c(dout)
+        dimg = torch.empty((b, h, w, c), device=dout.device, dtype=torch.float32)
+        _call(lib.fsv_crop_resize_bwd, ptr(dout), c, 0, c_vp(box.data_ptr()), ptr(dimg), b, c, h, w, size, stream())
+        return dimg.permute(0, 3, 1, 2), None, None
+
+
+def crop_resize(image, box, size):
+    """-> NHWC (B, size, size, C)."""
+    return CropResizeFn.apply(image, box, size)
+
+
+# --------------------------------------------------------------------------- discriminator input packing
+def pad_channels(c):
+    """Channel count a network-input buffer is padded to: thin-layer kernels serve Cin <= 8 as is; wider inputs (pose flow net 15,
+    pose D 20, street label 20 / D 46) are zero-padded to a multiple of 32 so that their first conv runs on the tcgen05 path (its
+    K block is 32 channels); the consumer conv zero-pads its weight to match (layers.Conv2d), so values are unchanged."""
+    return c if c <= 8 else (c + 31) // 32 * 32
+
+
+def pack_rows(dst, row0, tensors, coff):
+    """NCHW tensors -> consecutive channel slices (from ``coff``) of rows [row0, row0 + B) of the NHWC buffer ``dst``.
+    Returns the next free channel offset.  No autograd (constant inputs)."""
+    for t in tensors:
+        t = _c(t.detach())
+        b, c, h, w = t.shape
+        _call(lib.fsv_nchw_to_nhwc, ptr(t), c_vp(dst.data_ptr() + 4 * row0 * h * w * dst.shape[3]), b, c, h, w, dst.shape[3], coff, stream())
+        coff += c
+    return coff
+
+
+class DInputFn(torch.autograd.Function):
+    """The discriminator input of loss_collector.py:47-58: rows [fake ; real], channels [ref.. | label.. | image] in ONE NHWC
+    buffer.  Everything but the fake image is constant over an iteration and was packed once into ``base`` (2B, H, W, Cp);
+    a call copies ``base`` and drops the fake frame (an NCHW-shaped view of the generator's NHWC output) into rows [0, B) at
+    channel ``coff``.  Gradient: that channel slice of rows [0, B)."""
+
+    @staticmethod
+    def forward(ctx, base, fake, coff):
+        x = base.clone()
+        b, c, h, w = fake.shape
+        f = _c(fake.permute(0, 2, 3, 1))
+        _call(lib.fsv_copy_channels, ptr(f), c, 0, ptr(x), x.shape[3], coff, b * h * w, c, 0, stream())
+        ctx.dims = (b, c, h, w, coff)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        b, c, h, w, coff = ctx.dims
+        dx = _c(dx)
+        g = torch.empty((b, h, w, c), device=dx.device, dtype=torch.float32)
+        _call(lib.fsv_copy_channels, ptr(dx), dx.shape[3], coff, ptr(g), c, 0, b * h * w, c, 0, stream())
+        return None, g.permute(0, 3, 1, 2), None
+
+
+def d_input(base, fake, coff):
+    return DInputFn.apply(base, fake, coff)

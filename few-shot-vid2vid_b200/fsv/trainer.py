@@ -1,153 +1,45 @@
-"""One training iteration of the hot path: the mirror of the reference's inner loop
-(train.py:55-62 -> vid2vid_model.py:62-128 -> loss_collector.py:47-228) for the single-frame
-phase with ``--no_flow_gt --no_vgg_loss`` on datasets without a foreground mask (face / street):
+"""Optimizers, the training iteration and its CUDA-graph replay (train.py:55-62, base_model.py:39-48,201-211,259-279,
+loss_collector.py:217-228).  The loss graph itself lives in fsv.model.Vid2VidStep.
 
-    D-step: G forward under no_grad -> D on [fake ; real] -> hinge real/fake -> backward -> Adam
-    G-step: G forward -> D on [fake ; real] -> GAN + feature matching + warp L1 + mask losses -> backward -> Adam
-
-The loss arithmetic is the reference's own torch code path (it sits ABOVE the define_G/define_D
-boundary and is kept); the networks are the fsv drop-in modules.
+    D-step: G forward under no_grad -> D (+ face D, temporal D) on [fake ; real] -> hinge -> backward -> Adam
+    G-step: G forward -> D forward -> GAN + feature matching + warp + mask (+ pose / face) losses -> backward -> Adam
 """
 import torch
 
-from . import ops
-
-
-def _d_input(tgt_label, fake, real, ref_label, ref_image):
-    """loss_collector.py:47-58,104-110 with concat_ref_for_D: batch [fake ; real], channels
-    [ref_label, ref_image, tgt_label, image]."""
-    tgt = torch.cat([fake, real], dim=0)
-    tgt = torch.cat([tgt_label.repeat(2, 1, 1, 1), tgt], dim=1)
-    ref = torch.cat([ref_label, ref_image], dim=1).repeat(2, 1, 1, 1)
-    return torch.cat([ref, tgt], dim=1)
-
-
-def _split(pred):
-    """base_model.py:141-147 divide_pred."""
-    fake = [[t[:t.size(0) // 2] for t in p] for p in pred]
-    real = [[t[t.size(0) // 2:] for t in p] for p in pred]
-    return fake, real
-
-
-def _hinge(pred, target_is_real):
-    """loss.py:69-78 (for_discriminator=True branch -- also what the reference uses for the generator's GAN
-    term, because loss_collector.py:66 omits for_discriminator=False)."""
-    z = pred * 0
-    return -torch.mean(torch.min(pred - 1, z)) if target_is_real else -torch.mean(torch.min(-pred - 1, z))
-
-
-def _gan_loss(preds, target_is_real):
-    """loss.py:92-104."""
-    loss = 0
-    for p in preds:
-        loss = loss + _hinge(p[-1], target_is_real).view(1)
-    return loss / len(preds)
-
-
-def _feat_match(pred_real, pred_fake, lambda_feat):
-    """loss_collector.py:206-215."""
-    num_d = len(pred_fake)
-    loss = 0
-    for i in range(num_d):
-        for j in range(len(pred_fake[i]) - 1):
-            loss = loss + torch.nn.functional.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) / num_d
-    return loss * lambda_feat
-
-
-def _masked_l1(a, b, m):
-    m = m.expand_as(a)
-    return torch.nn.functional.l1_loss(a * m, b * m)
-
-
-def _mask_loss(flow_mask, warped, tgt, lambda_mask):
-    """loss_collector.py:191-204."""
-    conf = torch.clamp(1 - torch.sum(abs(warped - tgt), dim=1, keepdim=True), 0, 1)
-    zero, one = torch.zeros_like(flow_mask), torch.ones_like(flow_mask)
-    return (_masked_l1(flow_mask, zero, conf) + _masked_l1(flow_mask, one, 1 - conf)) * lambda_mask
-
-
-def discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=None):
-    """vid2vid_model.py:106-128.  ``prev`` = [prev_label, prev_image] in the temporal phase (warp_prev), else None."""
-    with torch.no_grad():
-        fake = (netG(tgt_label, ref_labels, ref_images) if prev is None else netG(tgt_label, ref_labels, ref_images, prev=prev))[0]
-    pred = netD(_d_input(tgt_label, fake.detach(), tgt_image, ref_labels[:, 0], ref_images[:, 0]))
-    pf, pr = _split(pred)
-    return {'D_real': _gan_loss(pr, True), 'D_fake': _gan_loss(pf, False)}
-
-
-def generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=None):
-    """vid2vid_model.py:62-104 (non-zero terms under --no_flow_gt --no_vgg_loss, no foreground mask).  With ``prev`` =
-    [prev_label, prev_image] (temporal phase) the warp / mask terms of the previous-frame branch are added
-    (loss_collector.py:132-136,165-168: both entries of flow / flow_mask / warped image contribute)."""
-    out = netG(tgt_label, ref_labels, ref_images) if prev is None else netG(tgt_label, ref_labels, ref_images, prev=prev)
-    fake, flow, fmask, warp = out[0], out[1], out[2], out[4]
-    pred = netD(_d_input(tgt_label, fake, tgt_image, ref_labels[:, 0], ref_images[:, 0]))
-    pf, pr = _split(pred)
-    losses = {'G_GAN': _gan_loss(pf, True), 'G_GAN_Feat': _feat_match(pr, pf, opt.lambda_feat)}
-    if flow[0] is not None:
-        losses['F_Warp'] = torch.nn.functional.l1_loss(warp[0], tgt_image) * opt.lambda_flow
-        losses['F_Mask'] = _mask_loss(fmask[0], warp[0], tgt_image, opt.lambda_mask)
-    if flow[1] is not None:
-        zero = tgt_image.new_zeros(())
-        losses['F_Warp'] = losses.get('F_Warp', zero) + torch.nn.functional.l1_loss(warp[1], tgt_image) * opt.lambda_flow
-        losses['F_Mask'] = losses.get('F_Mask', zero) + _mask_loss(fmask[1], warp[1], tgt_image, opt.lambda_mask)
-    return losses, fake
-
+from .model import Vid2VidStep, LOSS_NAMES_D, LOSS_NAMES_G  # noqa: F401
 
 FUSED_ADAM = True
 
 
-def make_optimizers(opt, netG, netD, capturable=False):
-    """base_model.py:39-48 Adam with TTUR.  ``capturable`` keeps the step counters on the device so the whole
-    iteration can be recorded into a CUDA graph (same arithmetic)."""
+def _adam(params, lr, betas, capturable):
+    params = list(params)
+    # fused=True: torch's single-kernel multi-tensor Adam (same update rule as the reference's torch.optim.Adam)
+    fused = FUSED_ADAM and all(p.is_cuda for p in params)
+    return torch.optim.Adam(params, lr=lr, betas=betas, capturable=capturable, fused=True if fused else None)
+
+
+def make_step_optimizers(opt, step, capturable=False):
+    """base_model.py:39-48 (TTUR) over netG and over netD [+ netDT] [+ netDf] (base_model.py:204-211,267-277).  Call again after
+    ``step.init_temporal_model()`` -- the reference re-creates both optimizers there."""
     if opt.no_TTUR:
         beta1, beta2, g_lr, d_lr = opt.beta1, 0.999, opt.lr, opt.lr
     else:
         beta1, beta2, g_lr, d_lr = 0.0, opt.beta2, opt.lr / 2, opt.lr * 2
-    # fused=True: torch's single-kernel multi-tensor Adam (same update rule; ~7 instead of ~30 passes over the 98 M generator
-    # parameters and their moments) -- the optimizer is parameter-side plumbing, as in the reference (base_model.py:39-48)
-    def adam(net, lr):
-        params = list(net.parameters())
-        fused = FUSED_ADAM and all(p.is_cuda for p in params)
-        return torch.optim.Adam(params, lr=lr, betas=(beta1, beta2), capturable=capturable, fused=True if fused else None)
-    return adam(netG, g_lr), adam(netD, d_lr)
+    return (_adam(step.netG.parameters(), g_lr, (float(beta1), float(beta2)), capturable),
+            _adam(step.d_parameters(), d_lr, (float(beta1), float(beta2)), capturable))
 
 
-class GraphedStep:
-    """The whole training iteration (train.py:58-62: D-step + G-step incl. both Adam updates) recorded once into a
-    CUDA graph and replayed: ~5000 kernel launches (ours + the parameter-side torch ops) become one graph launch,
-    which removes the host-side launch latency between the many small kernels.  Inputs are copied into static
-    buffers before each replay; the returned losses are static tensors overwritten by each replay."""
-
-    def __init__(self, opt, netG, netD, optG, optD, example, sync_G=None, sync_D=None, warmup=3):
-        self.static = {k: v.clone() for k, v in example.items()}
-        st = self.static
-
-        def run():
-            prev = [st['prev_label'], st['prev_image']] if 'prev_label' in st else None      # temporal phase inputs, if given
-            return train_step(opt, netG, netD, optG, optD, st['tgt_label'], st['tgt_image'], st['ref_labels'], st['ref_images'],
-                              sync_G=sync_G, sync_D=sync_D, prev=prev)
-        # Capture on the stream the eager iterations already ran on (it must not be the legacy default stream): autograd's
-        # AccumulateGrad nodes remember the stream they were created on, and a cross-stream wait would invalidate capture.
-        cur = torch.cuda.current_stream()
-        if cur == torch.cuda.default_stream():
-            raise RuntimeError('GraphedStep: run the training loop under a non-default stream (torch.cuda.set_stream)')
-        for _ in range(warmup):
-            run()
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=cur):
-            self.ld, self.lg, self.fake = run()
-
-    def __call__(self, inp):
-        for k, v in inp.items():
-            self.static[k].copy_(v, non_blocking=True)
-        self.graph.replay()
-        return self.ld, self.lg, self.fake
+def make_optimizers(opt, netG, netD, capturable=False):
+    """Two-network form kept for callers that hold bare modules."""
+    class _S:
+        pass
+    s = _S()
+    s.netG, s.d_parameters = netG, (lambda: list(netD.parameters()))
+    return make_step_optimizers(opt, s, capturable)
 
 
 def loss_backward(losses, optimizer, grad_sync=None):
-    """loss_collector.py:217-228: mean -> sum -> zero_grad -> backward -> [allreduce] -> step."""
+    """loss_collector.py:217-228: mean -> sum -> zero_grad -> backward -> [all-reduce] -> step."""
     loss = sum(torch.mean(v) for v in losses.values())
     optimizer.zero_grad()
     loss.backward()
@@ -157,11 +49,104 @@ def loss_backward(losses, optimizer, grad_sync=None):
     return loss
 
 
+def train_iteration(step, optG, optD, batch, sync_G=None, sync_D=None):
+    """train.py:58-62 for one frame: discriminator update, then generator update.  -> (d_losses, g_losses, fake, prevs_new)"""
+    c = step.prepare(batch)
+    d_losses = step.discriminator_losses(batch, c)
+    loss_backward(d_losses, optD, sync_D)
+    g_losses, fake, prevs = step.generator_losses(batch, c)
+    loss_backward(g_losses, optG, sync_G)
+    return d_losses, g_losses, fake, prevs
+
+
+class GraphedStep:
+    """The whole training iteration (both optimizer updates and, on N > 1 ranks, the gradient all-reduces included) recorded
+    once into a CUDA graph and replayed: thousands of kernel launches become one graph launch.  Inputs are copied into static
+    buffers before each replay; the returned losses / frame are static tensors overwritten by each replay.
+
+    Construction runs ``warmup`` real iterations on the example batch before capture (allocator / cuBLAS-free warm-up that
+    capture needs); by default the training state they touch -- parameters, optimizer moments and step counters, BatchNorm
+    running statistics, spectral-norm u / v -- is snapshotted before and restored after, so constructing the graph does not
+    advance training.  It must be constructed collectively (every rank, same order) when gradient syncs are passed."""
+
+    def __init__(self, step, optG, optD, example, sync_G=None, sync_D=None, warmup=3, preserve_state=True):
+        self.static = {k: v.clone() for k, v in example.items()}
+        st = self.static
+
+        def run():
+            return train_iteration(step, optG, optD, st, sync_G=sync_G, sync_D=sync_D)
+        # Capture on the stream the eager iterations already ran on (it must not be the legacy default stream): autograd's
+        # AccumulateGrad nodes remember the stream they were created on, and a cross-stream wait would invalidate capture.
+        cur = torch.cuda.current_stream()
+        if cur == torch.cuda.default_stream():
+            raise RuntimeError('GraphedStep: run the training loop under a non-default stream (torch.cuda.set_stream)')
+        mods = [step.netG] + step.d_modules()
+        snap = None
+        if preserve_state:
+            snap = ([{k: v.detach().clone() for k, v in m.state_dict().items()} for m in mods],
+                    [_clone_opt_state(o) for o in (optG, optD)])
+        for _ in range(warmup):
+            run()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=cur):
+            self.d_losses, self.g_losses, self.fake, self.prevs = run()
+        if snap is not None:
+            # restore IN PLACE (the graph holds the parameter / moment / buffer addresses)
+            with torch.no_grad():
+                for m, sd in zip(mods, snap[0]):
+                    for k, v in m.state_dict().items():
+                        v.copy_(sd[k])
+                for o, s in zip((optG, optD), snap[1]):
+                    _restore_opt_state(o, s)
+        torch.cuda.synchronize()
+
+    def __call__(self, inp):
+        for k, v in inp.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.d_losses, self.g_losses, self.fake, self.prevs
+
+
+def _clone_opt_state(o):
+    return [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in o.state.get(p, {}).items()} for g in o.param_groups for p in g['params']]
+
+
+def _restore_opt_state(o, snap):
+    i = 0
+    for g in o.param_groups:
+        for p in g['params']:
+            cur = o.state.get(p, {})
+            for k, v in snap[i].items():
+                if torch.is_tensor(v) and k in cur:
+                    cur[k].copy_(v)
+            for k in list(cur):
+                if k not in snap[i] and torch.is_tensor(cur[k]):
+                    cur[k].zero_()          # state created during warm-up (first step): back to its initial zeros
+            i += 1
+
+
+# ------------------------------------------------------------------------------------------------ bare-module helpers
+def _batch(tgt_label, tgt_image, ref_labels, ref_images, prev=None):
+    b = dict(tgt_label=tgt_label.unsqueeze(1), tgt_image=tgt_image.unsqueeze(1), ref_label=ref_labels, ref_image=ref_images)
+    if prev is not None:
+        b.update(prev_label=prev[0].unsqueeze(1), prev_real=prev[1].unsqueeze(1), prev_fake=prev[1].unsqueeze(1))
+    return b
+
+
+def discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=None, netDf=None, netDT=None):
+    """4-D tensor form (tgt_label (B,C,H,W), tgt_image (B,3,H,W)) on caller-held modules; ``prev`` = [prev_label, prev_fake_image]."""
+    step = Vid2VidStep(opt, netG, netD, netDf, netDT)
+    return step.discriminator_losses(_batch(tgt_label, tgt_image, ref_labels, ref_images, prev))
+
+
+def generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=None, netDf=None, netDT=None):
+    step = Vid2VidStep(opt, netG, netD, netDf, netDT)
+    g, fake, _ = step.generator_losses(_batch(tgt_label, tgt_image, ref_labels, ref_images, prev))
+    return g, fake
+
+
 def train_step(opt, netG, netD, optG, optD, tgt_label, tgt_image, ref_labels, ref_images, sync_G=None, sync_D=None, prev=None):
-    """train.py:58-62: discriminator update, then generator update, for one frame (``prev`` = [prev_label, prev_image] in
-    the temporal phase)."""
-    d_losses = discriminator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=prev)
-    ld = loss_backward(d_losses, optD, sync_D)
-    g_losses, fake = generator_losses(opt, netG, netD, tgt_label, tgt_image, ref_labels, ref_images, prev=prev)
-    lg = loss_backward(g_losses, optG, sync_G)
-    return ld, lg, fake
+    step = Vid2VidStep(opt, netG, netD)
+    d, g, fake, _ = train_iteration(step, optG, optD, _batch(tgt_label, tgt_image, ref_labels, ref_images, prev), sync_G, sync_D)
+    return sum(v.mean() for v in d.values()).detach(), sum(v.mean() for v in g.values()).detach(), fake

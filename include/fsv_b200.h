@@ -229,6 +229,28 @@ int fsv_spectral_fwd(const float* w_orig, float* u, float* v, int R, int Cin, in
 int fsv_spectral_bwd(const float* dw_ohwi, const float* w_sn_ohwi, const float* uvs, int R, int Cin, int taps, float* dw_orig,
                      float* work, void* stream);
 
+/* ------------------------------------------------------------------ pose label preprocessing + face region */
+/* (MaxPool2d(15, stride 1, pad 7)(plane) > thr).float(): get_fg_mask, models/input_process.py:52-61.  plane n starts at
+ * label + n*n_stride (pass the address of channel 2 of an NCHW label and n_stride = C*H*W); out (N, H, W). */
+int fsv_fg_mask(const float* label, long long n_stride, float* out, int N, int H, int W, float thr, void* stream);
+/* AvgPool2d(15, stride 1, pad 7)(get_face_mask(part)): input_process.py:81-93 + loss_collector.py:178-179; out (N, H, W). */
+int fsv_face_mask_avg15(const float* part, long long n_stride, float* out, int N, int H, int W, void* stream);
+/* get_part_mask (input_process.py:63-79): the 9 body-part group masks of a DensePose part-id plane; out NHWC (N, H, W, 9). */
+int fsv_part_masks(const float* part, long long n_stride, float* out, int N, int H, int W, void* stream);
+/* get_face_region (models/face_refiner.py:52-83) without nonzero()/.item(): face pixels = all given planes (p1, p2 may be
+ * NULL) > thr; plane k of sample n starts at pk + n*sk.  openpose != 0 selects the keypoint-box arithmetic (:64-66), else the
+ * DensePose one (:68-69).  box[n] = {ys, ye, xs, xe} (int32, device memory), shrunk by crop_smaller on every side. */
+int fsv_face_bbox(const float* p0, const float* p1, const float* p2, long long s0, long long s1, long long s2, float thr,
+                  int N, int H, int W, int openpose, int crop_smaller, int* box, void* stream);
+/* crop_face_region (face_refiner.py:34-38): dst[n] = F.interpolate(src[n, :, ys:ye, xs:xe], size=(S, S), mode='nearest') for the
+ * device-resident boxes; src element (n,c,y,x) lives at n*sn + c*sc + y*sh + x*sw (NCHW tensors and NCHW-shaped views of NHWC
+ * buffers alike), dst is NHWC (N, S, S, dst_ld) at channel offset dst_coff.  bwd: dsrc (N, H, W, C) NHWC, fully overwritten
+ * (zero outside the box), deterministic (gather form, no atomics); C <= 4. */
+int fsv_crop_resize_fwd(const float* src, long long sn, long long sc, long long sh, long long sw, const int* box,
+                        float* dst, int N, int C, int S, int dst_ld, int dst_coff, void* stream);
+int fsv_crop_resize_bwd(const float* ddst, int dst_ld, int dst_coff, const int* box, float* dsrc, int N, int C, int H, int W,
+                        int S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

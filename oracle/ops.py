@@ -253,3 +253,73 @@ def feat_match_loss(pred_real, pred_fake, lambda_feat=10.0):
         for j in range(len(pred_fake[i]) - 1):
             loss = loss + (pred_fake[i][j] - pred_real[i][j].detach()).abs().mean() / num_d
     return loss * lambda_feat
+
+
+# ---------------------------------------------------------------------------- pose label preprocessing / face region
+PART_GROUPS = [[0], [1, 2], [3, 4], [5, 6], [7, 9, 8, 10], [11, 13, 12, 14], [15, 17, 16, 18], [19, 21, 20, 22], [23, 24]]
+
+
+def fg_mask(label):
+    """models/input_process.py:52-61 get_fg_mask for label_nc == 0: channel 2 (DensePose part id, background exactly -1),
+    dilated by a 15x15 max filter, thresholded at -1.  label (B, C, H, W) -> (B, 1, H, W) in {0, 1}."""
+    m = F.max_pool2d(label[:, 2:3], 15, stride=1, padding=7)
+    return (m > -1).to(label.dtype)
+
+
+def part_masks(part):
+    """input_process.py:63-79 get_part_mask: part (B, H, W) in [-1, 1] -> (B, 9, H, W); id = (part/2+0.5)*24 within 0.1 of j."""
+    p = (part / 2 + 0.5) * 24
+    out = torch.zeros(part.shape[0], len(PART_GROUPS), *part.shape[1:], dtype=part.dtype)
+    for i, grp in enumerate(PART_GROUPS):
+        for j in grp:
+            out[:, i] = torch.maximum(out[:, i], ((p > j - 0.1) & (p < j + 0.1)).to(part.dtype))
+    return out
+
+
+def face_mask(part):
+    """input_process.py:81-93 get_face_mask: ids 23 and 24.  part (B, H, W) -> (B, 1, H, W)."""
+    p = (part / 2 + 0.5) * 24
+    m = torch.zeros_like(part, dtype=torch.bool)
+    for j in (23, 24):
+        m = m | ((p > j - 0.1) & (p < j + 0.1))
+    return m.to(part.dtype).unsqueeze(1)
+
+
+def face_mask_avg15(part):
+    """loss_collector.py:178-179: AvgPool2d(15, padding=7, stride=1) of the face mask (zero padding counted)."""
+    return F.avg_pool2d(face_mask(part), 15, stride=1, padding=7)
+
+
+def face_region(face, h, w, use_openpose, crop_smaller=0):
+    """models/face_refiner.py:52-83 get_face_region for ONE sample given its boolean face-pixel map (h, w)."""
+    idx = face.nonzero()
+    if idx.shape[0]:
+        y, x = idx[:, 0], idx[:, 1]
+        ys, ye, xs, xe = int(y.min()), int(y.max()), int(x.min()), int(x.max())
+        if use_openpose:
+            xc, yc = (xs + xe) // 2, (ys * 3 + ye * 2) // 5
+            ylen = int((xe - xs) * 2.5)
+        else:
+            xc, yc = (xs + xe) // 2, (ys + ye) // 2
+            ylen = int((ye - ys) * 1.25)
+        ylen = xlen = min(w, max(32, ylen))
+        yc = max(ylen // 2, min(h - 1 - ylen // 2, yc))
+        xc = max(xlen // 2, min(w - 1 - xlen // 2, xc))
+    else:
+        yc, xc = h // 4, w // 2
+        ylen = xlen = h // 32 * 8
+    ys, ye, xs, xe = yc - ylen // 2, yc + ylen // 2, xc - xlen // 2, xc + xlen // 2
+    return ys + crop_smaller, ye - crop_smaller, xs + crop_smaller, xe - crop_smaller
+
+
+def face_pixels(label, use_openpose):
+    """face_refiner.py:57-62: OpenPose: the LAST three channels all > 0; DensePose: channel 2 > 0.9.  label (B, C, H, W)."""
+    if use_openpose:
+        return (label[:, -3] > 0) & (label[:, -2] > 0) & (label[:, -1] > 0)
+    return label[:, 2] > 0.9
+
+
+def crop_face_region(image, boxes, size):
+    """face_refiner.py:34-38: per sample image[i, -3:, ys:ye, xs:xe] nearest-resized to (size, size)."""
+    outs = [F.interpolate(image[i:i + 1, -3:, ys:ye, xs:xe], size=(size, size)) for i, (ys, ye, xs, xe) in enumerate(boxes)]
+    return torch.cat(outs)

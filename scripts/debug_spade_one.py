@@ -6,7 +6,7 @@ for p in (ROOT, os.path.join(ROOT, 'few-shot-vid2vid_b200'), os.path.join(ROOT, 
 import torch
 from fsv import networks, ops
 from oracle import ops as O
-from util import load_npz, state_from, opt_from, T, rel_err, grad_err
+from fsvtest import load_npz, state_from, opt_from, T, rel_err, grad_err
 ops.CONV_USE_TC = 0
 z = load_npz('g_face_tiny.npz')
 opt = opt_from(z); opt.gpu_ids = [0]

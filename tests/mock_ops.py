@@ -37,8 +37,17 @@ def _nhwc(x):
 
 
 # ------------------------------------------------------------------ layout
-def to_nhwc(x):
-    return _nhwc(x)
+def pad_channels(c):
+    return c if c <= 8 else (c + 31) // 32 * 32
+
+
+def _padc(x_nhwc):
+    c = x_nhwc.shape[3]
+    return F.pad(x_nhwc, (0, pad_channels(c) - c))
+
+
+def to_nhwc(x, pad=True):
+    return _padc(_nhwc(x)) if pad else _nhwc(x)
 
 
 def to_nchw(x):
@@ -50,7 +59,21 @@ def nchw_view(x):
 
 
 def pack_nhwc(*xs):
-    return _nhwc(torch.cat(xs, dim=1))
+    return _padc(_nhwc(torch.cat(xs, dim=1)))
+
+
+def pack_rows(dst, row0, tensors, coff):
+    for t in tensors:
+        b, c = t.shape[:2]
+        dst[row0:row0 + b, :, :, coff:coff + c] = t.detach().permute(0, 2, 3, 1)
+        coff += c
+    return coff
+
+
+def d_input(base, fake, coff):
+    b, c = fake.shape[:2]
+    x = base.clone()
+    return torch.cat([torch.cat([x[:b, :, :, :coff], fake.permute(0, 2, 3, 1), x[:b, :, :, coff + c:]], dim=3), x[b:]], dim=0)
 
 
 def cat_channels(*xs):
@@ -176,3 +199,36 @@ def spectral_weight(w_orig, u, v, training, eps=1e-12, want_wt=False):
     w = w_orig / sigma
     out = w.permute(0, 2, 3, 1).contiguous() if w.dim() == 4 else w
     return (out, None) if want_wt else out
+
+
+# ------------------------------------------------------------------ pose label preprocessing + face region (oracle restatements)
+def fg_mask(label, ch=2, thr=-1.0):
+    assert ch == 2 and thr == -1.0
+    from oracle import ops as OO
+    return OO.fg_mask(label)
+
+
+def face_mask_avg15(label, ch=2):
+    from oracle import ops as OO
+    return OO.face_mask_avg15(label[:, ch])
+
+
+def part_masks(label, ch=2):
+    from oracle import ops as OO
+    return OO.part_masks(label[:, ch]).permute(0, 2, 3, 1).contiguous()
+
+
+def face_bbox(planes, thr, openpose, crop_smaller=0):
+    """(B, 4) int32 boxes; face pixels = all planes > thr."""
+    from oracle import ops as OO
+    f = None
+    for t, ch in planes:
+        m = t[:, ch % t.shape[1]] > thr
+        f = m if f is None else (f & m)
+    h, w = f.shape[1:]
+    return torch.tensor([OO.face_region(f[i], h, w, openpose, crop_smaller) for i in range(f.shape[0])], dtype=torch.int32)
+
+
+def crop_resize(image, box, size):
+    from oracle import ops as OO
+    return OO.crop_face_region(image, [tuple(int(v) for v in b) for b in box], size).permute(0, 2, 3, 1).contiguous()

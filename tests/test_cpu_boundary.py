@@ -8,7 +8,7 @@ import re
 import pytest
 import torch
 
-from util import load_npz, state_from, opt_from
+from fsvtest import load_npz, state_from, opt_from
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

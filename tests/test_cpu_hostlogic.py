@@ -12,7 +12,7 @@ import pytest
 import torch
 
 import mock_ops
-from util import load_npz, state_from, opt_from, T, rel_err, l2_err
+from fsvtest import load_npz, state_from, opt_from, T, rel_err, l2_err
 
 TOL = 5e-5
 GTOL = 1e-2     # network-level gradients: relative L2 (a LeakyReLU kink flip perturbs single entries, see util.l2_err)
@@ -161,8 +161,8 @@ def test_generator_two_reference_images(nets):
 def test_train_step_losses(nets, monkeypatch):
     """one D-step + G-step through fsv.trainer (the mirror of vid2vid_model.py:62-128 + loss_collector.py) on the
     emulated op layer: loss values, the generated frame and parameter gradients against the reference's LossCollector."""
-    from fsv import trainer
-    monkeypatch.setattr(trainer, 'ops', mock_ops)
+    from fsv import trainer, model
+    monkeypatch.setattr(model, 'ops', mock_ops)
     z = load_npz('step_face_tiny.npz')
     zg = load_npz('g_face_tiny.npz')
     opt = opt_from(zg)
@@ -194,8 +194,8 @@ def test_train_step_losses(nets, monkeypatch):
 def test_train_step_losses_temporal_phase(nets, monkeypatch):
     """G-step losses with a previous frame (warp_prev): warp / mask terms of both branches, against the reference's
     LossCollector (tests/golden/step_face_tiny_temporal.npz; state and inputs of g_face_tiny_temporal.npz)."""
-    from fsv import trainer
-    monkeypatch.setattr(trainer, 'ops', mock_ops)
+    from fsv import trainer, model
+    monkeypatch.setattr(model, 'ops', mock_ops)
     z = load_npz('step_face_tiny_temporal.npz')
     zt = load_npz('g_face_tiny_temporal.npz')
     opt = opt_from(zt)
@@ -219,8 +219,8 @@ def test_train_step_losses_temporal_phase(nets, monkeypatch):
 def test_train_step_runs_and_updates_parameters(nets, monkeypatch, temporal):
     """trainer.train_step (what bench.py calls every iteration: D-step + G-step incl. both Adam updates) end to end on the
     emulated op layer, single-frame and temporal phase: finite losses, parameters of G and D actually move."""
-    from fsv import trainer
-    monkeypatch.setattr(trainer, 'ops', mock_ops)
+    from fsv import trainer, model
+    monkeypatch.setattr(model, 'ops', mock_ops)
     zt = load_npz('g_face_tiny_temporal.npz' if temporal else 'g_face_tiny.npz')
     opt = opt_from(zt)
     G = _build(nets, opt, state_from(zt, 'sd.'), temporal=temporal)

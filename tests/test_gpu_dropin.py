@@ -26,7 +26,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'models')),
                                  reason='baseline/_ref missing: run `python baseline/install_reference.py` in the build container')]
 
-from util import rel_err, l2_err   # noqa: E402
+from fsvtest import rel_err, l2_err   # noqa: E402
 
 
 def trained_scale_(sd, seed=0):

@@ -35,7 +35,7 @@ def test_generator_other_geometries_vs_reference_golden(name):
     import torch
     from fsv import networks, ops
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    from util import load_npz, state_from, T, rel_err, l2_err
+    from fsvtest import load_npz, state_from, T, rel_err, l2_err
     z = load_npz('g_variants_tiny.npz')
     pre = name + '.'
     opt = Namespace(**json.loads(str(z[pre + 'opt'])))
@@ -73,7 +73,7 @@ def test_generator_two_reference_images_vs_reference_golden():
     import torch
     from fsv import networks, ops
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    from util import load_npz, state_from, opt_from, T, rel_err, l2_err
+    from fsvtest import load_npz, state_from, opt_from, T, rel_err, l2_err
     z = load_npz('g_kshot_tiny.npz')
     opt = opt_from(z)
     opt.gpu_ids = [0]

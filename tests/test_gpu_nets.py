@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import nets as ON     # noqa: E402  (checker only)
-from util import load_npz, state_from, opt_from, T, rel_err, l2_err as grad_err   # noqa: E402  (kink-robust metric, see util.l2_err)
+from fsvtest import load_npz, state_from, opt_from, T, rel_err, l2_err as grad_err   # noqa: E402  (kink-robust metric, see util.l2_err)
 
 TOL = 1e-3
 GTOL = 1e-2

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 from oracle import ops as O          # noqa: E402  (checker only)
-from util import rel_err, grad_err   # noqa: E402
+from fsvtest import rel_err, grad_err   # noqa: E402
 
 TOL = 1e-4
 

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 from oracle import ops as O           # noqa: E402
-from util import rel_err, grad_err    # noqa: E402
+from fsvtest import rel_err, grad_err    # noqa: E402
 
 TOL_TF32 = 3e-3
 G = torch.Generator().manual_seed(21)
@@ -218,7 +218,7 @@ def test_spade_tc_forward_and_backward(kind, C, Hs, up, Ks, adaptive, N, act):
         # ~sqrt(1e-3) ~ 1-3% on random inputs, up to ~4% on the smallest case here (16K elements: the flip count is
         # noisy).  The act=0 variant has no kink and pins the same kernels to 5e-3.  (The exact-fp32 kernels are held to
         # 1e-4 in test_gpu_ops.py.)
-        from util import l2_err
+        from fsvtest import l2_err
         GT = 5e-2 if act else 5e-3
         assert l2_err(xg.grad.permute(0, 3, 1, 2), x.grad) < GT
         for a, b in zip(mg, maps):

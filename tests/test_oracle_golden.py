@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import ops, nets
-from util import load_npz, state_from, opt_from, T, rel_err, grad_err
+from fsvtest import load_npz, state_from, opt_from, T, rel_err, grad_err
 
 TOL = 2e-5   # fp32 oracle vs fp32 reference: same math, different op order
 
