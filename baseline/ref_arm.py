@@ -50,8 +50,9 @@ def _create_cpu(opt):
     return m, m.optimizer_G, m.optimizer_D
 
 
-def run_gpu(wl, batch, steps, warmup, tf32=True, e2e=False):
-    """-> dict(ms_per_step, frames_per_s, ...) for the reference on cuda:0."""
+def run_gpu(wl, batch, steps, warmup, tf32=True):
+    """-> dict(ms_per_step, frames_per_s, e2e...) for the reference on cuda:0: K steps with device-resident inputs, then K steps
+    end to end (pinned host inputs copied in, every loss read back)."""
     torch.backends.cudnn.benchmark = True
     torch.backends.cudnn.allow_tf32 = bool(tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
@@ -60,26 +61,35 @@ def run_gpu(wl, batch, steps, warmup, tf32=True, e2e=False):
     host = {k: v.pin_memory() for k, v in host.items()}
     dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
     dl = refenv.data_list(dev)
+    d2h = [0]
 
     def step():
         return refenv.train_iteration(opt, model, opt_g, opt_d, dl)
 
     def step_e2e():
         d, g = refenv.train_iteration(opt, model, opt_g, opt_d, refenv.data_list(host, device='cuda'))
-        return torch.stack([x.detach().reshape(()) for x in list(d) + list(g)]).cpu()
-    fn = step_e2e if e2e else step
+        out = torch.stack([x.detach().reshape(()) for x in list(d) + list(g)]).cpu()
+        d2h[0] = out.numel() * out.element_size()
+        return out
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, out
     for _ in range(max(warmup, 3)):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        out = fn()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+        step()
+    ms, out = timed(step, steps)
+    step_e2e()
+    ms_e, _ = timed(step_e2e, steps)
     return dict(ms_per_step=ms, frames_per_s=batch / (ms / 1e3), tf32=bool(tf32), batch=batch,
-                losses=[float(x) for x in (out if e2e else list(out[0]) + list(out[1]))])
+                losses=[float(x) for x in list(out[0]) + list(out[1])],
+                e2e={'value': batch / (ms_e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': sum(v.numel() * v.element_size() for v in host.values()),
+                     'd2h_bytes_per_step': d2h[0]})
 
 
 def run_cpu(wl, batch, steps, warmup, threads):

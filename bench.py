@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- frames/sec of one full G+D forward-backward training step of the few-shot vid2vid hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fsv|reference] [--workload face256|face512|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fsv|reference|reference-gpu] [--workload pose512|...]
 
-A "step" is one reference training iteration for one frame (train.py:58-62): D-step (G forward under
-no_grad, D on [fake;real], hinge, backward, Adam) then G-step (G forward, D forward, GAN + feature
-matching + warp + mask losses, backward through D and G, Adam), flags --no_flow_gt --no_vgg_loss, single-frame
-phase, synthetic face tensors.  Prints ONE JSON line (rank 0).
+A "step" is one reference training iteration for one frame (train.py:55-62): D-step (G forward under no_grad, D [+ face D] on
+[fake;real], hinge, backward, Adam) then G-step (G forward, D forward, GAN + feature matching + warp + mask [+ pose / face]
+losses, backward through D and G, Adam); flags --no_flow_gt --no_vgg_loss (FlowNet2 / VGG19 weights are not obtainable
+offline), single-frame phase, synthetic tensors of SURVEY.md section 8(d) (baseline/synth.py).  Default workload = the
+configuration BASELINE.json's metric is quoted on: pose 512x512 --adaptive_spade --warp_ref --spade_combine --add_face_D,
+per-GPU batch 2 (config 3: global batch 16 on 8 GPUs).  Prints ONE JSON line (rank 0).
+
+  --impl fsv            this repo's sm_100a kernels (no CPU fallback)
+  --impl reference      the UNMODIFIED reference (baseline/_ref) on the host cores (reported baseline, not a target)
+  --impl reference-gpu  the UNMODIFIED reference on the GPU through its own create_model / model(data, mode) / loss_backward
+                        path (cuDNN/ATen, cudnn.benchmark=True as train.py:25; --ref-tf32 0/1): "reference PyTorch on same box"
 
   value   : whole-job frames/s with the step's inputs already resident in HBM
-  e2e     : same metric through the public API with HOST inputs: pinned-host -> device copies of every
-            input and a device -> host read of the losses inside the timed region
-  roofline: dominant kernel family of the step (conv, tensor-bound) measured with CUDA events in an
-            instrumented pass; roofline_spade: the fused SPADE kernel (HBM-bound) -- BASELINE.json names both
-  cpu_baseline / --impl reference: the CPU oracle (port of the reference's algorithm) timed on the host cores
+  e2e     : same metric through the public API with HOST inputs: pinned-host -> device copies of every input and a
+            device -> host read of the losses inside the timed region
+  roofline: the conv kernel family (tensor-bound), EXECUTED FLOPs (summed from the descriptors of the launches, 4/9 for the
+            upsample-collapsed convs, SPADE GEMMs not included) / their CUDA-event time; roofline_spade: fused SPADE (HBM-bound)
+  vs_reference_gpu / cpu_baseline: the two reference arms run as subprocesses on rank 0 at N = 1 (bounded samples)
 """
 import argparse
 import json
@@ -24,38 +31,46 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, 'few-shot-vid2vid_b200'), os.path.join(ROOT, 'tests')):
+for p in (ROOT, os.path.join(ROOT, 'few-shot-vid2vid_b200'), os.path.join(ROOT, 'baseline')):
     if p not in sys.path:
         sys.path.insert(0, p)
 
 import torch  # noqa: E402
 
+METRIC = 'frames_per_sec_full_G+D_fwd_bwd'
+FACE = dict(dataset_mode='fewshot_face', input_nc=1, label_nc=0)
+POSE = dict(dataset_mode='fewshot_pose', input_nc=6, label_nc=0, add_face_D=True)
+STREET = dict(dataset_mode='fewshot_street', input_nc=3, label_nc=20, warp_ref=False, spade_combine=False)
 WORKLOADS = {
-    # name: (H, W, per-GPU batch, option overrides)
-    'face256': dict(H=256, W=256, batch=8, opt=dict()),
-    'face512': dict(H=512, W=512, batch=2, opt=dict(fineSize=512)),
-    # temporal phase (warp_prev: second flow pass, previous-frame embedding, 3-map SPADEs).  Parity of this
-    # path is golden-tested on the GPU; this bench workload itself was added after the round-1 GPU budget was spent (not yet timed).
-    'face256t': dict(H=256, W=256, batch=8, opt=dict(), temporal=True),
-    'tiny': dict(H=64, W=64, batch=2, opt=dict(ngf=8, nff=8, ndf=8, n_downsample_G=4, n_adaptive_layers=3, n_blocks_F=2, fineSize=64)),
+    # name: geometry, per-GPU batch, conv+linear FLOPs per frame of the reference schedule 4 G + 5 D (+ 5 Df), options
+    'pose512': dict(kind='pose', H=512, W=512, batch=2, flop=1649e9, opt=dict(POSE, fineSize=512, aspect_ratio=1.0)),
+    'pose512x256': dict(kind='pose', H=512, W=256, batch=2, flop=836e9, opt=dict(POSE, fineSize=256, aspect_ratio=0.5)),
+    'face256': dict(kind='face', H=256, W=256, batch=8, flop=417e9, opt=dict(FACE, fineSize=256, aspect_ratio=1.0)),
+    'street256x512': dict(kind='street', H=256, W=512, batch=6, flop=432e9, opt=dict(STREET, fineSize=512, aspect_ratio=2.0)),
+    # temporal phase (warp_prev: second flow pass, previous-frame embedding, 3-map SPADEs, netDT)
+    'face256t': dict(kind='face', H=256, W=256, batch=8, flop=4 * 149.9e9 + 5 * 4.73e9, temporal=True, opt=dict(FACE, fineSize=256, aspect_ratio=1.0)),
+    'pose512t': dict(kind='pose', H=512, W=512, batch=2, flop=None, temporal=True, opt=dict(POSE, fineSize=512, aspect_ratio=1.0)),
+    'tiny': dict(kind='pose', H=64, W=64, batch=2, flop=None,
+                 opt=dict(POSE, ngf=8, nff=8, ndf=8, n_downsample_G=4, n_adaptive_layers=3, n_blocks_F=2, fineSize=64, aspect_ratio=1.0),
+                 ref_extra=['--ngf', '8', '--nff', '8', '--ndf', '8', '--n_downsample_G', '4', '--n_adaptive_layers', '3', '--n_blocks_F', '2']),
 }
+FLAGS = {'face': '--adaptive_spade --warp_ref --spade_combine', 'pose': '--adaptive_spade --warp_ref --spade_combine --add_face_D',
+         'street': '--adaptive_spade'}
 
-# options/base_options.py defaults + the BASELINE config flags (--adaptive_spade --warp_ref --spade_combine)
+# options/base_options.py + train_options.py defaults with the BASELINE flags (--adaptive_spade --warp_ref --spade_combine)
 BASE_OPT = dict(
     n_downsample_G=5, n_downsample_A=2, ngf=32, norm_G='spectralspadesyncbatch', conv_ks=3, embed_ks=1, spade_ks=1,
     spade_combine=True, n_sc_layers=2, add_raw_output_loss=False, adaptive_spade=True, no_adaptive_embed=False,
-    adaptive_conv=False, n_adaptive_layers=4, use_label_ref='mul', fineSize=256, aspect_ratio=1, n_fc_layers=2,
+    adaptive_conv=False, n_adaptive_layers=4, use_label_ref='mul', fineSize=256, aspect_ratio=1.0, n_fc_layers=2,
     label_nc=0, input_nc=1, output_nc=3, res_for_ref=False, netS='encoderdecoder', n_shot=1, lambda_kld=0.0,
     warp_ref=True, for_face=False, sc_arch='unet', norm_F='spectralsyncbatch', nff=32, n_blocks_F=6, n_downsample_F=3,
     flow_multiplier=20, isTrain=True, gpu_ids=[0], print_G=False, print_D=False, init_type='xavier', init_variance=0.02,
-    netG='fewshot', n_frames_G=2, sep_flow_prev=False, no_sep_warp_embed=False, which_model_netD='multiscale',
-    adaptive_D_layers=1, ndf=32, n_layers_D=4, num_D=1, norm_D='spectralinstance', netD_subarch='n_layers',
-    gan_mode='hinge', lambda_feat=10.0, lambda_flow=10.0, lambda_mask=10.0, lambda_vgg=10.0, lambda_temp=0.0,
-    no_ganFeat_loss=False, no_vgg_loss=True, no_flow_gt=True, dataset_mode='fewshot_face', add_face_D=False,
+    netG='fewshot', n_frames_G=2, n_frames_D=2, n_frames_per_gpu=1, sep_flow_prev=False, no_sep_warp_embed=False,
+    which_model_netD='multiscale', adaptive_D_layers=1, ndf=32, n_layers_D=4, num_D=1, norm_D='spectralinstance',
+    netD_subarch='n_layers', gan_mode='hinge', lambda_feat=10.0, lambda_flow=10.0, lambda_mask=10.0, lambda_vgg=10.0,
+    lambda_temp=0.0, lambda_face=10.0, no_ganFeat_loss=False, no_vgg_loss=True, no_flow_gt=True, dataset_mode='fewshot_face',
+    add_face_D=False, pose_type='both', remove_face_labels=False, basic_point_only=False, refine_face=False, finetune=False,
     lr=0.0004, beta1=0.5, beta2=0.999, no_TTUR=False)
-
-# forward MACs per frame at face 256x256 from BASELINE.md section 2 (G 49.21 GMAC, D pair 2.37 GMAC); step = 4 G + 5 D
-FLOP_PER_FRAME = {'face256': 417e9, 'face512': 1645e9, 'face256t': 4 * 149.9e9 + 5 * 4.73e9}
 
 
 def make_opt(workload):
@@ -65,24 +80,16 @@ def make_opt(workload):
     return Namespace(**o)
 
 
-def synth_inputs(workload, batch, seed, device='cpu', pin=False):
-    """SURVEY.md section 8(d) face inputs: 1-channel edge maps in {0,1} (Bernoulli 0.03, 3x3 dilated), images U(-1,1)."""
+def describe(workload):
     wl = WORKLOADS[workload]
-    H, W = wl['H'], wl['W']
-    g = torch.Generator().manual_seed(seed)
+    return '%s %s %dx%d %s --no_flow_gt --no_vgg_loss%s' % (workload, wl['kind'], wl['H'], wl['W'], FLAGS[wl['kind']],
+                                                            ' (temporal phase)' if wl.get('temporal') else '')
 
-    def edges(*shape):
-        e = (torch.rand(*shape, generator=g) < 0.03).float()
-        return torch.nn.functional.max_pool2d(e.view(-1, 1, H, W), 3, 1, 1).view(*shape)
-    t = dict(tgt_label=edges(batch, 1, H, W), tgt_image=torch.rand(batch, 3, H, W, generator=g) * 2 - 1,
-             ref_labels=edges(batch, 1, 1, H, W), ref_images=torch.rand(batch, 1, 3, H, W, generator=g) * 2 - 1)
-    if wl.get('temporal'):
-        t.update(prev_label=edges(batch, 1, H, W), prev_image=torch.rand(batch, 3, H, W, generator=g) * 2 - 1)
-    if pin and torch.cuda.is_available():
-        t = {k: v.pin_memory() for k, v in t.items()}
-    if device != 'cpu':
-        t = {k: v.to(device) for k, v in t.items()}
-    return t
+
+def synth_inputs(workload, batch, seed):
+    import synth
+    wl = WORKLOADS[workload]
+    return synth.make(wl['kind'], batch, wl['H'], wl['W'], seed=seed, K=wl.get('K', 1), temporal=bool(wl.get('temporal')))
 
 
 class ClockSampler:
@@ -137,72 +144,80 @@ def load_peaks():
     return dict(hbm=6650.0, tflops=1400.0, src='fallback (B200_PROFILING.md)')
 
 
-# ----------------------------------------------------------------------------------------------------- CPU arm
-def cpu_step_time(workload, batch, threads, steps=1, warmup=0):
-    """One reference-schedule step (D-step + G-step forward/backward, no optimiser) of the CPU oracle."""
-    from oracle import nets as ON
-    torch.set_num_threads(threads)
-    opt = make_opt(workload)
-    opt.gpu_ids = []
-    from fsv import networks
-    torch.manual_seed(0)
-    g_cpu = networks.define_G(opt)
-    if WORKLOADS[workload].get('temporal'):
-        g_cpu.init_temporal_network()
-    sdG = {k: v.detach().clone() for k, v in g_cpu.state_dict().items()}
-    sdD = {k: v.detach().clone() for k, v in
-           networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, opt.num_D, True, gpu_ids=[]).state_dict().items()}
-    for sd in (sdG, sdD):
-        for k, v in sd.items():
-            if v.is_floating_point() and not k.endswith(('running_mean', 'running_var', 'weight_u', 'weight_v')):
-                v.requires_grad_(True)
-    inp = synth_inputs(workload, batch, seed=1234)
-    temporal = bool(WORKLOADS[workload].get('temporal'))
-    prev = (inp['prev_label'], inp['prev_image']) if temporal else (None, None)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            fake = ON.generator_forward(sdG, opt, inp['tgt_label'], inp['ref_labels'], inp['ref_images'], prev=prev, training=True,
-                                        temporal=temporal)[0]
-        dl = ON.discriminator_losses(sdD, inp['tgt_label'], fake, inp['tgt_image'], inp['ref_labels'][:, 0], inp['ref_images'][:, 0],
-                                     opt.n_layers_D, opt.num_D)
-        sum(v.sum() for v in dl.values()).backward()
-        gl, _ = ON.generator_losses(sdG, sdD, opt, inp['tgt_label'], inp['tgt_image'], inp['ref_labels'], inp['ref_images'],
-                                    opt.n_layers_D, opt.num_D, prev=prev if temporal else None)
-        sum(v.sum() for v in gl.values()).backward()
-        for sd in (sdG, sdD):
-            for v in sd.values():
-                v.grad = None
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+def host_threads():
+    return min(os.cpu_count() or 1, 32)   # more threads than this slows the small per-layer CPU convs down
+
+
+# ----------------------------------------------------------------------------------------------------- reference arms
+def base_line(args, wl, value, ms, dtype, batch, extra_cfg=None):
+    cfg = {'workload': describe(args.workload), 'per_gpu_batch': batch}
+    cfg.update(extra_cfg or {})
+    return {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic', 'config': cfg}
 
 
 def run_reference(args):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
+    """The unmodified reference on the host cores (rank 0 only).  Bounded sample: batch 1, 1 warm-up + K <= 3 steps."""
+    if int(os.environ.get('RANK', '0')) != 0:
         return
-    threads = min(os.cpu_count() or 1, 32)   # more threads than this slows the small per-layer CPU convs down
-    sample_batch = 1
-    t = cpu_step_time(args.workload, sample_batch, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
-    v = sample_batch / t
+    import refenv
+    if not refenv.available():
+        emit(json.dumps({'impl': 'reference', 'unavailable': 'baseline/_ref is missing (python baseline/install_reference.py needs /root/reference)'}))
+        return
+    import ref_arm
     wl = WORKLOADS[args.workload]
-    line = {'impl': 'reference', 'metric': 'frames_per_sec_full_G+D_fwd_bwd', 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': '%s %dx%d --adaptive_spade --warp_ref --spade_combine --no_flow_gt --no_vgg_loss' % (args.workload, wl['H'], wl['W']),
-                       'per_gpu_batch': wl['batch'], 'sample_batch': sample_batch},
-            'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                             'sample': 'CPU oracle (torch-CPU port of the reference), one D-step+G-step fwd/bwd at batch %d, no optimiser' % sample_batch},
-            'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    threads, sample_batch, steps = host_threads(), 1, max(1, min(args.steps, 3))
+    r = ref_arm.run_cpu(wl, sample_batch, steps, 1, threads)
+    sample = 'unmodified reference (baseline/_ref, .cuda() as a no-op) train.py:55-62 iteration incl. Adam, batch %d, 1 warm-up + %d steps' % (sample_batch, steps)
+    line = base_line(args, wl, r['frames_per_s'], r['ms_per_step'], 'fp32', wl['batch'], {'sample_batch': sample_batch})
+    line.update({'impl': 'reference', 'steps': steps, 'warmup': 1,
+                 'cpu_baseline': {'value': r['frames_per_s'], 'unit': 'frames/s', 'cores': threads, 'kind': 'reference', 'sample': sample},
+                 'e2e': {'value': r['frames_per_s'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
     emit(json.dumps(line))
 
 
-# ----------------------------------------------------------------------------------------------------- GPU arm
+def run_reference_gpu(args):
+    """The unmodified reference on cuda:0 (rank 0 only; one GPU: the reference's multi-GPU path is single-process DataParallel)."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    import refenv
+    if not refenv.available():
+        emit(json.dumps({'impl': 'reference-gpu', 'unavailable': 'baseline/_ref is missing'}))
+        return
+    import ref_arm
+    wl = WORKLOADS[args.workload]
+    batch = wl['batch'] if args.batch is None else args.batch
+    r = ref_arm.run_gpu(wl, batch, args.steps, args.warmup, tf32=bool(args.ref_tf32))
+    line = base_line(args, wl, r['frames_per_s'], r['ms_per_step'], 'tf32' if args.ref_tf32 else 'fp32', batch,
+                     {'cudnn_benchmark': True, 'allow_tf32': bool(args.ref_tf32)})
+    line.update({'impl': 'reference-gpu', 'n_gpus': 1, 'losses': r['losses'], 'e2e': r['e2e']})
+    emit(json.dumps(line))
+
+
+def sub_arm(args, impl, extra, timeout):
+    """Run another arm of this script in a fresh process (so that it cannot share state with the fsv arm) and parse its line."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', impl, '--workload', args.workload] + extra
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT')}
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        lines = [l for l in p.stdout.splitlines() if l.startswith('{')]
+        return json.loads(lines[-1]) if lines else {'error': (p.stderr or 'no output')[-400:]}
+    except Exception as e:   # the baseline arms are context: their failure must not take the bench line down
+        return {'error': str(e)[:400]}
+
+
+# ----------------------------------------------------------------------------------------------------- fsv arm
+def conv_flops(fn_name, cd):
+    """FLOPs a conv-family C-ABI call executes (2 * MACs), from its descriptor."""
+    macs = float(cd.N) * cd.Ho * cd.Wo * cd.kh * cd.kw * cd.Cin * cd.Cout
+    if fn_name == 'fsv_conv2d_fwd_tc_up2':
+        macs *= 4.0 / 9.0            # four 2x2-tap parity convs at source resolution instead of 3x3 at the upsampled one
+    return 2.0 * macs
+
+
 def run_fsv(args):
     import torch.distributed as dist
-    from fsv import networks, ops, parallel, trainer
+    from fsv import ops, parallel, trainer, model
     rank, world, local_rank = parallel.init_from_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -212,34 +227,33 @@ def run_fsv(args):
     opt = make_opt(args.workload)
     opt.gpu_ids = [local_rank]
     torch.manual_seed(0)
-    netG = networks.define_G(opt)
+    step = model.Vid2VidStep(opt)
     if wl.get('temporal'):
-        netG.init_temporal_network()
-    netD = networks.define_D(opt, 8, opt.ndf, opt.n_layers_D, opt.norm_D, opt.netD_subarch, opt.num_D, True, gpu_ids=[local_rank])
-    netG.train(), netD.train()
-    parallel.broadcast_state(netG), parallel.broadcast_state(netD)
+        step.init_temporal_model()
+    mods = [step.netG] + step.d_modules()
+    for m in mods:
+        m.train()
+        parallel.broadcast_state(m)
     use_graph = args.graph          # NCCL collectives are capturable too (one graph per rank, replayed in lock-step)
-    optG, optD = trainer.make_optimizers(opt, netG, netD, capturable=use_graph)
-    syncG = parallel.GradSync(netG.parameters()) if world > 1 else None
-    syncD = parallel.GradSync(netD.parameters()) if world > 1 else None
-    host = synth_inputs(args.workload, batch, seed=1234 + rank, pin=True)
+    optG, optD = trainer.make_step_optimizers(opt, step, capturable=use_graph)
+    syncG = parallel.GradSync(step.netG.parameters()) if world > 1 else None
+    syncD = parallel.GradSync(step.d_parameters()) if world > 1 else None
+    host = {k: v.pin_memory() for k, v in synth_inputs(args.workload, batch, seed=1234 + rank).items()}
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
     def eager_step(inp):
-        prev = [inp['prev_label'], inp['prev_image']] if 'prev_label' in inp else None
-        return trainer.train_step(opt, netG, netD, optG, optD, inp['tgt_label'], inp['tgt_image'], inp['ref_labels'], inp['ref_images'],
-                                  sync_G=syncG, sync_D=syncD, prev=prev)
-    step = eager_step
+        return trainer.train_iteration(step, optG, optD, inp, sync_G=syncG, sync_D=syncD)
+    run = eager_step
     n_eager0 = ops.LAUNCHES[0]
     eager_step(devin)
     launches_per_step = ops.LAUNCHES[0] - n_eager0
     graph_note = None
     if use_graph:
         try:
-            step = trainer.GraphedStep(opt, netG, netD, optG, optD, devin, sync_G=syncG, sync_D=syncD)
+            run = trainer.GraphedStep(step, optG, optD, devin, sync_G=syncG, sync_D=syncD)
         except Exception as e:      # capture is an optimisation of the launch path only; the eager path runs the same kernels
-            graph_note = 'capture failed, eager launches used: %s' % str(e)[:200]
+            graph_note = 'capture failed, eager launches used: %s' % str(e)[:300]
             use_graph = False
             torch.cuda.synchronize()
 
@@ -265,35 +279,34 @@ def run_fsv(args):
         return ms
 
     for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
-        step(devin)
+        run(devin)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    n0 = ops.LAUNCHES[0]
-    ms = timed(lambda: step(devin), args.steps)
-    launches = launches_per_step      # C-ABI kernel-launching calls per step (counted on an eager step; a graph replays the same launches)
+    ms = timed(lambda: run(devin), args.steps)
     clk = clocks.stop() if rank == 0 else None
-
     if args.quick:
         if rank == 0:
-            emit(json.dumps({'quick': True, 'ms_per_step': ms / args.steps, 'note': 'profiling aid, not a bench value'}))
+            emit(json.dumps({'quick': True, 'ms_per_step': ms / args.steps, 'launches': launches_per_step, 'graph_note': graph_note,
+                             'note': 'profiling aid, not a bench value'}))
         return
-    # e2e: host inputs (pinned) -> device every step, losses read back to the host every step
+
+    # e2e: host inputs (pinned) -> device every step, every loss of the iteration read back to the host every step
     d2h = [0]
 
     def e2e_step():
         inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        ld, lg, _ = step(inp)
-        out = torch.stack([ld.detach(), lg.detach()]).cpu()
+        dl, gl, _, _ = run(inp)
+        out = torch.stack([v.detach().reshape(()) for v in list(dl.values()) + list(gl.values())]).cpu()
         d2h[0] = out.numel() * out.element_size()
+        return out
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    losses = e2e_step().tolist()
 
     # instrumented pass: CUDA-event time per C-ABI kernel family (every rank runs the steps -- they contain the gradient
     # all-reduce -- but only rank 0 records events)
-    prof = {}
-    detail = {}
-    spade_bytes = 0.0
+    prof, detail, acc = {}, {}, dict(spade_bytes=0.0, conv_flops=0.0)
     psteps = 2
     if rank == 0:
         real_call = ops._call
@@ -306,11 +319,11 @@ def run_fsv(args):
             real_call(fn, *a)
             e.record()
             key = fn.__name__
-            if key.startswith('fsv_conv2d') and key != 'fsv_conv2d_tc_eligible':
+            if key.startswith('fsv_conv2d'):
                 cd = a[0]._obj
-                key += ' %dx%d %d->%d k%d s%d up%d%s%s' % (cd.H, cd.W, cd.Cin, cd.Cout, cd.kh, cd.stride, cd.up,
-                                                          ' persample' if cd.w_nstride else '', ' TC' if (cd.use_tc != 0 and lib.fsv_conv2d_tc_eligible(a[0])) else '')
-            detail.setdefault(key, [0.0, 0])
+                key += ' %dx%d %d->%d k%d s%d up%d%s%s' % (cd.H, cd.W, cd.Cin, cd.Cout, cd.kh, cd.stride, cd.up, ' persample' if cd.w_nstride else '',
+                                                          ' TC' if (cd.use_tc != 0 and lib.fsv_conv2d_tc_eligible(a[0])) else '')
+                acc['conv_flops'] += conv_flops(fn.__name__, cd) / psteps
             pending.append((fn.__name__, a, s, e, key))
         ops._call = prof_call
     for _ in range(psteps):
@@ -319,18 +332,19 @@ def run_fsv(args):
     if rank == 0:
         ops._call = real_call
         for name, a, s, e, key in pending:
+            t = s.elapsed_time(e) / psteps
             d = prof.setdefault(name, [0.0, 0])
-            d[0] += s.elapsed_time(e) / psteps
+            d[0] += t
             d[1] += 1.0 / psteps
-            detail[key][0] += s.elapsed_time(e) / psteps
-            detail[key][1] += 1.0 / psteps
+            dd = detail.setdefault(key, [0.0, 0])
+            dd[0] += t
+            dd[1] += 1.0 / psteps
             if name in ('fsv_spade_fwd', 'fsv_spade_fwd_tc'):
                 sd = a[0]._obj
                 px = sd.N * sd.H * sd.W
-                spade_bytes += 4.0 * (px * sd.C / (sd.up * sd.up) + sum(px * sd.K[i] for i in range(sd.nmaps)) + px * sd.C) / psteps
+                acc['spade_bytes'] += 4.0 * (px * sd.C / (sd.up * sd.up) + sum(px * sd.K[i] for i in range(sd.nmaps)) + px * sd.C) / psteps
     if world > 1:
         dist.barrier()
-
     if rank != 0:
         return
     if args.breakdown:
@@ -341,40 +355,40 @@ def run_fsv(args):
     t_step = ms / args.steps / 1e3
     gbatch = batch * world
     value = gbatch / t_step
-    flop = FLOP_PER_FRAME.get(args.workload)
     conv_ms = sum(v[0] for k, v in prof.items() if k.startswith('fsv_conv2d'))
     total_ms = sum(v[0] for v in prof.values())
-    roof = None
-    if flop:
-        conv_flops = flop * batch      # conv/linear FLOPs of one step on this rank
-        ach = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-        roof = {'bound': 'tensor', 'kernel': 'fsv_conv2d_{fwd,dgrad,wgrad} (all launches of one step)', 'achieved': ach,
-                'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
-                'traffic_note': 'aggregate over launches of many shapes, so no single per-launch figure; one captured launch '
-                                '(profiles/ncu_full_r1_summary.txt, k_conv_tc grid 256): 33.9 MB DRAM read+write vs 34.2 MB algorithmic (x + y + w)',
-                'peak_source': peaks['src'] + ', dense bf16 sustained', 'share_of_step_kernel_time': conv_ms / total_ms if total_ms else None}
+    ach = acc['conv_flops'] / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    roof = {'bound': 'tensor', 'kernel': 'fsv_conv2d_{fwd,dgrad,wgrad}* (all launches of one step)', 'achieved': ach, 'peak': peaks['tflops'],
+            'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
+            'flops_executed_per_step': acc['conv_flops'], 'family_ms_per_step_eager': conv_ms,
+            'note': 'executed FLOPs summed from the launch descriptors (4/9 for upsample-collapsed convs; SPADE gamma/beta GEMMs excluded), '
+                    'time = CUDA events around each launch in an eager pass; traffic: aggregate over many shapes, per-launch dram bytes are in profiles/',
+            'peak_source': peaks['src'] + ', dense bf16 sustained', 'share_of_step_kernel_time': conv_ms / total_ms if total_ms else None}
+    if wl.get('flop'):
+        roof['whole_step'] = {'achieved': value / world * wl['flop'] / 1e12, 'frac': value / world * wl['flop'] / 1e12 / peaks['tflops'],
+                              'flop_per_frame_reference_schedule': wl['flop']}
     sp_ms = sum(prof[k][0] for k in ('fsv_spade_fwd', 'fsv_spade_fwd_tc') if k in prof)
-    sp = [sp_ms]
     roof_spade = None
     if sp_ms > 0:
-        ach = spade_bytes / (sp[0] / 1e3) / 1e9
-        roof_spade = {'bound': 'hbm', 'kernel': 'fsv_spade_fwd[_tc] (all launches of one step)', 'achieved': ach, 'peak': peaks['hbm'],
-                      'unit': 'GB/s', 'frac': ach / peaks['hbm'], 'traffic': None, 'peak_source': peaks['src']}
-    line = {'metric': 'frames_per_sec_full_G+D_fwd_bwd', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'fp32' if ops.CONV_USE_TC == 0 else 'tf32', 'data': 'synthetic',
-            'config': {'workload': '%s %dx%d --adaptive_spade --warp_ref --spade_combine --no_flow_gt --no_vgg_loss' % (args.workload, wl['H'], wl['W']),
-                       'per_gpu_batch': batch, 'global_batch': gbatch, 'parallelism': 'dp%d' % world, 'cuda_graph': bool(use_graph), 'cuda_graph_note': graph_note,
-                       'l2': 'per-step working set (activations of a %d-frame batch) is far larger than the 126 MB L2' % batch},
-            'clocks': clk, 'gpu_launches': int(launches),
-            'e2e': {'value': gbatch / (ms_e2e / args.steps / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h[0]},
-            'roofline': roof, 'roofline_spade': roof_spade,
-            'kernel_ms_per_step': {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
-    if world == 1 and not args.no_cpu_baseline:
-        threads = min(os.cpu_count() or 1, 32)
-        t_cpu = cpu_step_time(args.workload, 1, threads)
-        line['cpu_baseline'] = {'value': 1.0 / t_cpu, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                                'sample': 'CPU oracle (torch-CPU port of the reference), one D-step+G-step fwd/bwd at batch 1, no optimiser'}
+        a = acc['spade_bytes'] / (sp_ms / 1e3) / 1e9
+        roof_spade = {'bound': 'hbm', 'kernel': 'fsv_spade_fwd[_tc] (all launches of one step)', 'achieved': a, 'peak': peaks['hbm'],
+                      'unit': 'GB/s', 'frac': a / peaks['hbm'], 'traffic': None, 'peak_source': peaks['src']}
+    line = base_line(args, wl, value, t_step * 1e3, 'fp32' if ops.CONV_USE_TC == 0 else 'tf32', batch,
+                     {'global_batch': gbatch, 'parallelism': 'dp%d' % world, 'cuda_graph': bool(use_graph), 'cuda_graph_note': graph_note,
+                      'l2': 'per-step working set (activations of %d %dx%d frames) is far larger than the 126 MB L2' % (batch, wl['H'], wl['W'])})
+    line.update({'n_gpus': world, 'warmup': max(args.warmup, 3), 'clocks': clk, 'gpu_launches': int(launches_per_step),
+                 'e2e': {'value': gbatch / (ms_e2e / args.steps / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h[0]},
+                 'roofline': roof, 'roofline_spade': roof_spade, 'losses': dict(zip(trainer.LOSS_NAMES_D[:4] + trainer.LOSS_NAMES_G, losses)) if len(losses) == 14 else losses,
+                 'kernel_ms_per_step': {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}})
+    if world == 1 and not args.no_baselines:
+        torch.cuda.empty_cache()
+        rg = sub_arm(args, 'reference-gpu', ['--steps', str(min(args.steps, 10)), '--warmup', '3', '--ref-tf32', '1'] + (['--batch', str(batch)]), 600)
+        line['reference_gpu'] = {k: rg.get(k) for k in ('value', 'ms_per_step', 'dtype', 'config', 'error', 'unavailable') if k in rg}
+        if rg.get('value'):
+            line['vs_reference_gpu'] = {'value_ratio': value / rg['value'], 'e2e_ratio': line['e2e']['value'] / rg['value'],
+                                        'note': 'this arm / unmodified reference on the same GPU (cuDNN TF32, cudnn.benchmark), same workload and batch'}
+        rc = sub_arm(args, 'reference', ['--steps', '2'], 900)
+        line['cpu_baseline'] = rc.get('cpu_baseline', {'error': rc.get('error', rc.get('unavailable'))})
     emit(json.dumps(line))
 
 
@@ -404,18 +418,24 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='fsv', choices=['fsv', 'reference'])
-    ap.add_argument('--workload', default='face256', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='fsv', choices=['fsv', 'reference', 'reference-gpu'])
+    ap.add_argument('--workload', default='pose512', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the workload\'s)')
     ap.add_argument('--simt', action='store_true', help='force the exact-fp32 SIMT conv path')
-    ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
-    ap.add_argument('--graph', dest='graph', action='store_true', default=True, help='replay the step from a CUDA graph (default, single GPU)')
+    ap.add_argument('--ref-tf32', dest='ref_tf32', type=int, default=1, help='reference-gpu arm: torch.backends.{cudnn,cuda.matmul}.allow_tf32')
+    ap.add_argument('--no-baselines', '--no-cpu-baseline', dest='no_baselines', action='store_true', help='skip the reference sub-arms (GPU + CPU)')
+    ap.add_argument('--graph', dest='graph', action='store_true', default=True, help='replay the step from a CUDA graph (default)')
     ap.add_argument('--no-graph', dest='graph', action='store_false')
-    ap.add_argument('--quick', action='store_true', help='profiling aid: W warm-up + K timed steps only (no e2e / instrumented / CPU passes); not a bench result')
+    ap.add_argument('--quick', action='store_true', help='profiling aid: W warm-up + K timed steps only (no e2e / instrumented / baseline passes); not a bench result')
     ap.add_argument('--breakdown', default=None, help='write a per-kernel/per-shape time breakdown of one step to this file')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+        return
+    if args.impl == 'reference-gpu':
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: --impl reference-gpu needs a CUDA device')
+        run_reference_gpu(args)
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: the fsv arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')

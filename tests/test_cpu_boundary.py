@@ -120,8 +120,9 @@ def test_product_never_imports_the_oracle():
 
 
 def test_bench_reference_arm_prints_one_json_line():
-    """bench.py --impl reference (the CPU arm: the oracle port on host threads) keeps the driver's output contract: exactly
-    one JSON line on stdout with the metric keys; the fsv arm refuses to run without a CUDA device (no CPU fallback)."""
+    """bench.py --impl reference (the CPU arm: the unmodified reference from baseline/_ref on host threads) keeps the driver's
+    output contract: exactly one JSON line on stdout with the metric keys, and it must not load this repo's product;
+    the fsv arm refuses to run without a CUDA device (no CPU fallback)."""
     import json
     import subprocess
     import sys
@@ -132,12 +133,37 @@ def test_bench_reference_arm_prints_one_json_line():
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+    for k in ('impl',) if 'unavailable' in d else ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
               'dtype', 'data', 'config', 'e2e', 'cpu_baseline'):
         assert k in d, k
-    assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port'
+    if 'unavailable' in d:
+        assert not os.path.isdir(os.path.join(root, 'baseline', '_ref'))
+        return
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'reference'
+    src = open(os.path.join(root, 'baseline', 'ref_arm.py')).read() + open(os.path.join(root, 'baseline', 'refenv.py')).read()
+    assert 'import fsv' not in src and 'from fsv' not in src and 'import oracle' not in src
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     if not torch.cuda.is_available():
         r2 = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1', '--warmup', '0'],
                             capture_output=True, text=True, timeout=600)
         assert r2.returncode != 0 and 'no CPU fallback' in (r2.stderr + r2.stdout)
+
+
+def test_bench_options_equal_the_reference_parser():
+    """bench.make_opt (the fsv arm builds its options without the reference installed) must agree with what the reference's own
+    option parser produces for the same flags (the reference arms use that parser) on every field both define."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, 'baseline'))
+    import refenv
+    if not refenv.available():
+        import pytest
+        pytest.skip('reference not installed')
+    import bench
+    for name, wl in bench.WORKLOADS.items():
+        mine = vars(bench.make_opt(name))
+        ref = vars(refenv.parse_opt(wl['kind'], wl['H'], wl['W'], wl['batch'], extra=wl.get('ref_extra', []), gpu=False))
+        for k, v in mine.items():
+            if k in ref and k not in ('gpu_ids', 'for_face'):
+                assert ref[k] == v, (name, k, ref[k], v)

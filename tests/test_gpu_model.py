@@ -1,0 +1,100 @@
+"""GPU parity of the pose / face-region kernels (vs the oracle restatements, bit-exact: masks and boxes are integer work) and of
+fsv.model.Vid2VidStep -- the sync-free training step the bench times -- against the UNMODIFIED reference model
+(baseline/_ref: Vid2VidModel + LossCollector + FaceRefineModel on cuDNN/ATen, TF32 off) on the same GPU, weights and batch."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+import refenv   # noqa: E402
+import synth    # noqa: E402
+from oracle import ops as OO   # noqa: E402  (checker only)
+from fsvtest import rel_err, l2_err   # noqa: E402
+
+pytestmark = pytest.mark.gpu
+HAVE_REF = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'models'))
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason='baseline/_ref missing: run `python baseline/install_reference.py` in the build container')
+
+
+@pytest.mark.parametrize('H,W', [(64, 64), (96, 40), (256, 256)])
+def test_pose_masks_bit_exact(H, W):
+    from fsv import ops
+    lab = synth.make('pose', 3, H, W, seed=H + W)['tgt_label'][:, 0]
+    lab[1, 2] = torch.rand(H, W) * 2 - 1                                     # arbitrary part values too (ids off the 1/24 grid)
+    g = lab.cuda()
+    assert torch.equal(ops.fg_mask(g).cpu(), OO.fg_mask(lab))
+    assert torch.equal(ops.part_masks(g).cpu(), OO.part_masks(lab[:, 2]).permute(0, 2, 3, 1))
+    assert torch.equal(ops.face_mask_avg15(g).cpu(), OO.face_mask_avg15(lab[:, 2]))
+
+
+@pytest.mark.parametrize('openpose', [True, False])
+def test_face_box_and_crop_vs_oracle(openpose):
+    from fsv import ops
+    H, W, S = 128, 96, 32
+    b = synth.make('pose', 4, H, W, seed=5)
+    lab = b['tgt_label'][:, 0]
+    lab[3, 3:] = -1.0                                                        # one sample without any face pixel -> fallback box
+    lab[3, 2] = -1.0
+    face = OO.face_pixels(lab, openpose)
+    boxes = [OO.face_region(face[i], H, W, openpose) for i in range(4)]
+    g = lab.cuda()
+    planes = [(g, -3), (g, -2), (g, -1)] if openpose else [(g, 2)]
+    box = ops.face_bbox(planes, 0.0 if openpose else 0.9, openpose)
+    assert box.cpu().tolist() == [list(x) for x in boxes]
+    img = b['tgt_image'][:, 0].clone().requires_grad_(True)
+    ref = OO.crop_face_region(img, boxes, S)
+    r = torch.randn(ref.shape)
+    (ref * r).sum().backward()
+    # both an NCHW tensor and an NCHW-shaped view of an NHWC buffer
+    for src in (img.detach().cuda().requires_grad_(True), img.detach().cuda().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)):
+        out = ops.crop_resize(src, box, S)
+        assert torch.equal(out.permute(0, 3, 1, 2).cpu(), ref.detach())
+        (out.permute(0, 3, 1, 2) * r.cuda()).sum().backward()
+        assert rel_err(src.grad, img.grad) < 1e-6
+
+
+CASES = [('pose', 128, 128, [], 0, 1e-3), ('pose', 256, 256, [], -1, 5e-3), ('pose', 128, 64, ['--remove_face_labels'], 0, 1e-3),
+         ('street', 64, 128, [], 0, 1e-3), ('face', 128, 128, [], 0, 1e-3)]
+
+
+@needs_ref
+@pytest.mark.parametrize('kind,H,W,extra,use_tc,tol', CASES)
+def test_step_matches_reference_model_on_gpu(kind, H, W, extra, use_tc, tol):
+    from fsv import ops, model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    opt = refenv.parse_opt(kind, H, W, 2, extra=list(extra), gpu=True)
+    ref, _, _ = refenv.create_model(opt)
+    ref = ref.module
+    old = ops.CONV_USE_TC
+    ops.CONV_USE_TC = use_tc
+    try:
+        step = model.Vid2VidStep(opt)
+        for a, b in ((ref.netG, step.netG), (ref.netD, step.netD), (getattr(ref, 'netDf', None), step.netDf)):
+            assert (a is None) == (b is None)
+            if a is not None:
+                b.load_state_dict(a.state_dict())
+                b.train()
+        batch = {k: v.cuda() for k, v in synth.make(kind, 2, H, W, seed=21).items()}
+        dl = refenv.data_list(batch)
+        d0 = ref(dl, mode='discriminator')
+        d1 = step.discriminator_losses(batch)
+        for (n, b), a in zip(d1.items(), d0):
+            assert abs(float(a) - float(b)) < tol * max(1.0, abs(float(a))), ('D', n, float(a), float(b))
+        g0, gen0, _ = ref(dl, save_images=True, mode='generator')
+        g1, fake, _ = step.generator_losses(batch)
+        assert rel_err(fake, gen0[0][:, 0] if gen0[0].dim() == 5 else gen0[0]) < tol
+        for (n, b), a in zip(g1.items(), g0):
+            assert abs(float(a) - float(b)) < tol * max(1.0, abs(float(a))), ('G', n, [float(x) for x in g0], [float(x) for x in g1.values()])
+        sum(v.mean() for v in g1.values()).backward()
+        sum(v.mean() for v in g0).backward()
+        worst = 0.0
+        for (n, p0), (_, p1) in zip(ref.netG.named_parameters(), step.netG.named_parameters()):
+            if p0.grad is not None and float(p0.grad.abs().max()) > 1e-6 and 'weight' in n and p0.dim() > 1:
+                worst = max(worst, l2_err(p1.grad, p0.grad))
+        assert worst < (1e-2 if use_tc == 0 else 3e-2), worst
+    finally:
+        ops.CONV_USE_TC = old
