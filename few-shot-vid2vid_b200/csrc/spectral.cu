@@ -50,12 +50,13 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket, unsigned int nb
 
 // phase 1: t = W^T u.  Grid (column chunks, row splits); the last row-split block of each column chunk (one ticket per
 // chunk) folds that chunk's partials in a fixed order into t (kept in split 0's slot) and leaves the chunk's |t|^2.
-__global__ void __launch_bounds__(SN_THREADS) k_sn_wtu(const float* __restrict__ W, const float* __restrict__ u, int R, int K,
-                                                       int rows_per_split, float* part, float* __restrict__ nrm_part) {
+__device__ __forceinline__ void sn_wtu_body(const float* __restrict__ W, const float* __restrict__ u, int R, int K, int rows_per_split,
+                                            float* part, float* __restrict__ nrm_part, int chunk, int split, int nsplits,
+                                            unsigned int* ticket) {
     __shared__ float sh[SN_THREADS / 32];
     __shared__ int flag;
-    int c = blockIdx.x * SN_THREADS + threadIdx.x;
-    int r0 = blockIdx.y * rows_per_split, r1 = min(R, r0 + rows_per_split);
+    int c = chunk * SN_THREADS + threadIdx.x;
+    int r0 = split * rows_per_split, r1 = min(R, r0 + rows_per_split);
     if (c < K) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int r = r0;
@@ -66,24 +67,28 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_wtu(const float* __restrict__
             a3 = fmaf(W[(size_t)(r + 3) * K + c], u[r + 3], a3);
         }
         for (; r < r1; ++r) a0 = fmaf(W[(size_t)r * K + c], u[r], a0);
-        part[(size_t)blockIdx.y * K + c] = (a0 + a1) + (a2 + a3);
+        part[(size_t)split * K + c] = (a0 + a1) + (a2 + a3);
     }
-    if (!last_block(&g_sn_colticket[blockIdx.x], gridDim.y, &flag)) return;
+    if (!last_block(ticket, nsplits, &flag)) return;
     const volatile float* vp = part;
     float t = 0.f;
     if (c < K) {
-        for (int s = 0; s < (int)gridDim.y; ++s) t += vp[(size_t)s * K + c];
+        for (int s = 0; s < nsplits; ++s) t += vp[(size_t)s * K + c];
         part[c] = t;
     }
     float nrm = block_sum(t * t, sh);
-    if (threadIdx.x == 0) nrm_part[blockIdx.x] = nrm;
+    if (threadIdx.x == 0) nrm_part[chunk] = nrm;
+}
+__global__ void __launch_bounds__(SN_THREADS) k_sn_wtu(const float* __restrict__ W, const float* __restrict__ u, int R, int K,
+                                                       int rows_per_split, float* part, float* __restrict__ nrm_part) {
+    sn_wtu_body(W, u, R, K, rows_per_split, part, nrm_part, blockIdx.x, blockIdx.y, gridDim.y, &g_sn_colticket[blockIdx.x]);
 }
 
 // phase 2: v = t / max(|t|, eps) (training), s = W v (warp per row); last block: sigma, u
-__global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ W, const float* __restrict__ t, const float* __restrict__ nrm_part,
-                                                      int nchunks, int R, int K, int power, float eps, float* s, float* u_buf,
-                                                      float* __restrict__ u_save, float* __restrict__ v_buf, float* __restrict__ v_save,
-                                                      float* __restrict__ sigma) {
+__device__ __forceinline__ void sn_wv_body(const float* __restrict__ W, const float* __restrict__ t, const float* __restrict__ nrm_part,
+                                           int nchunks, int R, int K, int power, float eps, float* s, float* u_buf,
+                                           float* __restrict__ u_save, float* __restrict__ v_buf, float* __restrict__ v_save,
+                                           float* __restrict__ sigma, int blk, int nblk, unsigned int* ticket) {
     __shared__ float sh[SN_THREADS / 32];
     __shared__ int flag;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ 
         n = block_sum(n, sh);
         inv = 1.f / fmaxf(sqrtf(n), eps);
     }
-    int r = blockIdx.x * (SN_THREADS / 32) + warp;
+    int r = blk * (SN_THREADS / 32) + warp;
     if (r < R) {
         const float* wr = W + (size_t)r * K;
         float a = 0.f;
@@ -130,15 +135,15 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ 
     }
     // the normalised v: every block writes its slice (training: also into the weight_v buffer)
     {
-        int per = (K + gridDim.x - 1) / gridDim.x;
-        int k0 = blockIdx.x * per, k1 = min(K, k0 + per);
+        int per = (K + nblk - 1) / nblk;
+        int k0 = blk * per, k1 = min(K, k0 + per);
         for (int k = k0 + threadIdx.x; k < k1; k += SN_THREADS) {
             float vv = t[k] * inv;
             v_save[k] = vv;
             if (power) v_buf[k] = vv;
         }
     }
-    if (!last_block(&g_sn_ticket[1], gridDim.x, &flag)) return;
+    if (!last_block(ticket, nblk, &flag)) return;
     const volatile float* sv = s;
     if (power) {
         float nrm = 0.f;
@@ -164,6 +169,13 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ 
         sg = block_sum(sg, sh);
         if (threadIdx.x == 0) *sigma = sg;
     }
+}
+
+__global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ W, const float* __restrict__ t, const float* __restrict__ nrm_part,
+                                                      int nchunks, int R, int K, int power, float eps, float* s, float* u_buf,
+                                                      float* __restrict__ u_save, float* __restrict__ v_buf, float* __restrict__ v_save,
+                                                      float* __restrict__ sigma) {
+    sn_wv_body(W, t, nrm_part, nchunks, R, K, power, eps, s, u_buf, u_save, v_buf, v_save, sigma, blockIdx.x, gridDim.x, &g_sn_ticket[1]);
 }
 
 // phase 3: W_sn (R, taps, Cin) = W (R, Cin, taps) / sigma.  Block = (SN_CI input channels of one row): a coalesced
@@ -196,12 +208,12 @@ __global__ void __launch_bounds__(SN_CI) k_sn_scale(const float* __restrict__ W,
 // channel axes swapped, which is the B operand of the tcgen05 data gradient (conv_tc.cu) -- otherwise a strided torch
 // copy per conv per step.  Block = (RB rows) x (32 input channels) x all taps, staged in shared memory with odd pitches
 // so that both output orders are written in full 128-byte (64-byte for RB = 16) segments without bank conflicts.
-__global__ void __launch_bounds__(SN_THREADS) k_sn_scale_t(const float* __restrict__ W, const float* __restrict__ sigma, int R, int Cin,
-                                                           int taps, int RB, float* __restrict__ out, float* __restrict__ wt) {
+__device__ __forceinline__ void sn_scale_t_body(const float* __restrict__ W, const float* __restrict__ sigma, int R, int Cin, int taps, int RB,
+                                                float* __restrict__ out, float* __restrict__ wt, int bx, int by) {
     extern __shared__ float smt[];                 // [(row * 33 + j) * tp + t]
     const float inv = 1.f / *sigma;
     const int tp = taps | 1;
-    const int r0 = blockIdx.y * RB, ci0 = blockIdx.x * 32;
+    const int r0 = by * RB, ci0 = bx * 32;
     const int nr = min(RB, R - r0), nj = min(32, Cin - ci0);
     const size_t K = (size_t)Cin * taps;
     const int run = nj * taps;                     // contiguous floats per row in the source
@@ -216,11 +228,16 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_scale_t(const float* __restri
         const int t = rt % taps, row = rt / taps;
         if (j < nj) out[(size_t)(r0 + row) * K + (size_t)t * Cin + ci0 + j] = smt[(row * 33 + j) * tp + t];
     }
+    if (wt == nullptr) return;
     for (int e = threadIdx.x; e < nj * taps * RB; e += SN_THREADS) {        // wt[ci][t][r]
         const int row = e % RB, jt = e / RB;
         const int t = jt % taps, j = jt / taps;
         if (row < nr) wt[((size_t)(ci0 + j) * taps + t) * R + r0 + row] = smt[(row * 33 + j) * tp + t];
     }
+}
+__global__ void __launch_bounds__(SN_THREADS) k_sn_scale_t(const float* __restrict__ W, const float* __restrict__ sigma, int R, int Cin,
+                                                           int taps, int RB, float* __restrict__ out, float* __restrict__ wt) {
+    sn_scale_t_body(W, sigma, R, Cin, taps, RB, out, wt, blockIdx.x, blockIdx.y);
 }
 
 // backward phase 1: c = sum dW_sn * W_sn  (both OHWI, contiguous)
@@ -270,6 +287,7 @@ __global__ void __launch_bounds__(SN_CI) k_sn_bwd(const float* __restrict__ dws,
     }
 }
 
+
 static int sn_splits(int R, int K, int* rows_per_split) {
     int gx = fsv_cdiv(K, SN_THREADS);
     int want = (2 * fsv_sm_count() + gx - 1) / gx;
@@ -279,6 +297,88 @@ static int sn_splits(int R, int K, int* rows_per_split) {
     if (rs > 32) rs = 32;
     *rows_per_split = fsv_cdiv(R, rs);
     return fsv_cdiv(R, *rows_per_split);
+}
+
+// ------------------------------------------------------------------------------------------------ grouped forward
+// All spectral weights a network touches in one forward, in THREE launches (one per phase) instead of three per weight:
+// ~110 weights x 3 phases x 2 generator forwards (+ the discriminators) per training step were ~660 dependent launches of
+// pure latency.  The host builds a plan once (fsv_spectral_group_plan): per-weight descriptors with absolute parameter /
+// buffer pointers (stable for the life of the modules), offsets into a per-call output arena and work arena (their base
+// pointers are kernel arguments, so fresh allocations per call need no table update -> CUDA-graph friendly), and per-phase
+// block maps (flattened grid -> (item, local block)).  Tickets of the last-block reductions live in a per-plan buffer,
+// so groups on different streams do not share counters.  Arithmetic and summation order per weight are those of the
+// single-weight kernels above (same bodies).
+__global__ void __launch_bounds__(SN_THREADS) k_sng_wtu(const fsv_sn_item* __restrict__ items, const int2* __restrict__ map, float* work,
+                                                        unsigned int* tickets) {
+    const int2 m = map[blockIdx.x];
+    const fsv_sn_item it = items[m.x];
+    const int chunk = m.y % it.nchunks, split = m.y / it.nchunks;
+    float* w = work + it.work_off;
+    sn_wtu_body(it.w_orig, it.u, it.R, it.K, it.rps, w, w + (size_t)it.rs * it.K + it.R, chunk, split, it.rs, tickets + it.ticket_off + chunk);
+}
+__global__ void __launch_bounds__(SN_THREADS) k_sng_wv(const fsv_sn_item* __restrict__ items, const int2* __restrict__ map, float* work,
+                                                       float* out, unsigned int* tickets, int power, float eps) {
+    const int2 m = map[blockIdx.x];
+    const fsv_sn_item it = items[m.x];
+    float* w = work + it.work_off;
+    float* s = w + (size_t)it.rs * it.K;
+    float* uvs = out + it.uvs_off;
+    sn_wv_body(it.w_orig, power ? w : it.v, s + it.R, it.nchunks, it.R, it.K, power, eps, s, it.u, uvs + it.K, it.v, uvs, uvs + it.K + it.R,
+               m.y, it.nblk2, tickets + it.ticket_off + it.nchunks);
+}
+__global__ void __launch_bounds__(SN_THREADS) k_sng_scale(const fsv_sn_item* __restrict__ items, const int2* __restrict__ map, float* out,
+                                                          int emit_wt) {
+    const int2 m = map[blockIdx.x];
+    const fsv_sn_item it = items[m.x];
+    const int gx = (it.Cin + 31) / 32;
+    const int RB = it.taps <= 9 ? 32 : 16;
+    sn_scale_t_body(it.w_orig, out + it.uvs_off + it.K + it.R, it.R, it.Cin, it.taps, RB, out + it.out_off,
+                    (emit_wt && it.want_wt) ? out + it.wt_off : nullptr, m.y % gx, m.y / gx);
+}
+
+extern "C" int fsv_spectral_group_plan(fsv_sn_item* items, int n, long long* totals) {
+    FSV_REQUIRE(items && totals && n > 0, "spectral_group_plan: bad args");
+    long long out = 0, work = 0, tick = 0, b1 = 0, b2 = 0, b3 = 0;
+    for (int i = 0; i < n; ++i) {
+        fsv_sn_item& it = items[i];
+        FSV_REQUIRE(it.R > 0 && it.R <= 65535 && it.Cin > 0 && it.taps > 0 && it.taps <= SN_MAXTAPS, "spectral_group_plan: bad dims in item %d", i);
+        it.K = it.Cin * it.taps;
+        it.nchunks = fsv_cdiv(it.K, SN_THREADS);
+        it.rs = sn_splits(it.R, it.K, &it.rps);
+        it.nblk2 = fsv_cdiv(it.R, SN_THREADS / 32);
+        const int RB = it.taps <= 9 ? 32 : 16;
+        it.nblk3 = fsv_cdiv(it.Cin, 32) * fsv_cdiv(it.R, RB);
+        const long long rk = (long long)it.R * it.K;
+        it.out_off = out; out += (rk + 3) / 4 * 4;
+        it.wt_off = out; if (it.want_wt) out += (rk + 3) / 4 * 4;
+        it.uvs_off = out; out += ((long long)it.K + it.R + 1 + 3) / 4 * 4;     // [v | u | sigma], 16-byte aligned slots
+        it.work_off = work; work += ((long long)it.rs * it.K + it.R + it.nchunks + 3) / 4 * 4;
+        it.ticket_off = (int)tick; tick += it.nchunks + 1;
+        it.blk1 = (int)b1; b1 += (long long)it.nchunks * it.rs;
+        it.blk2 = (int)b2; b2 += it.nblk2;
+        it.blk3 = (int)b3; b3 += it.nblk3;
+    }
+    totals[0] = out; totals[1] = work; totals[2] = tick; totals[3] = b1; totals[4] = b2; totals[5] = b3;
+    return FSV_OK;
+}
+
+// map layout: [b1 int2 | b2 int2 | b3 int2]; filled on the host by the caller from the plan (item index, local block)
+extern "C" int fsv_spectral_group_fwd(const fsv_sn_item* items_dev, const int* map_dev, const long long* totals, int power, float eps,
+                                      int emit_wt, float* out, float* work, unsigned int* tickets, void* stream) {
+    FSV_REQUIRE(items_dev && map_dev && totals && out && work && tickets, "spectral_group_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int2* map = reinterpret_cast<const int2*>(map_dev);
+    const long long b1 = totals[3], b2 = totals[4], b3 = totals[5];
+    if (power) {
+        k_sng_wtu<<<(unsigned)b1, SN_THREADS, 0, st>>>(items_dev, map, work, tickets);
+        FSV_CHECK_LAUNCH("spectral_group_wtu");
+    }
+    k_sng_wv<<<(unsigned)b2, SN_THREADS, 0, st>>>(items_dev, map + b1, work, out, tickets, power, eps);
+    FSV_CHECK_LAUNCH("spectral_group_wv");
+    const size_t sm = (size_t)32 * 33 * 9 * sizeof(float) > (size_t)16 * 33 * 17 * sizeof(float) ? (size_t)32 * 33 * 9 * sizeof(float) : (size_t)16 * 33 * 17 * sizeof(float);
+    k_sng_scale<<<(unsigned)b3, SN_THREADS, sm, st>>>(items_dev, map + b1 + b2, out, emit_wt);
+    FSV_CHECK_LAUNCH("spectral_group_scale");
+    return FSV_OK;
 }
 
 extern "C" long long fsv_spectral_workspace(int R, int K) {

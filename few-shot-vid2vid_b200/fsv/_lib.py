@@ -31,6 +31,13 @@ class SpadeDesc(ctypes.Structure):
                 ('m_coff', c_int * SPADE_MAX_MAPS), ('w_nstride', c_ll * SPADE_MAX_MAPS), ('dgb_ld', c_int * SPADE_MAX_MAPS)]
 
 
+class SnItem(ctypes.Structure):
+    _fields_ = [('w_orig', c_vp), ('u', c_vp), ('v', c_vp), ('R', c_int), ('Cin', c_int), ('taps', c_int), ('want_wt', c_int),
+                ('K', c_int), ('nchunks', c_int), ('rs', c_int), ('rps', c_int), ('nblk2', c_int), ('nblk3', c_int), ('ticket_off', c_int),
+                ('blk1', c_int), ('blk2', c_int), ('blk3', c_int),
+                ('out_off', c_ll), ('wt_off', c_ll), ('uvs_off', c_ll), ('work_off', c_ll)]
+
+
 PtrArray = c_vp * SPADE_MAX_MAPS
 _CD, _SD = ctypes.POINTER(ConvDesc), ctypes.POINTER(SpadeDesc)
 
@@ -77,6 +84,8 @@ SIGNATURES = {
     'fsv_spectral_workspace': [c_int, c_int],
     'fsv_spectral_fwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     'fsv_spectral_bwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    'fsv_spectral_group_plan': [c_vp, c_int, c_vp],
+    'fsv_spectral_group_fwd': [c_vp, c_vp, c_vp, c_int, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
     'fsv_fg_mask': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_float, c_vp],
     'fsv_face_mask_avg15': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp],
     'fsv_part_masks': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp],

@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import ACT_NONE, ACT_LRELU
-from .layers import Conv2d, InstanceNorm, BatchNorm, spectral
+from .layers import Conv2d, InstanceNorm, BatchNorm, SpectralPlanner, spectral
 from .generator import BaseNetwork, _Act
 
 
@@ -33,6 +33,24 @@ def get_nonspade_norm_layer(opt, norm_type='instance'):
             raise ValueError('normalization layer %s is not recognized' % sub)
         return nn.Sequential(layer, norm)
     return add_norm_layer
+
+
+class _planned:
+    """One grouped spectral-norm launch for the whole discriminator forward (layers.SpectralPlanner)."""
+
+    def __init__(self, net):
+        import torch
+        self.p = net.__dict__.get('_planner')
+        if self.p is None:
+            self.p = net.__dict__['_planner'] = SpectralPlanner(net)
+        self.sig = (net.training, torch.is_grad_enabled())
+
+    def __enter__(self):
+        self.started = self.p.begin(self.sig)
+
+    def __exit__(self, *exc):
+        if self.started:
+            self.p.end()
 
 
 class NLayerDiscriminator(BaseNetwork):
@@ -68,7 +86,8 @@ class NLayerDiscriminator(BaseNetwork):
         return feats
 
     def forward(self, input):
-        feats = [ops.nchw_view(f) for f in self.forward_nhwc(ops.to_nhwc(input))]
+        with _planned(self):
+            feats = [ops.nchw_view(f) for f in self.forward_nhwc(ops.to_nhwc(input))]
         return feats if self.getIntermFeat else feats[-1]
 
 
@@ -90,9 +109,10 @@ class MultiscaleDiscriminator(BaseNetwork):
     def forward_nhwc(self, x):
         """Same result for an input that is already NHWC (and possibly channel-padded, ops.pad_channels): what fsv.model packs."""
         result = []
-        for i in range(self.num_D):
-            feats = [ops.nchw_view(f) for f in getattr(self, 'discriminator_%d' % i).forward_nhwc(x)]
-            result.append(feats if self.getIntermFeat else [feats[-1]])
-            if i != self.num_D - 1:
-                x = ops.avgpool3s2(x)
+        with _planned(self):
+            for i in range(self.num_D):
+                feats = [ops.nchw_view(f) for f in getattr(self, 'discriminator_%d' % i).forward_nhwc(x)]
+                result.append(feats if self.getIntermFeat else [feats[-1]])
+                if i != self.num_D - 1:
+                    x = ops.avgpool3s2(x)
         return result

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID
-from .layers import Conv2d, Linear, BatchNorm, ConvNormAct, SPADEResnetBlock, spectral, init_weights
+from .layers import Conv2d, Linear, BatchNorm, ConvNormAct, SPADEResnetBlock, SpectralPlanner, spectral, init_weights
 
 
 class BaseNetwork(nn.Module):
@@ -249,6 +249,7 @@ class FewShotGenerator(BaseNetwork):
                 self.img_prev_embedding.init_weights(opt.init_type, opt.init_variance)
             else:
                 self.img_prev_embedding = self.img_ref_embedding
+        self.__dict__.pop('_planner', None)          # new spectral modules: the grouped plans are re-recorded
         if self.warp_ref:
             if self.sep_prev_flownet:
                 self.load_pretrained_net(self.flow_network_ref, self.flow_network_temp)
@@ -365,6 +366,18 @@ class FewShotGenerator(BaseNetwork):
     def forward(self, label, label_refs, img_refs, prev=[None, None], t=0, img_coarse=None):
         if img_coarse is not None:
             raise NotImplementedError('forward_face (--refine_face) is a "next" row of SURVEY.md section 8(f)')
+        planner = self.__dict__.get('_planner')
+        if planner is None:
+            planner = self.__dict__['_planner'] = SpectralPlanner(self)
+        sig = (self.training, torch.is_grad_enabled(), prev[0] is not None, self.warp_prev, bool(self.opt.isTrain or t == 0), img_refs.shape[1])
+        started = planner.begin(sig)
+        try:
+            return self._forward(label, label_refs, img_refs, prev, t)
+        finally:
+            if started:
+                planner.end()
+
+    def _forward(self, label, label_refs, img_refs, prev, t):
         b, n = img_refs.shape[0], img_refs.shape[1]
         if n != 1 and n != self.n_shot:
             raise ValueError('got %d reference images but the network was built with n_shot=%d' % (n, self.n_shot))

@@ -16,6 +16,87 @@ from .. import ops
 from ..ops import ACT_NONE, ACT_LRELU, NORM_BATCH, NORM_INSTANCE
 
 
+# one grouped spectral-norm launch per network forward instead of one per module (see SpectralPlanner); False = per-module calls
+GROUP_SPECTRAL = True
+
+
+class SpectralPlanner:
+    """Per top-level network (generator, discriminator): computes the spectral weights of ALL modules a forward pass will call in
+    three kernel launches up front (ops.SpectralGroup) instead of three launches per module.
+
+    Which modules a forward calls depends on its arguments (temporal inputs, eval-time weight cache, K-shot attention), and
+    torch.nn.utils.spectral_norm semantics must be kept exactly: ``weight_u/_v`` advance once per module CALL in training mode,
+    and only for modules that are called.  So the first forward with a given signature runs the ordinary per-module path and
+    records the sequence of spectral modules it touched; later forwards with the same signature compute that recorded set in one
+    group at entry, and each module picks its weight up when it runs.  A module called a second time in the same forward (the
+    shared flow network of the temporal phase, generator.py:159,166) falls back to its own power iteration, as does any module
+    the recording missed."""
+
+    def __init__(self, net):
+        self.plans = {}          # signature -> dict(mods=[(module, want_wt)], group=SpectralGroup or None)
+        self.ready = None
+        self.recording = None
+        self.active = False
+        for m in net.modules():
+            if getattr(m, 'fsv_spectral', False):
+                m._sn_planner = self
+
+    def begin(self, sig):
+        if not GROUP_SPECTRAL or self.active:
+            return False
+        self.active = True
+        plan = self.plans.get(sig)
+        self.sig = sig
+        if plan is None:
+            self.recording, self.ready = [], {}
+            return True
+        mods = plan['mods']
+        self.recording = None
+        if not mods:
+            self.ready = {}
+            return True
+        entries = [(m.weight_orig, m.weight_u, m.weight_v, want) for m, want in mods]
+        if plan['group'] is None or not plan['group'].matches(entries):
+            plan['group'] = ops.SpectralGroup(entries)
+        m0 = mods[0][0]
+        ws, wts = ops.spectral_group_weights(plan['group'], m0.training, m0.fsv_spectral_eps, [e[0] for e in entries])
+        self.ready = {id(m): (w, wt) for (m, _), w, wt in zip(mods, ws, wts)}
+        return True
+
+    def end(self):
+        if self.recording is not None:
+            seen, mods = set(), []
+            for m, want in self.recording:
+                if id(m) not in seen:
+                    seen.add(id(m))
+                    mods.append((m, want))
+            self.plans[self.sig] = dict(mods=mods, group=None)
+        self.recording, self.ready, self.active = None, None, False
+
+    def get(self, module, want_wt):
+        """-> (w_sn OHWI, wt or None)"""
+        if self.active and self.ready:
+            hit = self.ready.pop(id(module), None)
+            if hit is not None:
+                return hit          # (a missing channel-swapped copy is rebuilt by the conv's backward itself)
+        if self.active and self.recording is not None:
+            self.recording.append((module, bool(want_wt)))
+        return _spectral_single(module, want_wt)
+
+
+def _spectral_single(module, want_wt):
+    if want_wt:
+        return ops.spectral_weight(module.weight_orig, module.weight_u, module.weight_v, module.training, module.fsv_spectral_eps, want_wt=True)
+    return ops.spectral_weight(module.weight_orig, module.weight_u, module.weight_v, module.training, module.fsv_spectral_eps), None
+
+
+def spectral_weight_of(module, want_wt):
+    planner = getattr(module, '_sn_planner', None)
+    if planner is not None:
+        return planner.get(module, want_wt)
+    return _spectral_single(module, want_wt)
+
+
 class Conv2d(nn.Module):
     """nn.Conv2d stand-in (weight (Cout,Cin,kh,kw), optional bias) running fsv conv kernels."""
 
@@ -30,8 +111,8 @@ class Conv2d(nn.Module):
     def ohwi(self, want_wt=False):
         """OHWI weight [and its channel-swapped copy for the tcgen05 data gradient, or None]."""
         if getattr(self, 'fsv_spectral', False):
-            return ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v, self.training, self.fsv_spectral_eps,
-                                       want_wt=want_wt)
+            w, wt = spectral_weight_of(self, want_wt)
+            return (w, wt) if want_wt else w
         w = self.weight.permute(0, 2, 3, 1).contiguous()
         return (w, None) if want_wt else w
 
@@ -66,9 +147,7 @@ class Linear(nn.Module):
         wt = None
         if getattr(self, 'fsv_spectral', False):
             want = self.in_features % 16 == 0 and self.out_features % 32 == 0 and x.requires_grad
-            w, wt = ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v, self.training, self.fsv_spectral_eps,
-                                        want_wt=True) if want else (ops.spectral_weight(self.weight_orig, self.weight_u, self.weight_v,
-                                                                                        self.training, self.fsv_spectral_eps), None)
+            w, wt = spectral_weight_of(self, want)
         else:
             w = self.weight
         return ops.linear(x, w, self.bias, act=act, wt=wt)

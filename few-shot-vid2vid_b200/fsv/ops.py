@@ -432,6 +432,100 @@ def spectral_weight(w_orig, u, v, training, eps=1e-12, want_wt=False):
     return (out, None) if want_wt else out
 
 
+class SpectralGroup:
+    """Plan for computing the spectral weights of a fixed list of modules in three launches (fsv_spectral_group_fwd).
+    ``entries`` = [(w_orig, u, v, want_wt)]; the device tables hold the parameters' / buffers' addresses, so the plan is valid as
+    long as those tensors are not re-allocated (``matches`` checks)."""
+
+    def __init__(self, entries):
+        import numpy as np
+        n = len(entries)
+        self.n = n
+        self.dev = entries[0][0].device
+        self.ptrs = [(w.data_ptr(), u.data_ptr(), v.data_ptr()) for w, u, v, _ in entries]
+        self.shapes = [tuple(w.shape) for w, _, _, _ in entries]
+        items = (_lib.SnItem * n)()
+        for it, (w, u, v, want) in zip(items, entries):
+            _lib.require_cuda(w, u, v)
+            if not w.is_contiguous() or w.dtype != torch.float32:
+                raise _lib.FsvError('spectral group: weight_orig must be contiguous float32')
+            it.w_orig, it.u, it.v = w.data_ptr(), u.data_ptr(), v.data_ptr()
+            it.R, it.Cin = w.shape[0], w.shape[1]
+            it.taps = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
+            it.want_wt = 1 if want else 0
+        self.totals = (_lib.c_ll * 6)()
+        check(lib.fsv_spectral_group_plan(ctypes.byref(items), n, ctypes.byref(self.totals)), 'fsv_spectral_group_plan')
+        self.items = [dict(R=it.R, Cin=it.Cin, taps=it.taps, K=it.K, want_wt=bool(it.want_wt), out_off=it.out_off, wt_off=it.wt_off,
+                           uvs_off=it.uvs_off) for it in items]
+        maps = []
+        for nb in ('blk1', 'blk2', 'blk3'):
+            cnt = {'blk1': [it.nchunks * it.rs for it in items], 'blk2': [it.nblk2 for it in items], 'blk3': [it.nblk3 for it in items]}[nb]
+            idx = np.repeat(np.arange(n, dtype=np.int32), cnt)
+            loc = np.concatenate([np.arange(c, dtype=np.int32) for c in cnt])
+            maps.append(np.stack([idx, loc], axis=1))
+        self.map_dev = torch.from_numpy(np.ascontiguousarray(np.concatenate(maps, axis=0))).to(self.dev)
+        self.items_dev = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.dev)
+        self.tickets = torch.zeros(int(self.totals[2]) + 1, device=self.dev, dtype=torch.int32)
+        torch.cuda.current_stream().synchronize()
+
+    def matches(self, entries):
+        return len(entries) == self.n and all(p == (w.data_ptr(), u.data_ptr(), v.data_ptr()) for p, (w, u, v, _) in zip(self.ptrs, entries))
+
+
+class GroupSpectralFn(torch.autograd.Function):
+    """W_sn (OHWI) [+ channel-swapped copies] of every weight of a SpectralGroup: forward = 3 launches for the whole group; backward =
+    the per-weight fsv_spectral_bwd for the weights that received a gradient."""
+
+    @staticmethod
+    def forward(ctx, group, training, eps, emit_wt, *w_origs):
+        out = torch.empty(int(group.totals[0]) + 4, device=group.dev, dtype=torch.float32)
+        work = torch.empty(int(group.totals[1]) + 4, device=group.dev, dtype=torch.float32)
+        _call(lib.fsv_spectral_group_fwd, ptr(group.items_dev), ptr(group.map_dev), ctypes.byref(group.totals), 1 if training else 0, float(eps),
+              1 if emit_wt else 0, ptr(out), ptr(work), ptr(group.tickets), stream())
+        ws, wts = [], []
+        for it, shp in zip(group.items, group.shapes):
+            R, Cin, K = it['R'], it['Cin'], it['K']
+            oshape = (R, shp[2], shp[3], Cin) if len(shp) == 4 else (R, Cin)
+            ws.append(out[it['out_off']:it['out_off'] + R * K].view(oshape))
+            if emit_wt and it['want_wt']:
+                wts.append(out[it['wt_off']:it['wt_off'] + R * K].view((Cin, shp[2], shp[3], R) if len(shp) == 4 else (Cin, R)))
+            else:
+                wts.append(None)
+        ctx.group, ctx.arena = group, out
+        real_wts = [t for t in wts if t is not None]
+        ctx.mark_non_differentiable(*real_wts)
+        ctx.n = len(ws)
+        return tuple(ws) + tuple(real_wts)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        group, out = ctx.group, ctx.arena
+        res = []
+        st = stream()
+        for i, (it, shp) in enumerate(zip(group.items, group.shapes)):
+            g = grads[i]
+            if g is None:
+                res.append(None)
+                continue
+            g = _c(g)
+            R, Cin, K, taps = it['R'], it['Cin'], it['K'], it['taps']
+            dw = torch.empty(shp, device=g.device, dtype=torch.float32)
+            work = torch.empty(lib.fsv_spectral_workspace(R, K) // 4, device=g.device, dtype=torch.float32)
+            _call(lib.fsv_spectral_bwd, ptr(g), _off(out, it['out_off']), _off(out, it['uvs_off']), R, Cin, taps, ptr(dw), ptr(work), st)
+            res.append(dw)
+        return (None, None, None, None) + tuple(res)
+
+
+def spectral_group_weights(group, training, eps, w_origs):
+    """-> ([W_sn_i], [wt_i or None]) for the group's modules."""
+    emit = torch.is_grad_enabled() and SPECTRAL_EMIT_WT
+    outs = GroupSpectralFn.apply(group, training, eps, emit, *w_origs)
+    n = group.n
+    ws, rest = list(outs[:n]), list(outs[n:])
+    wts = [(rest.pop(0) if (emit and it['want_wt']) else None) for it in group.items]
+    return ws, wts
+
+
 # --------------------------------------------------------------------------- normalisation (+ activation)
 
 def _stats(x, n, hw, c, mode, training, running_mean, running_var, eps, momentum, unbias_mul=1):

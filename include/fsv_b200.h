@@ -229,6 +229,23 @@ int fsv_spectral_fwd(const float* w_orig, float* u, float* v, int R, int Cin, in
 int fsv_spectral_bwd(const float* dw_ohwi, const float* w_sn_ohwi, const float* uvs, int R, int Cin, int taps, float* dw_orig,
                      float* work, void* stream);
 
+/* Grouped forward: every spectral weight a network touches in one forward pass in THREE launches (one per phase).
+ * Fill w_orig/u/v/R/Cin/taps/want_wt of each item, call fsv_spectral_group_plan (host; fills the derived fields and
+ * totals[6] = {out floats, work floats, ticket words, phase-1 blocks, phase-2 blocks, phase-3 blocks}), upload the items and a
+ * block map ([(item, local block)] for the three phases back to back, int32 pairs) once, and keep a zero-initialised ticket
+ * buffer per plan.  Per call pass freshly allocated `out` / `work` arenas: item i's W_sn lives at out + out_off (OHWI), its
+ * channel-swapped copy at out + wt_off (when want_wt and emit_wt), [v | u | sigma] at out + uvs_off. */
+typedef struct fsv_sn_item {
+    const float* w_orig; float* u; float* v;
+    int R, Cin, taps, want_wt;
+    /* derived by fsv_spectral_group_plan */
+    int K, nchunks, rs, rps, nblk2, nblk3, ticket_off, blk1, blk2, blk3;
+    long long out_off, wt_off, uvs_off, work_off;
+} fsv_sn_item;
+int fsv_spectral_group_plan(fsv_sn_item* items, int n, long long* totals);
+int fsv_spectral_group_fwd(const fsv_sn_item* items_dev, const int* map_dev, const long long* totals, int power, float eps,
+                           int emit_wt, float* out, float* work, unsigned int* tickets, void* stream);
+
 /* ------------------------------------------------------------------ pose label preprocessing + face region */
 /* (MaxPool2d(15, stride 1, pad 7)(plane) > thr).float(): get_fg_mask, models/input_process.py:52-61.  plane n starts at
  * label + n*n_stride (pass the address of channel 2 of an NCHW label and n_stride = C*H*W); out (N, H, W). */

@@ -232,3 +232,18 @@ def face_bbox(planes, thr, openpose, crop_smaller=0):
 def crop_resize(image, box, size):
     from oracle import ops as OO
     return OO.crop_face_region(image, [tuple(int(v) for v in b) for b in box], size).permute(0, 2, 3, 1).contiguous()
+
+
+# ------------------------------------------------------------------ grouped spectral norm (layers.SpectralPlanner)
+class SpectralGroup:
+    def __init__(self, entries):
+        self.entries = entries
+        self.n = len(entries)
+
+    def matches(self, entries):
+        return len(entries) == self.n and all(a[0] is b[0] for a, b in zip(self.entries, entries))
+
+
+def spectral_group_weights(group, training, eps, w_origs):
+    ws = [spectral_weight(w, u, v, training, eps) for w, u, v, _ in group.entries]
+    return ws, [None] * group.n

@@ -424,3 +424,45 @@ def test_spectral_weight_vs_oracle(R, cin, k, training):
     o3, wt = ops.spectral_weight(wc, uc.clone(), vc.clone(), False, want_wt=True)
     assert wt is not None and torch.equal(wt, (o3.permute(3, 1, 2, 0) if k > 1 else o3.t()).contiguous())
     assert rel_err(o3, o2 if not training else o3) < tol
+
+
+@pytest.mark.parametrize('training', [True, False])
+def test_spectral_group_equals_per_weight_calls(training):
+    """fsv_spectral_group_fwd (all weights of a network in three launches) against the per-weight entry point on the same
+    inputs: weights, channel-swapped copies, advanced u / v, and the weight_orig gradients (same kernels' bodies -> bit-equal)."""
+    from fsv import ops
+    g = torch.Generator().manual_seed(7)
+    shapes = [(64, 32, 3, 3), (257, 64), (32, 6, 3, 3), (512, 256, 4, 4), (1024, 1024), (128, 128, 1, 1), (33, 20, 4, 4), (514, 128)]
+    ents, singles = [], []
+    for shp in shapes:
+        R, K = shp[0], int(torch.tensor(shp[1:]).prod())
+        w = (torch.randn(shp, generator=g) * 0.05).cuda()
+        u = torch.nn.functional.normalize(torch.randn(R, generator=g), dim=0).cuda()
+        v = torch.nn.functional.normalize(torch.randn(K, generator=g), dim=0).cuda()
+        want = shp[1] % 16 == 0 and R % 32 == 0
+        ents.append((w.clone().requires_grad_(True), u.clone(), v.clone(), want))
+        singles.append((w.clone().requires_grad_(True), u.clone(), v.clone(), want))
+    group = ops.SpectralGroup(ents)
+    for rep in range(2):                     # twice: tickets must have reset themselves, u / v keep advancing
+        ws, wts = ops.spectral_group_weights(group, training, 1e-12, [e[0] for e in ents])
+        for (w, u, v, want), (w1, u1, v1, _), o, ot in zip(ents, singles, ws, wts):
+            r = ops.spectral_weight(w1, u1, v1, training, want_wt=want)
+            ro, rt = r if want else (r, None)
+            assert torch.equal(o, ro), tuple(w.shape)
+            assert torch.equal(u, u1) and torch.equal(v, v1)
+            assert (ot is None) == (rt is None)
+            if ot is not None:
+                assert torch.equal(ot, rt)
+        gs = [torch.randn(o.shape, generator=g).cuda() for o in ws]
+        ga = torch.autograd.grad(sum((o * q).sum() for o, q in zip(ws, gs)), [e[0] for e in ents])
+        for (w1, u1, v1, want), q, gg in zip(singles, gs, ga):
+            pass
+    # gradients: group backward == per-weight backward (fresh forward on both sides from identical buffers)
+    ws, _ = ops.spectral_group_weights(group, training, 1e-12, [e[0] for e in ents])
+    rs = [ops.spectral_weight(w1, u1, v1, training) for (w1, u1, v1, _) in singles]
+    gs = [torch.randn(o.shape, generator=g).cuda() for o in ws]
+    ga = torch.autograd.grad(sum((o * q).sum() for o, q in zip(ws[:-1], gs[:-1])), [e[0] for e in ents], allow_unused=True)
+    gb = torch.autograd.grad(sum((o * q).sum() for o, q in zip(rs[:-1], gs[:-1])), [s[0] for s in singles], allow_unused=True)
+    assert ga[-1] is None and gb[-1] is None                  # a weight whose output was not used gets no gradient
+    for a, b in zip(ga[:-1], gb[:-1]):
+        assert torch.equal(a, b)
