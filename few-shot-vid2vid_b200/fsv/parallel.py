@@ -37,17 +37,26 @@ def shard_batch(global_batch, rank, world):
 
 
 class GradSync:
-    """Mean all-reduce of the gradients of ``params`` in flat buckets of at most ``bucket_mb`` MiB.
+    """Mean all-reduce of the gradients of ``params``, overlapped with backward and without any pack / unpack copies.
 
-    Call it after ``backward()`` and before ``optimizer.step()``.  Parameters whose grad is None on this
-    rank take part with zeros (all ranks must issue identical collectives)."""
+    The gradients LIVE in flat buckets: at construction every parameter's ``.grad`` becomes a view into one of a few contiguous
+    buffers (filled in reverse parameter order, i.e. roughly the order backward produces them, <= ``bucket_mb`` MiB each), and
+    autograd accumulates into those views in place.  A post-accumulate hook per parameter counts arrivals; when a bucket's last
+    gradient has landed its all-reduce is launched asynchronously (the collective runs on the process group's own stream while
+    backward keeps going on the compute stream).  ``sync()`` after ``backward()`` launches whatever is left (parameters without a
+    gradient this iteration contribute zeros), waits, and the optimizer then reads the averaged values through the same views.
+    NCCL averages inside the collective (ReduceOp.AVG); other backends (gloo in the CPU tests) sum and scale the bucket once.
 
-    def __init__(self, params, bucket_mb=256, group=None):
+    Protocol per optimizer step:  sync.zero()  ->  sync.arm()  ->  loss.backward()  ->  sync()  ->  optimizer.step().
+    ``arm`` matters because the generator's backward also runs through the discriminator: D's buckets must not fire then.
+    Everything is capturable into a CUDA graph (no host-device synchronisation; NCCL collectives are graph-capturable)."""
+
+    def __init__(self, params, bucket_mb=32, group=None, overlap=True):
         self.params = [p for p in params if p.requires_grad]
-        self.group = group
+        self.group, self.overlap = group, overlap
+        limit = max(1, int(bucket_mb * (1 << 20) // 4))
         self.buckets, cur, size = [], [], 0
-        limit = bucket_mb * (1 << 20) // 4
-        for p in self.params:
+        for p in reversed(self.params):
             if cur and size + p.numel() > limit:
                 self.buckets.append(cur)
                 cur, size = [], 0
@@ -55,42 +64,81 @@ class GradSync:
             size += p.numel()
         if cur:
             self.buckets.append(cur)
-        self._flat = [None] * len(self.buckets)
+        self.flat, self.views, self.bucket_of = [], {}, {}
+        for bi, bucket in enumerate(self.buckets):
+            flat = torch.zeros(sum(p.numel() for p in bucket), device=bucket[0].device, dtype=bucket[0].dtype)
+            off = 0
+            for p in bucket:
+                v = flat[off:off + p.numel()].view_as(p)
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
+                self.views[p] = v
+                self.bucket_of[p] = bi
+                off += p.numel()
+            self.flat.append(flat)
+        self.armed = False
+        self.count = [0] * len(self.buckets)
+        self.fired = [False] * len(self.buckets)
+        self.handles = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] if overlap else []
+        backend = dist.get_backend(group) if dist.is_initialized() else 'none'
+        self.native_avg = backend == 'nccl'
 
     @property
     def world(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
-    def __call__(self):
+    def zero(self):
+        """Replaces optimizer.zero_grad(): one memset per bucket, and the gradient views stay bound to the buckets."""
+        for flat in self.flat:
+            flat.zero_()
+        for p, v in self.views.items():
+            if p.grad is not v:
+                p.grad = v
+
+    def arm(self):
+        self.armed = True
+        self.count = [0] * len(self.buckets)
+        self.fired = [False] * len(self.buckets)
+        self.handles = []
+
+    def _fire(self, bi):
+        self.fired[bi] = True
         if self.world == 1:
             return
-        handles = []
-        for bi, bucket in enumerate(self.buckets):
-            n = sum(p.numel() for p in bucket)
-            flat = self._flat[bi]
-            if flat is None or flat.device != bucket[0].device:
-                flat = self._flat[bi] = torch.empty(n, device=bucket[0].device, dtype=bucket[0].dtype)
-            off = 0
-            for p in bucket:
-                v = flat[off:off + p.numel()]
-                if p.grad is None:
-                    v.zero_()
-                else:
-                    v.copy_(p.grad.reshape(-1))
-                off += p.numel()
-            handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        inv = 1.0 / self.world
-        for bi, bucket in enumerate(self.buckets):
-            handles[bi].wait()
-            flat = self._flat[bi]
-            off = 0
-            for p in bucket:
-                g = flat[off:off + p.numel()].view_as(p)
-                if p.grad is None:
-                    p.grad = (g * inv).clone()
-                else:
-                    p.grad.copy_(g).mul_(inv)
-                off += p.numel()
+        op = dist.ReduceOp.AVG if self.native_avg else dist.ReduceOp.SUM
+        self.handles.append((bi, dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True)))
+
+    def _on_grad(self, p):
+        if not self.armed:
+            return
+        bi = self.bucket_of[p]
+        if p.grad is not self.views[p]:          # somebody re-bound .grad (e.g. zero_grad(set_to_none=True)): fold it back in
+            self.views[p].copy_(p.grad)
+            p.grad = self.views[p]
+        self.count[bi] += 1
+        if self.count[bi] == len(self.buckets[bi]) and not self.fired[bi]:
+            self._fire(bi)
+
+    def __call__(self):
+        """After backward(): launch the buckets that did not fill up, wait for all of them, finish the mean."""
+        if not self.armed:
+            self.arm()
+        for p, v in self.views.items():
+            if p.grad is not v:
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
+        for bi in range(len(self.buckets)):
+            if not self.fired[bi]:
+                self._fire(bi)
+        for bi, h in self.handles:
+            h.wait()
+            if not self.native_avg:
+                self.flat[bi].mul_(1.0 / self.world)
+        self.armed = False
+        self.handles = []
 
 
 def broadcast_state(module, src=0, group=None):

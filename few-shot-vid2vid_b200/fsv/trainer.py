@@ -41,7 +41,11 @@ def make_optimizers(opt, netG, netD, capturable=False):
 def loss_backward(losses, optimizer, grad_sync=None):
     """loss_collector.py:217-228: mean -> sum -> zero_grad -> backward -> [all-reduce] -> step."""
     loss = sum(torch.mean(v) for v in losses.values())
-    optimizer.zero_grad()
+    if grad_sync is not None:
+        grad_sync.zero()             # gradients live in the sync's flat buckets (views): zero them in place
+        grad_sync.arm()
+    else:
+        optimizer.zero_grad()
     loss.backward()
     if grad_sync is not None:
         grad_sync()

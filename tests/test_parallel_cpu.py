@@ -30,11 +30,17 @@ def _worker(rank, world, port, out):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(8, 6, generator=g)
     lo, hi = parallel.shard_batch(8, rank, world)
-    loss = net(x[lo:hi]).square().mean()
-    loss.backward()
     unused = torch.nn.Parameter(torch.zeros(3))          # a parameter without grad on this rank
-    sync = parallel.GradSync(list(net.parameters()) + [unused], bucket_mb=1)
-    sync()
+    sync = parallel.GradSync(list(net.parameters()) + [unused], bucket_mb=5e-5)      # tiny buckets: several of them, fired from hooks
+    assert len(sync.buckets) >= 3
+    for it in range(2):                                   # twice: zero / arm / backward / sync protocol, views stay bound
+        sync.zero()
+        sync.arm()
+        loss = net(x[lo:hi]).square().mean()
+        loss.backward()
+        assert any(sync.fired)                            # overlap: buckets were launched from inside backward
+        sync()
+        assert all(p.grad is sync.views[p] for p in sync.params)
     ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     ref.load_state_dict(net.state_dict())
     ref(x).square().mean().backward()
