@@ -7,6 +7,8 @@ call the fsv C ABI through ``fsv.ops`` on NHWC activations.  Spectral normalisat
 hooks) exactly as the reference applies it, but the per-forward weight computation (one power iteration in
 training mode) runs in ``fsv_spectral_fwd/bwd`` instead of the ~20-launch torch hook.
 """
+import os
+
 import torch
 import torch.nn as nn
 from torch.nn.utils import spectral_norm as _sn
@@ -17,7 +19,7 @@ from ..ops import ACT_NONE, ACT_LRELU, NORM_BATCH, NORM_INSTANCE
 
 
 # one grouped spectral-norm launch per network forward instead of one per module (see SpectralPlanner); False = per-module calls
-GROUP_SPECTRAL = True
+GROUP_SPECTRAL = os.environ.get('FSV_GROUP_SPECTRAL', '1') != '0'
 
 
 class SpectralPlanner:
