@@ -115,7 +115,7 @@ class Conv2d(nn.Module):
         if getattr(self, 'fsv_spectral', False):
             w, wt = spectral_weight_of(self, want_wt)
             return (w, wt) if want_wt else w
-        w = self.weight.permute(0, 2, 3, 1).contiguous()
+        w = ops.to_ohwi(self.weight)
         return (w, None) if want_wt else w
 
     def forward(self, x, up=1, act=ACT_NONE, residual=None, out_scale=1.0, in_act=ACT_NONE):
@@ -131,8 +131,15 @@ class Conv2d(nn.Module):
             w = torch.nn.functional.pad(w, (0, cin - self.in_channels))
             if wt is not None:
                 wt = torch.nn.functional.pad(wt, (0, 0, 0, 0, 0, 0, 0, cin - self.in_channels))
+        if not self.__dict__.get('_guarded'):
+            for p in self.parameters(recurse=False):
+                ops.guard_param(p)
+            self.__dict__['_guarded'] = True
+        # weight / bias gradients of this conv are consumed by the spectral backward or OhwiFn (both continue on the side stream) and
+        # then adopted by the leaves: safe to compute off the critical path.  Not so for a zero-padded weight (its gradient is sliced
+        # by torch on the main stream).
         return ops.conv2d(x, w, self.bias, stride=self.stride, pad=self.padding, up=up, act=act,
-                          out_scale=out_scale, residual=residual, in_act=in_act, wt=wt)
+                          out_scale=out_scale, residual=residual, in_act=in_act, wt=wt, side_ok=(cin == self.in_channels))
 
 
 class Linear(nn.Module):
@@ -152,7 +159,11 @@ class Linear(nn.Module):
             w, wt = spectral_weight_of(self, want)
         else:
             w = self.weight
-        return ops.linear(x, w, self.bias, act=act, wt=wt)
+        if not self.__dict__.get('_guarded'):
+            for p in self.parameters(recurse=False):
+                ops.guard_param(p)
+            self.__dict__['_guarded'] = True
+        return ops.linear(x, w, self.bias, act=act, wt=wt, side_ok=bool(getattr(self, 'fsv_spectral', False)))
 
 
 def spectral(module):

@@ -5,6 +5,7 @@ device memory, streams and autograd bookkeeping only; every forward/backward bod
 or more calls into libfsv_b200.so on the current CUDA stream.
 """
 import ctypes
+import os
 
 import torch
 
@@ -18,6 +19,45 @@ NORM_BATCH, NORM_INSTANCE = _lib.NORM_BATCH, _lib.NORM_INSTANCE
 CONV_USE_TC = -1
 # launch counter (bench.py reports it as gpu_launches): number of C-ABI compute calls issued
 LAUNCHES = [0]
+
+
+# Weight-gradient work (conv wgrad + the spectral-norm backward that consumes it) is enqueued on a side stream: nothing downstream
+# in the backward pass needs dW, so it overlaps with the data-gradient chain (the critical path) and fills SMs the small kernels
+# leave idle.  The fork is `side.wait_stream(main)`; the join is ONE `main.wait_stream(side)` in a callback that the autograd engine
+# runs when the backward pass ends (before any optimizer can read .grad).  Everything is capturable into a CUDA graph (the side
+# stream becomes a parallel branch of the graph).  FSV_WGRAD_SIDE=0 keeps everything on one stream.
+WGRAD_SIDE_STREAM = os.environ.get('FSV_WGRAD_SIDE', '1') != '0'
+_SIDE, _SIDE_DIRTY = {}, {}
+
+
+def side_fork(*tensors):
+    """-> the side stream, made to wait for everything enqueued on the current stream so far; ``tensors`` (allocated on the
+    current stream, about to be read on the side stream) are registered with the allocator so their memory is not reused early."""
+    dev = torch.cuda.current_device()
+    side = _SIDE.get(dev)
+    if side is None:
+        side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    for t in tensors:
+        if t is not None:
+            t.record_stream(side)
+    if not _SIDE_DIRTY.get(dev):
+        _SIDE_DIRTY[dev] = True
+        torch.autograd.Variable._execution_engine.queue_callback(side_join)
+    return side
+
+
+def side_join():
+    """current stream waits for the side stream's pending weight-gradient work (no-op when there is none)."""
+    dev = torch.cuda.current_device()
+    if _SIDE_DIRTY.get(dev):
+        _SIDE_DIRTY[dev] = False
+        torch.cuda.current_stream().wait_stream(_SIDE[dev])
+
+
+def on_side_stream():
+    dev = torch.cuda.current_device()
+    return dev in _SIDE and torch.cuda.current_stream() == _SIDE[dev]
 
 
 def _c(t):
@@ -245,6 +285,14 @@ def _up2_selector(device):
     return _UP2_SEL[key]
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = act(conv(x, w) + b + residual) * out_scale on NHWC.
 
@@ -333,18 +381,23 @@ class Conv2dFn(torch.autograd.Function):
         need_b = ctx.has_b and ctx.needs_input_grad[2]
         if need_w or need_b:
             shared = d.w_nstride == 0 and cfg.get('w_off', 0) == 0
-            dw = torch.empty_like(wbase) if shared else torch.zeros_like(wbase)
-            if need_b:
-                db = dw if ctx.same_base else torch.zeros(ctx.bshape, device=dy.device, dtype=torch.float32)
-            w_done = False
-            if need_w and shared and d.use_tc != 0 and lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(d)):
-                ws = torch.empty(int(lib.fsv_conv2d_wgrad_tc_workspace(ctypes.byref(d))) // 4 + 1, device=dy.device, dtype=torch.float32)
-                _call(lib.fsv_conv2d_wgrad_tc, ctypes.byref(d), ptr(x), ptr(g), ptr(dw), ptr(ws), 0, st)
-                w_done = True
-            if not w_done or need_b:
-                _call(lib.fsv_conv2d_wgrad, ctypes.byref(d), ptr(x), ptr(g),
-                      _off(dw, cfg.get('w_off', 0)) if (need_w and not w_done) else None,
-                      _off(db, cfg.get('b_off', 0)) if need_b else None, 0 if shared else 1, st)
+            # shared weights whose gradient goes to a spectral-norm backward or straight to the leaf: off the critical path
+            use_side = WGRAD_SIDE_STREAM and shared and cfg.get('side_ok', False) and not on_side_stream()
+            side = side_fork(x, g) if use_side else None
+            with torch.cuda.stream(side) if side is not None else _NullCtx():
+                sw = stream()
+                dw = torch.empty_like(wbase) if shared else torch.zeros_like(wbase)
+                if need_b:
+                    db = dw if ctx.same_base else torch.zeros(ctx.bshape, device=dy.device, dtype=torch.float32)
+                w_done = False
+                if need_w and shared and d.use_tc != 0 and lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(d)):
+                    ws = torch.empty(int(lib.fsv_conv2d_wgrad_tc_workspace(ctypes.byref(d))) // 4 + 1, device=dy.device, dtype=torch.float32)
+                    _call(lib.fsv_conv2d_wgrad_tc, ctypes.byref(d), ptr(x), ptr(g), ptr(dw), ptr(ws), 0, sw)
+                    w_done = True
+                if not w_done or need_b:
+                    _call(lib.fsv_conv2d_wgrad, ctypes.byref(d), ptr(x), ptr(g),
+                          _off(dw, cfg.get('w_off', 0)) if (need_w and not w_done) else None,
+                          _off(db, cfg.get('b_off', 0)) if need_b else None, 0 if shared else 1, sw)
             if ctx.same_base:
                 db = None          # the single flat gradient is returned through wbase
             if not need_w:
@@ -355,12 +408,14 @@ class Conv2dFn(torch.autograd.Function):
 
 
 def conv2d(x, w_ohwi, bias=None, stride=1, pad=0, up=1, act=ACT_NONE, out_scale=1.0, residual=None, use_tc=None,
-           in_act=ACT_NONE, wt=None):
+           in_act=ACT_NONE, wt=None, side_ok=False):
     """``wt``: optional (Cin, kh, kw, Cout) copy of the weight with swapped channel axes (spectral_weight(want_wt=True));
     saves the transposing copy the tcgen05 data gradient would otherwise make."""
     cout, kh, kw, _ = w_ohwi.shape
+    # side_ok: the caller guarantees that the weight / bias gradients are consumed only by stream-aware code (the spectral-norm
+    # backward of this module, which continues on the side stream) or by the leaf accumulation at the end of backward
     cfg = dict(cout=cout, kh=kh, kw=kw, stride=stride, pad=pad, up=up, act=act, out_scale=out_scale, use_tc=use_tc,
-               in_act=in_act, wt=wt)
+               in_act=in_act, wt=wt, side_ok=side_ok)
     return Conv2dFn.apply(x, w_ohwi, bias, residual, cfg)
 
 
@@ -372,12 +427,48 @@ def batch_conv1x1(x, flat, cout, cin, w_off, b_off, act=ACT_NONE):
     return Conv2dFn.apply(x, flat, flat, None, cfg)
 
 
-def linear(x2d, w, bias, act=ACT_NONE, wt=None):
+def linear(x2d, w, bias, act=ACT_NONE, wt=None, side_ok=False):
     """F.linear on (rows, K) with w (out, K): a 1x1 conv over a rows x 1 'image'."""
     rows, k = x2d.shape
     wcols = 32 if rows % 32 == 0 else 1      # a 1x1 conv does not care how the rows are arranged as an image; 32-wide rows
-    y = conv2d(x2d.reshape(1, rows // wcols, wcols, k), w.reshape(w.shape[0], 1, 1, k), bias, act=act, wt=wt)   # suit the TMA boxes
+    y = conv2d(x2d.reshape(1, rows // wcols, wcols, k), w.reshape(w.shape[0], 1, 1, k), bias, act=act, wt=wt, side_ok=side_ok)   # suit the TMA boxes
     return y.reshape(rows, w.shape[0])
+
+
+class OhwiFn(torch.autograd.Function):
+    """(Cout, Cin, kh, kw) parameter -> OHWI copy for the conv kernels.  Backward re-lays the (side-stream produced) OHWI weight
+    gradient out on the side stream, so the leaf receives a contiguous tensor and its accumulation launches nothing."""
+
+    @staticmethod
+    def forward(ctx, w):
+        return w.permute(0, 2, 3, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, dw):
+        side = side_fork(dw) if (WGRAD_SIDE_STREAM and dw.is_cuda and not on_side_stream()) else None
+        with torch.cuda.stream(side) if side is not None else _NullCtx():
+            return dw.permute(0, 3, 1, 2).contiguous()
+
+
+def to_ohwi(w):
+    return OhwiFn.apply(w)
+
+
+def guard_param(p):
+    """Stream safety net for the side-stream weight gradients: a leaf that already holds a gradient when another one arrives
+    (a module called twice in one pass, gradient accumulation over several backward calls, .grad bound to a flat bucket) gets an
+    in-place add on the main stream -- which must then first wait for the side stream.  The common case (.grad is None: the
+    engine just adopts the tensor) costs nothing."""
+    if getattr(p, '_fsv_guarded', False) or not WGRAD_SIDE_STREAM:
+        return p
+
+    def hook(grad, p=p):
+        if p.grad is not None and grad.is_cuda:
+            side_join()
+        return grad
+    p.register_hook(hook)
+    p._fsv_guarded = True
+    return p
 
 
 # --------------------------------------------------------------------------- spectral normalisation of weights
@@ -417,10 +508,12 @@ class SpectralWeightFn(torch.autograd.Function):
     def backward(ctx, dout, *unused):
         out, uvs = ctx.saved_tensors
         R, cin, taps, shape = ctx.dims
-        dout = _c(dout)
-        dw = torch.empty(shape, device=dout.device, dtype=torch.float32)
-        work = torch.empty(lib.fsv_spectral_workspace(R, cin * taps) // 4, device=dout.device, dtype=torch.float32)
-        _call(lib.fsv_spectral_bwd, ptr(dout), ptr(out), ptr(uvs), R, cin, taps, ptr(dw), ptr(work), stream())
+        side = side_fork(out, uvs, dout) if (WGRAD_SIDE_STREAM and not on_side_stream()) else None   # dout usually comes from a side-stream wgrad
+        with torch.cuda.stream(side) if side is not None else _NullCtx():
+            dout = _c(dout)
+            dw = torch.empty(shape, device=dout.device, dtype=torch.float32)
+            work = torch.empty(lib.fsv_spectral_workspace(R, cin * taps) // 4, device=dout.device, dtype=torch.float32)
+            _call(lib.fsv_spectral_bwd, ptr(dout), ptr(out), ptr(uvs), R, cin, taps, ptr(dw), ptr(work), stream())
         return dw, None, None, None, None, None
 
 
@@ -501,18 +594,20 @@ class GroupSpectralFn(torch.autograd.Function):
     def backward(ctx, *grads):
         group, out = ctx.group, ctx.arena
         res = []
-        st = stream()
-        for i, (it, shp) in enumerate(zip(group.items, group.shapes)):
-            g = grads[i]
-            if g is None:
-                res.append(None)
-                continue
-            g = _c(g)
-            R, Cin, K, taps = it['R'], it['Cin'], it['K'], it['taps']
-            dw = torch.empty(shp, device=g.device, dtype=torch.float32)
-            work = torch.empty(lib.fsv_spectral_workspace(R, K) // 4, device=g.device, dtype=torch.float32)
-            _call(lib.fsv_spectral_bwd, ptr(g), _off(out, it['out_off']), _off(out, it['uvs_off']), R, Cin, taps, ptr(dw), ptr(work), st)
-            res.append(dw)
+        side = side_fork(out, *grads) if (WGRAD_SIDE_STREAM and not on_side_stream()) else None
+        with torch.cuda.stream(side) if side is not None else _NullCtx():
+            st = stream()
+            for i, (it, shp) in enumerate(zip(group.items, group.shapes)):
+                g = grads[i]
+                if g is None:
+                    res.append(None)
+                    continue
+                g = _c(g)
+                R, Cin, K, taps = it['R'], it['Cin'], it['K'], it['taps']
+                dw = torch.empty(shp, device=g.device, dtype=torch.float32)
+                work = torch.empty(lib.fsv_spectral_workspace(R, K) // 4, device=g.device, dtype=torch.float32)
+                _call(lib.fsv_spectral_bwd, ptr(g), _off(out, it['out_off']), _off(out, it['uvs_off']), R, Cin, taps, ptr(dw), ptr(work), st)
+                res.append(dw)
         return (None, None, None, None) + tuple(res)
 
 

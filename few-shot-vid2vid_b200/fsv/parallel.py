@@ -51,8 +51,14 @@ class GradSync:
     ``arm`` matters because the generator's backward also runs through the discriminator: D's buckets must not fire then.
     Everything is capturable into a CUDA graph (no host-device synchronisation; NCCL collectives are graph-capturable)."""
 
-    def __init__(self, params, bucket_mb=32, group=None, overlap=True):
+    def __init__(self, params, bucket_mb=32, group=None, overlap=None):
         self.params = [p for p in params if p.requires_grad]
+        if overlap is None:
+            # With the side-stream weight gradients (ops.WGRAD_SIDE_STREAM) the leaves must receive their gradients with .grad ==
+            # None (adoption launches nothing; an in-place add on the compute stream would race the side stream), so the buckets are
+            # filled by ONE multi-tensor copy after backward instead of in place, and the all-reduces start then ("collect" mode).
+            from . import ops
+            overlap = not (ops.WGRAD_SIDE_STREAM and any(p.is_cuda for p in self.params))
         self.group, self.overlap = group, overlap
         limit = max(1, int(bucket_mb * (1 << 20) // 4))
         self.buckets, cur, size = [], [], 0
@@ -72,7 +78,8 @@ class GradSync:
                 v = flat[off:off + p.numel()].view_as(p)
                 if p.grad is not None:
                     v.copy_(p.grad)
-                p.grad = v
+                if overlap:
+                    p.grad = v
                 self.views[p] = v
                 self.bucket_of[p] = bi
                 off += p.numel()
@@ -90,7 +97,12 @@ class GradSync:
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
     def zero(self):
-        """Replaces optimizer.zero_grad(): one memset per bucket, and the gradient views stay bound to the buckets."""
+        """Replaces optimizer.zero_grad(): one memset per bucket, and the gradient views stay bound to the buckets (overlap mode);
+        collect mode: gradients set to None (backward then hands each leaf a fresh tensor, no kernel)."""
+        if not self.overlap:
+            for p in self.params:
+                p.grad = None
+            return
         for flat in self.flat:
             flat.zero_()
         for p, v in self.views.items():
@@ -123,6 +135,15 @@ class GradSync:
 
     def __call__(self):
         """After backward(): launch the buckets that did not fill up, wait for all of them, finish the mean."""
+        if not self.overlap:
+            have = [p for p in self.params if p.grad is not None and p.grad is not self.views[p]]
+            if have:
+                torch._foreach_copy_([self.views[p] for p in have], [p.grad for p in have])     # one multi-tensor kernel per chunk
+            for p in self.params:
+                if p.grad is None:
+                    self.views[p].zero_()
+                p.grad = self.views[p]
+            self.arm()
         if not self.armed:
             self.arm()
         for p, v in self.views.items():

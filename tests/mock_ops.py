@@ -89,8 +89,16 @@ def avgpool3s2(x):
 
 
 # ------------------------------------------------------------------ convs
+def to_ohwi(w):
+    return w.permute(0, 2, 3, 1).contiguous()
+
+
+def guard_param(p):
+    return p
+
+
 def conv2d(x, w_ohwi, bias=None, stride=1, pad=0, up=1, act=ACT_NONE, out_scale=1.0, residual=None, use_tc=None,
-           in_act=ACT_NONE, wt=None):
+           in_act=ACT_NONE, wt=None, side_ok=False):
     """y = act(conv(up2?(in_act(x)), w) + bias + residual) * out_scale; w is (Cout, kh, kw, Cin)."""
     xin = _act(_nchw(x), in_act)
     if up == 2:
@@ -101,7 +109,7 @@ def conv2d(x, w_ohwi, bias=None, stride=1, pad=0, up=1, act=ACT_NONE, out_scale=
     return _nhwc(_act(y, act) * out_scale)
 
 
-def linear(x2d, w, bias, act=ACT_NONE, wt=None):
+def linear(x2d, w, bias, act=ACT_NONE, wt=None, side_ok=False):
     return _act(F.linear(x2d, w, bias), act)
 
 

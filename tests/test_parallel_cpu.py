@@ -31,16 +31,19 @@ def _worker(rank, world, port, out):
     x = torch.randn(8, 6, generator=g)
     lo, hi = parallel.shard_batch(8, rank, world)
     unused = torch.nn.Parameter(torch.zeros(3))          # a parameter without grad on this rank
-    sync = parallel.GradSync(list(net.parameters()) + [unused], bucket_mb=5e-5)      # tiny buckets: several of them, fired from hooks
-    assert len(sync.buckets) >= 3
-    for it in range(2):                                   # twice: zero / arm / backward / sync protocol, views stay bound
-        sync.zero()
-        sync.arm()
-        loss = net(x[lo:hi]).square().mean()
-        loss.backward()
-        assert any(sync.fired)                            # overlap: buckets were launched from inside backward
-        sync()
-        assert all(p.grad is sync.views[p] for p in sync.params)
+    for overlap in (True, False):                         # in-place buckets fired from hooks / collect-after-backward
+        for p in list(net.parameters()) + [unused]:
+            p.grad = None
+        sync = parallel.GradSync(list(net.parameters()) + [unused], bucket_mb=5e-5, overlap=overlap)      # tiny buckets: several of them
+        assert len(sync.buckets) >= 3
+        for it in range(2):                               # twice: zero / arm / backward / sync protocol, views stay bound
+            sync.zero()
+            sync.arm()
+            loss = net(x[lo:hi]).square().mean()
+            loss.backward()
+            assert any(sync.fired) == overlap             # overlap: buckets were launched from inside backward
+            sync()
+            assert all(p.grad is sync.views[p] for p in sync.params)
     ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     ref.load_state_dict(net.state_dict())
     ref(x).square().mean().backward()
