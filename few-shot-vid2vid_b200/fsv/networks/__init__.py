@@ -12,10 +12,12 @@ def define_G(opt):
         raise ValueError('generator not implemented!')
     if opt.isTrain and getattr(opt, 'print_G', False):
         netG.print_network()
-    if len(opt.gpu_ids) > 0:
+    moved = len(opt.gpu_ids) > 0
+    if moved:
         assert torch.cuda.is_available()
         netG.cuda()
-    netG.init_weights(opt.init_type, opt.init_variance)
+    # after the move the reference's init no longer reaches weight_orig of spectral layers (see layers.init_weights)
+    netG.init_weights(opt.init_type, opt.init_variance, reach_spectral=not moved)
     return netG
 
 
@@ -30,8 +32,9 @@ def define_D(opt, input_nc, ndf, n_layers_D, norm='spectralinstance', subarch='n
         raise ValueError('unknown type discriminator %s!' % opt.which_model_netD)
     if opt.isTrain and getattr(opt, 'print_D', False):
         netD.print_network()
-    if len(gpu_ids) > 0:
+    moved = len(gpu_ids) > 0
+    if moved:
         assert torch.cuda.is_available()
         netD.cuda()
-    netD.init_weights(opt.init_type, opt.init_variance)
+    netD.init_weights(opt.init_type, opt.init_variance, reach_spectral=not moved)
     return netD

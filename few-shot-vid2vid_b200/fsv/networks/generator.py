@@ -26,8 +26,8 @@ class BaseNetwork(nn.Module):
         print(self)
         print('Total number of parameters: %d' % num_params)
 
-    def init_weights(self, init_type='normal', gain=0.02):
-        init_weights(self, init_type, gain)
+    def init_weights(self, init_type='normal', gain=0.02, reach_spectral=True):
+        init_weights(self, init_type, gain, reach_spectral)
 
     def load_pretrained_net(self, net_src, net_dst):
         source, target = net_src.state_dict(), net_dst.state_dict()
@@ -238,6 +238,20 @@ class FewShotGenerator(BaseNetwork):
         self.sep_prev_flownet = opt.sep_flow_prev or (opt.n_frames_G != 2) or not opt.warp_ref
         self.sep_prev_embedding = self.spade_combine and (not opt.no_sep_warp_embed or not opt.warp_ref)
         dev = self.conv_img.weight.device
+        # generator.py:157,179: the new sub-networks are drawn under seed 0 on every rank (one process per GPU here, so without this
+        # the replicas would start from different weights); the caller's RNG streams are restored afterwards.  New parameters: the
+        # optimizer must be re-created by the caller (base_model.py:267-269 does), see trainer.make_step_optimizers.
+        cpu_state = torch.get_rng_state()
+        cuda_state = torch.cuda.get_rng_state(dev) if dev.type == 'cuda' else None
+        torch.manual_seed(0)
+        try:
+            self._build_temporal(opt, dev)
+        finally:
+            torch.set_rng_state(cpu_state)
+            if cuda_state is not None:
+                torch.cuda.set_rng_state(cuda_state, dev)
+
+    def _build_temporal(self, opt, dev):
         if self.sep_prev_flownet:
             self.flow_network_temp = FlowGenerator(opt, opt.n_frames_G).to(dev)
             self.flow_network_temp.init_weights(opt.init_type, opt.init_variance)

@@ -322,14 +322,25 @@ class SPADEResnetBlock(nn.Module):
         return self.conv_1(self.bn_1(dx, maps, nw[1], up=1, act=ACT_LRELU), residual=xs)
 
 
-def init_weights(net, init_type='xavier', gain=0.02):
-    """base_network.py:86-115: xavier-normal (gain) on every conv / linear weight (reaching ``weight_orig``
-    under spectral norm), zero biases; norm-layer affine parameters are left at (1, 0) -- the reference's
-    'BatchNorm2d' name test does not match its SyncBatchNorm / InstanceNorm classes."""
+def init_weights(net, init_type='xavier', gain=0.02, reach_spectral=True):
+    """base_network.py:86-115: the requested init (default xavier-normal, gain 0.02) on every conv / linear weight, zero biases;
+    norm-layer affine parameters stay at (1, 0) -- the reference's 'BatchNorm2d' name test does not match its SyncBatchNorm /
+    InstanceNorm classes.
+
+    ``reach_spectral``: the reference writes through ``m.weight.data``, which aliases ``weight_orig`` of a spectral-normalised
+    module only as long as the module has not been moved: ``define_G`` / ``define_D`` call ``.cuda()`` BEFORE ``init_weights``
+    (networks/__init__.py:35-38,51-54), after which ``m.weight`` is a detached copy and the init never reaches ``weight_orig`` --
+    on a GPU the reference's spectral layers therefore keep PyTorch's default kaiming-uniform init (their biases are still
+    zeroed).  The forward is invariant to that scale (W / sigma) but Adam's relative step on ``weight_orig`` is not, so the
+    factories mirror the effective behaviour: ``reach_spectral = (no GPU move happened)``.  ``init_temporal_network`` builds and
+    initialises its new sub-networks before they are moved (generator.py:160-172), there the init does reach ``weight_orig``."""
     for m in net.modules():
         if isinstance(m, (Conv2d, Linear)):
-            w = m.weight_orig if hasattr(m, 'weight_orig') else m.weight
-            if init_type == 'normal':
+            spectral_m = hasattr(m, 'weight_orig')
+            w = m.weight_orig if spectral_m else m.weight
+            if spectral_m and not reach_spectral:
+                pass
+            elif init_type == 'normal':
                 nn.init.normal_(w.data, 0.0, gain)
             elif init_type == 'xavier':
                 nn.init.xavier_normal_(w.data, gain=gain)
