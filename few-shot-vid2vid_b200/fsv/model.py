@@ -107,6 +107,23 @@ def _split(pred):
     return fake, real
 
 
+class _frozen:
+    """The generator update needs gradients THROUGH the discriminators, not FOR them: with their parameters frozen during that
+    forward the backward pass skips every discriminator weight gradient (the reference computes and then discards them:
+    optimizer_D.zero_grad() of the next iteration, loss_collector.py:217-228)."""
+
+    def __init__(self, modules):
+        self.params = [p for m in modules for p in m.parameters() if p.requires_grad]
+
+    def __enter__(self):
+        for p in self.params:
+            p.requires_grad_(False)
+
+    def __exit__(self, *exc):
+        for p in self.params:
+            p.requires_grad_(True)
+
+
 class Vid2VidStep:
     """Networks + per-iteration loss graph of one rank.  ``batch`` (reference layout, data/fewshot_*_dataset.py):
     tgt_label (B,1,C,H,W), tgt_image (B,1,3,H,W), ref_label (B,K,C,H,W), ref_image (B,K,3,H,W) and, in the temporal phase,
@@ -318,8 +335,9 @@ class Vid2VidStep:
         c = self.prepare(batch) if c is None else c
         fake, flow, fmask, warp, r, prevs_new, _ = self.generate(c)
         z = fake.new_zeros(1)
-        gt = self._temporal_gan(c, fake, False)
-        g = self._discriminate(c, r, fake, False) + self._discriminate_face(c, r, fake, False)
+        with _frozen(self.d_modules()):
+            gt = self._temporal_gan(c, fake, False)
+            g = self._discriminate(c, r, fake, False) + self._discriminate_face(c, r, fake, False)
         tgt = c['tgt_image']
 
         # ---- flow losses (loss_collector.py:131-163): F_Flow = 0 (--no_flow_gt)

@@ -38,12 +38,12 @@ def get_nonspade_norm_layer(opt, norm_type='instance'):
 class _planned:
     """One grouped spectral-norm launch for the whole discriminator forward (layers.SpectralPlanner)."""
 
-    def __init__(self, net):
+    def __init__(self, net, x):
         import torch
         self.p = net.__dict__.get('_planner')
         if self.p is None:
             self.p = net.__dict__['_planner'] = SpectralPlanner(net)
-        self.sig = (net.training, torch.is_grad_enabled())
+        self.sig = (net.training, torch.is_grad_enabled(), bool(x.requires_grad))
 
     def __enter__(self):
         self.started = self.p.begin(self.sig)
@@ -86,8 +86,9 @@ class NLayerDiscriminator(BaseNetwork):
         return feats
 
     def forward(self, input):
-        with _planned(self):
-            feats = [ops.nchw_view(f) for f in self.forward_nhwc(ops.to_nhwc(input))]
+        x = ops.to_nhwc(input)
+        with _planned(self, x):
+            feats = [ops.nchw_view(f) for f in self.forward_nhwc(x)]
         return feats if self.getIntermFeat else feats[-1]
 
 
@@ -109,7 +110,7 @@ class MultiscaleDiscriminator(BaseNetwork):
     def forward_nhwc(self, x):
         """Same result for an input that is already NHWC (and possibly channel-padded, ops.pad_channels): what fsv.model packs."""
         result = []
-        with _planned(self):
+        with _planned(self, x):
             for i in range(self.num_D):
                 feats = [ops.nchw_view(f) for f in getattr(self, 'discriminator_%d' % i).forward_nhwc(x)]
                 result.append(feats if self.getIntermFeat else [feats[-1]])
