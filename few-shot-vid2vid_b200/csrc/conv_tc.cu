@@ -360,6 +360,18 @@ static int pick_bn(int cout) {
     return 0;
 }
 
+// Few output-pixel tiles (low-resolution, wide layers: 1024 -> 1024 3x3 at 8x8 streams a 37.7 MB weight through 32 CTAs): narrow the
+// N tile until the grid covers the SMs, so that the weight stream is spread over all of them (A tiles are tiny there; the extra
+// A re-reads stay in L2).  FSV_TC_BN_OCC=0 disables.
+static int occupancy_bn(int bn, int cout, long long m_tiles) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("FSV_TC_BN_OCC"); on = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!on) return bn;
+    const long long sms = fsv_sm_count();
+    while (bn >= 64 && 2 * m_tiles * (cout / bn) <= sms && cout % (bn / 2) == 0 && (bn / 2) % 16 == 0) bn /= 2;   // less than half the SMs busy
+    return bn;
+}
+
 extern "C" int fsv_conv2d_tc_eligible(const fsv_conv_desc* d) {
     if (!d) return 0;
     if (d->up != 1 || d->in_act != FSV_ACT_NONE) return 0;
@@ -478,12 +490,12 @@ extern "C" int fsv_conv2d_fwd_tc(const fsv_conv_desc* d, const float* x, const f
     FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w) & 15) == 0 && (((uintptr_t)y) & 15) == 0, "conv2d_fwd_tc: pointers must be 16-byte aligned");
     TcParams p;
     memset(&p, 0, sizeof(p));
-    const int BN = pick_bn(d->Cout);
     int TW, TH, TN;
     pick_tile(d->Ho, d->Wo, TW, TH, TN);
     p.TW = TW; p.TH = TH; p.TN = TN;
     p.tiles_w = fsv_cdiv(d->Wo, TW); p.tiles_h = fsv_cdiv(d->Ho, TH);
     const int tiles_n = fsv_cdiv(d->N, TN);
+    const int BN = occupancy_bn(pick_bn(d->Cout), d->Cout, (long long)p.tiles_w * p.tiles_h * tiles_n);
     p.ntaps = d->kh * d->kw; p.Cin = d->Cin; p.Cout = d->Cout; p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
     p.OH = d->Ho; p.OW = d->Wo; p.os = 1; p.oph = 0; p.opw = 0;
     p.y_ld = d->y_ld; p.y_coff = d->y_coff; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.act = d->act; p.out_scale = d->out_scale;
@@ -550,7 +562,7 @@ extern "C" int fsv_conv2d_dgrad_tc(const fsv_conv_desc* d, const float* dy, cons
         return FSV_ENOTSUP;
     }
     FSV_REQUIRE((((uintptr_t)dy) & 15) == 0 && (((uintptr_t)wt) & 15) == 0 && (((uintptr_t)dx) & 15) == 0, "conv2d_dgrad_tc: pointers must be 16-byte aligned");
-    const int BN = pick_bn(d->Cin);
+    const int BN0 = pick_bn(d->Cin);
     const int taps_all = d->kh * d->kw;
     const long long ld = d->y_ld;
     const float* dyb = dy + d->y_coff;
@@ -570,6 +582,7 @@ extern "C" int fsv_conv2d_dgrad_tc(const fsv_conv_desc* d, const float* dy, cons
         p.Cin = d->Cout; p.Cout = d->Cin; p.N = d->N; p.Ho = OHc; p.Wo = OWc;
         p.OH = d->H; p.OW = d->W; p.os = d->stride; p.oph = ph; p.opw = pw;
         p.y_ld = d->x_ld; p.y_coff = d->x_coff; p.res_ld = d->x_ld; p.res_coff = 0; p.act = FSV_ACT_NONE; p.out_scale = 1.f;
+        const int BN = occupancy_bn(BN0, d->Cin, (long long)p.tiles_w * p.tiles_h * tiles_n);
         p.BN = BN;
         int nt = 0;
         for (int r = 0; r < d->kh; ++r)
@@ -620,7 +633,7 @@ extern "C" int fsv_conv2d_fwd_tc_up2(const fsv_conv_desc* d, const float* x, con
     }
     FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w4) & 15) == 0 && (((uintptr_t)y) & 15) == 0, "conv2d_fwd_tc_up2: pointers must be 16-byte aligned");
     const int Hs = d->H / 2, Ws = d->W / 2;
-    const int BN = pick_bn(d->Cout);
+    const int BN0 = pick_bn(d->Cout);
     const long long ld = d->x_ld;
     for (int cls = 0; cls < 4; ++cls) {
         const int ph = cls >> 1, pw = cls & 1;
@@ -634,6 +647,7 @@ extern "C" int fsv_conv2d_fwd_tc_up2(const fsv_conv_desc* d, const float* x, con
         p.Cin = d->Cin; p.Cout = d->Cout; p.N = d->N; p.Ho = Hs; p.Wo = Ws;
         p.OH = d->Ho; p.OW = d->Wo; p.os = 2; p.oph = ph; p.opw = pw;
         p.y_ld = d->y_ld; p.y_coff = d->y_coff; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.act = d->act; p.out_scale = d->out_scale;
+        const int BN = occupancy_bn(BN0, d->Cout, (long long)p.tiles_w * p.tiles_h * tiles_n);
         p.BN = BN;
         p.ntaps = 4;
         for (int a = 0; a < 2; ++a)
