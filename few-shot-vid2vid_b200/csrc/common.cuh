@@ -38,6 +38,8 @@ void fsv_set_error(const char* fmt, ...);
 
 static inline int fsv_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int fsv_sm_count();
+// true the first time it is called for (flag set, current device): per-DEVICE one-time setup (cudaFuncSetAttribute is per device)
+bool fsv_first_on_device(unsigned long long* flags);
 
 __device__ __forceinline__ float fsv_act(float v, int act) {
     if (act == FSV_ACT_LRELU) return v > 0.f ? v : v * FSV_LRELU_SLOPE;

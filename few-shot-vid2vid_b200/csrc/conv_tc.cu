@@ -451,19 +451,17 @@ static int launch_tc(TcParams& p, int tiles_n, const float* bias, const float* r
     const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 4;
     p.stages = pick_stages(stage_bytes, p.ntaps * (p.Cin / TC_BK));
     const int smem_bytes = p.stages * stage_bytes + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (fsv_first_on_device(&configured)) {
         FSV_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        configured = true;
     }
     p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
     static int persist = -1;
     if (persist < 0) { const char* e = getenv("FSV_TC_PERSIST"); persist = (e && atoi(e)) ? 1 : 0; }
     if (persist) {      // round-2 candidate, see k_conv_tc_p; off by default
-        static bool configured_p = false;
-        if (!configured_p) {
+        static unsigned long long configured_p = 0;
+        if (fsv_first_on_device(&configured_p)) {
             FSV_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            configured_p = true;
         }
         const int smem_p = smem_bytes + 4 * 8;
         const long long total = (long long)p.m_tiles * (p.Cout / p.BN);

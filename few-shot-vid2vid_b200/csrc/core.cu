@@ -12,13 +12,22 @@ void fsv_set_error(const char* fmt, ...) {
 }
 
 int fsv_sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0) sms[dev] = 148;
     }
-    return sms;
+    return sms[dev];
+}
+
+bool fsv_first_on_device(unsigned long long* flags) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const unsigned long long bit = 1ull << dev;
+    if (*flags & bit) return false;
+    *flags |= bit;
+    return true;
 }
 
 extern "C" const char* fsv_last_error(void) { return g_err; }

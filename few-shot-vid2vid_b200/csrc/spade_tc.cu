@@ -352,13 +352,12 @@ static int spade_tc_launch(const fsv_spade_desc* d, const float* x, const float*
         }
     }
     const int smem_bytes = SP_STAGES * SP_STAGE_BYTES_OF(CB) + (2 * SP_STAGES + 1) * 8 + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (fsv_first_on_device(&configured)) {
         FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        configured = true;
     }
     dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->C / CB);
     cudaStream_t st = (cudaStream_t)stream;

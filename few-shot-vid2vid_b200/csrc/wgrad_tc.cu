@@ -532,10 +532,9 @@ static int wgrad_tc_mn(const fsv_conv_desc* d, const float* x, const float* dy, 
         p.stages = stg;
     }
     const int smem_bytes = p.stages * (4 * WGMN_BLOCK_BYTES + (p.BN / 32) * WGMN_BLOCK_BYTES) + (2 * WG_MAX_STAGES + 1) * 8 + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (fsv_first_on_device(&configured)) {
         FSV_CUDA(cudaFuncSetAttribute(k_wgrad_tc_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     dim3 grid((unsigned)splits, taps, p.mtiles * p.ntiles);
     k_wgrad_tc_mn<<<grid, 192, smem_bytes, st>>>(p, dw);
@@ -601,10 +600,9 @@ extern "C" int fsv_conv2d_wgrad_tc(const fsv_conv_desc* d, const float* x, const
     p.kb_per_split = (int)((KB + splits - 1) / splits);
     splits = (KB + p.kb_per_split - 1) / p.kb_per_split;
     const int smem_bytes = WG_STAGES * (TC_A_BYTES + p.BN * TC_BK * 4) + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (fsv_first_on_device(&configured)) {
         FSV_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     dim3 grid((unsigned)splits, taps, p.mtiles * p.ntiles);
     k_wgrad_tc<<<grid, 192, smem_bytes, st>>>(p, dw);
