@@ -38,6 +38,10 @@ class SnItem(ctypes.Structure):
                 ('out_off', c_ll), ('wt_off', c_ll), ('uvs_off', c_ll), ('work_off', c_ll)]
 
 
+class AdamItem(ctypes.Structure):
+    _fields_ = [('param', c_vp), ('grad', c_vp), ('exp_avg', c_vp), ('exp_avg_sq', c_vp), ('numel', c_ll)]
+
+
 PtrArray = c_vp * SPADE_MAX_MAPS
 _CD, _SD = ctypes.POINTER(ConvDesc), ctypes.POINTER(SpadeDesc)
 
@@ -86,6 +90,8 @@ SIGNATURES = {
     'fsv_spectral_bwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'fsv_spectral_group_plan': [c_vp, c_int, c_vp],
     'fsv_spectral_group_fwd': [c_vp, c_vp, c_vp, c_int, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
+    'fsv_adam_chunks': [c_ll],
+    'fsv_adam_step': [c_vp, c_vp, c_ll, c_vp, c_float, c_float, c_float, c_float, c_vp],
     'fsv_fg_mask': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_float, c_vp],
     'fsv_face_mask_avg15': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp],
     'fsv_part_masks': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp],
@@ -107,6 +113,7 @@ def _load():
     lib.fsv_conv2d_wgrad_tc_workspace.restype = c_ll
     lib.fsv_spectral_workspace.restype = c_ll
     lib.fsv_norm_work_doubles.restype = c_ll
+    lib.fsv_adam_chunks.restype = c_ll
     lib.fsv_last_error.argtypes = []
     lib.fsv_last_error.restype = ctypes.c_char_p
     return lib

@@ -8,14 +8,18 @@ import torch
 
 from .model import Vid2VidStep, LOSS_NAMES_D, LOSS_NAMES_G  # noqa: F401
 
-FUSED_ADAM = True
+import os
+
+OWN_ADAM = os.environ.get('FSV_OWN_ADAM', '1') != '0'      # fsv.optim.Adam (one launch on the C ABI); 0 = torch's fused Adam
 
 
 def _adam(params, lr, betas, capturable):
     params = list(params)
-    # fused=True: torch's single-kernel multi-tensor Adam (same update rule as the reference's torch.optim.Adam)
-    fused = FUSED_ADAM and all(p.is_cuda for p in params)
-    return torch.optim.Adam(params, lr=lr, betas=betas, capturable=capturable, fused=True if fused else None)
+    on_gpu = all(p.is_cuda for p in params)
+    if OWN_ADAM and on_gpu:
+        from .optim import Adam
+        return Adam(params, lr=lr, betas=betas)
+    return torch.optim.Adam(params, lr=lr, betas=betas, capturable=capturable and on_gpu, fused=True if on_gpu else None)
 
 
 def make_step_optimizers(opt, step, capturable=False):

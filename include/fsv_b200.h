@@ -246,6 +246,18 @@ int fsv_spectral_group_plan(fsv_sn_item* items, int n, long long* totals);
 int fsv_spectral_group_fwd(const fsv_sn_item* items_dev, const int* map_dev, const long long* totals, int power, float eps,
                            int emit_wt, float* out, float* work, unsigned int* tickets, void* stream);
 
+/* ------------------------------------------------------------------ multi-tensor Adam (base_model.py:39-48, loss_collector.py:227) */
+/* One launch for all parameters of an optimizer; same update rule as torch.optim.Adam(lr, betas, eps) without amsgrad / weight
+ * decay.  items: device array describing each parameter; chunks: device array of (item, chunk) int32 pairs covering every item
+ * in pieces of fsv_adam_chunks(1) elements; step_dev: device float holding the number of steps taken so far (advanced here). */
+typedef struct fsv_adam_item {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+    long long numel;
+} fsv_adam_item;
+long long fsv_adam_chunks(long long numel);
+int fsv_adam_step(const fsv_adam_item* items_dev, const int* chunks_dev, long long nchunks, float* step_dev, float lr,
+                  float beta1, float beta2, float eps, void* stream);
+
 /* ------------------------------------------------------------------ pose label preprocessing + face region */
 /* (MaxPool2d(15, stride 1, pad 7)(plane) > thr).float(): get_fg_mask, models/input_process.py:52-61.  plane n starts at
  * label + n*n_stride (pass the address of channel 2 of an NCHW label and n_stride = C*H*W); out (N, H, W). */

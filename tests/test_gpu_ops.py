@@ -466,3 +466,57 @@ def test_spectral_group_equals_per_weight_calls(training):
     assert ga[-1] is None and gb[-1] is None                  # a weight whose output was not used gets no gradient
     for a, b in zip(ga[:-1], gb[:-1]):
         assert torch.equal(a, b)
+
+
+def test_own_adam_matches_torch_adam_eager_and_graphed():
+    """fsv.optim.Adam (fsv_adam_step: one launch, device-side step counter) against torch.optim.Adam with the reference's TTUR
+    settings (base_model.py:39-48): three eager steps with fresh gradient tensors every step, then the same update replayed
+    from a CUDA graph; state_dict layout interchangeable."""
+    from fsv.optim import Adam
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 32, 3, 3), (257,), (5, 7), (1024, 1024), (3,)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = Adam(pa, lr=2e-4, betas=(0.0, 0.999))
+    ob = torch.optim.Adam(pb, lr=2e-4, betas=(0.0, 0.999))
+    for it in range(3):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).cuda()
+            a.grad, b.grad = gr.clone(), gr.clone()          # new tensors every step, as autograd hands them to the leaves
+        oa.step()
+        ob.step()
+    for a, b in zip(pa, pb):
+        assert rel_err(a, b) < 1e-6
+    sa, sb = oa.state_dict()['state'], ob.state_dict()['state']
+    assert set(sa[0]) == set(sb[0]) == {'step', 'exp_avg', 'exp_avg_sq'} and float(sa[0]['step']) == float(sb[0]['step']) == 3
+    # CUDA graph: static gradient buffers, counter on the device
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for a in pa:
+            a.grad = torch.zeros_like(a)
+        oa.step()
+        ob_ref = [p.detach().clone() for p in pa]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            oa.step()
+    torch.cuda.synchronize()
+    for b, r in zip(pb, ob_ref):
+        b.data.copy_(r)                                       # restart the torch side from the same point (moments differ only by the zero-grad steps)
+    for a, b in zip(pa, pb):
+        ob.state[b]['exp_avg'].copy_(oa.state[a]['exp_avg'])
+        ob.state[b]['exp_avg_sq'].copy_(oa.state[a]['exp_avg_sq'])
+        ob.state[b]['step'].fill_(float(oa.state[a]['step']) - 1)     # the capture itself advanced the device counter once... 
+    for a, b in zip(pa, pb):
+        b.data.copy_(a.data)
+    for a, b in zip(pa, pb):
+        ob.state[b]['step'].fill_(float(oa.state[a]['step']))
+    for it in range(2):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).cuda()
+            a.grad.copy_(gr)
+            b.grad = gr.clone()
+        graph.replay()
+        ob.step()
+    torch.cuda.synchronize()
+    for a, b in zip(pa, pb):
+        assert rel_err(a, b) < 1e-5
