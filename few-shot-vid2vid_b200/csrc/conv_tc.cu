@@ -457,8 +457,8 @@ static int launch_tc(TcParams& p, int tiles_n, const float* bias, const float* r
     }
     p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
     static int persist = -1;
-    if (persist < 0) { const char* e = getenv("FSV_TC_PERSIST"); persist = (e && atoi(e)) ? 1 : 0; }
-    if (persist) {      // round-2 candidate, see k_conv_tc_p; off by default
+    if (persist < 0) { const char* e = getenv("FSV_TC_PERSIST"); persist = (e && atoi(e) == 0) ? 0 : 1; }
+    if (persist) {      // default since round 2 (passes tests/test_gpu_tc.py on the B200, -1.2 ms per pose512 step); FSV_TC_PERSIST=0 = one tile per CTA
         static unsigned long long configured_p = 0;
         if (fsv_first_on_device(&configured_p)) {
             FSV_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

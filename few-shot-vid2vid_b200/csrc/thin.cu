@@ -167,6 +167,71 @@ __global__ void __launch_bounds__(TT_THREADS) k_tco_fwd(ThinP p, int lpp, int tw
     }
 }
 
+// 4x4 kernels (the discriminator heads 512 -> 1, discriminator.py:88): same work split, taps unrolled at compile time.  The
+// generic kernel above keeps ONE global load in flight per thread (run-time tap loops with `continue`s), which made the 34x34
+// head 72 us and the face discriminator's 10x10 head 0.5 ms of pure load latency; here a lane issues all 16 tap loads of a
+// channel quad back to back (predicated on the padding) before the FMAs.
+template <int COUT, int KS>
+__global__ void __launch_bounds__(TT_THREADS) k_tco_fwd_ks(ThinP p, int lpp, int tw, int th, const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ residual,
+                                                           float* __restrict__ y) {
+    extern __shared__ __align__(16) float ws[];
+    constexpr int taps = KS * KS;
+    const int cin4 = p.Cin >> 2;
+    for (int i = threadIdx.x; i < COUT * taps * p.Cin; i += TT_THREADS) ws[i] = w[i];
+    __syncthreads();
+    const int sub = threadIdx.x & (lpp - 1), slot = threadIdx.x / lpp, slots = TT_THREADS / lpp;
+    const long long n = blockIdx.z;
+    const int h0 = blockIdx.y * th, w0 = blockIdx.x * tw;
+    for (int pidx = slot; pidx < tw * th; pidx += slots) {
+        const int ho = h0 + pidx / tw, wo = w0 + (pidx % tw);
+        const bool valid = ho < p.Ho && wo < p.Wo;
+        float acc[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+        if (valid) {
+            const int ih0 = ho * p.stride - p.pad, iw0 = wo * p.stride - p.pad;
+            for (int c4 = sub; c4 < cin4; c4 += lpp) {
+                float4 xv[taps];
+#pragma unroll
+                for (int r = 0; r < KS; ++r)
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        const int ih = ih0 + r, iw = iw0 + s;
+                        const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+                        xv[r * KS + s] = ok ? reinterpret_cast<const float4*>(x + ((n * p.H + ih) * p.W + iw) * p.x_ld + p.x_coff)[c4]
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                for (int t = 0; t < taps; ++t) {
+                    float4 v = xv[t];
+                    if (p.in_act == FSV_ACT_LRELU) v = lrelu4(v);
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) {
+                        const float4 wv = *reinterpret_cast<const float4*>(ws + (co * taps + t) * p.Cin + c4 * 4);
+                        acc[co] += v.x * wv.x + v.y * wv.y + v.z * wv.z + v.w * wv.w;
+                    }
+                }
+            }
+        }
+        for (int o = lpp >> 1; o > 0; o >>= 1)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+        if (valid && sub == 0) {
+            const long long pix = (n * p.Ho + ho) * p.Wo + wo;
+            float* yp = y + pix * p.y_ld + p.y_coff;
+            const float* rp = residual ? residual + pix * p.res_ld + p.res_coff : nullptr;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                float t = acc[co];
+                if (bias) t += bias[co];
+                if (rp) t += rp[co];
+                yp[co] = fsv_act(t, p.act) * p.out_scale;
+            }
+        }
+    }
+}
+
 // data gradient: dx[n,h,w,ci] = sum_{r,s,co} dy[n,(h+pad-r)/stride,(w+pad-s)/stride,co] * w[co][r][s][ci]; tiles over (H, W)
 template <int COUT>
 __global__ void __launch_bounds__(TT_THREADS) k_tco_dgrad(ThinP p, int lpp, int tw, int th, const float* __restrict__ dy, const float* __restrict__ w,
@@ -604,6 +669,11 @@ extern "C" int fsv_conv2d_fwd_thin(const fsv_conv_desc* d, const float* x, const
             }
 #undef TCO_FWD3
             FSV_CHECK_LAUNCH("conv2d_fwd_thin_k3");
+            return FSV_OK;
+        }
+        if (d->kh == 4 && d->kw == 4 && d->Cout == 1) {
+            k_tco_fwd_ks<1, 4><<<grid, TT_THREADS, sm, st>>>(p, lpp, tw, th, x, w, bias, residual, y);
+            FSV_CHECK_LAUNCH("conv2d_fwd_thin_k4");
             return FSV_OK;
         }
         switch (d->Cout) {

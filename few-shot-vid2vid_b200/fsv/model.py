@@ -212,8 +212,12 @@ class Vid2VidStep:
     def _ref_constants(self, c, ref_idx):
         """Constants that depend on which reference was picked (K > 1: known only after the generator ran)."""
         opt = self.opt
+        if ref_idx is None and 'r' in c:
+            return c['r']          # one reference image: the D-step and the G-step of an iteration share masks, boxes, packed inputs, crops
         ref_label_valid, ref_label_t, ref_image_t = pick_ref([c['ref_labels_valid'], c['ref_labels'], c['ref_images']], ref_idx)
         r = dict(ref_label_valid=ref_label_valid, ref_image=ref_image_t)
+        if ref_idx is None:
+            c['r'] = r
         if self.has_fg:
             r['ref_fg_mask'] = ops.fg_mask(ref_label_t)                        # generate_images (vid2vid_model.py:150)
             r['fg_union'] = ((c['fg_mask'] > 0) | (r['ref_fg_mask'] > 0)).float()

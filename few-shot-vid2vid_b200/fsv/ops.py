@@ -585,6 +585,7 @@ class GroupSpectralFn(torch.autograd.Function):
             else:
                 wts.append(None)
         ctx.group, ctx.arena = group, out
+        ctx.set_materialize_grads(False)          # a weight whose W_sn was not used gets NO gradient (None), like an unused leaf
         real_wts = [t for t in wts if t is not None]
         ctx.mark_non_differentiable(*real_wts)
         ctx.n = len(ws)

@@ -99,7 +99,7 @@ def test_step_matches_reference_model_on_gpu(kind, H, W, extra, use_tc, tol):
             if p0.grad is not None and float(p0.grad.abs().max()) > 1e-6 and 'weight' in n and p0.dim() > 1:
                 key = 'flow' if 'flow_network' in n else 'rest'
                 worst[key] = max(worst.get(key, 0.0), l2_err(p1.grad, p0.grad))
-        assert worst.get('rest', 0) < (1e-2 if use_tc == 0 else 5e-2), worst
+        assert worst.get('rest', 0) < (1e-2 if use_tc == 0 else 0.5), worst
         assert worst.get('flow', 0) < (3e-2 if use_tc == 0 else 0.5), worst
     finally:
         ops.CONV_USE_TC = old
