@@ -14,7 +14,17 @@
 #define RED_TY 8
 #define RED_MAX_TICKETS 8192
 
-__device__ unsigned int g_red_ticket[RED_MAX_TICKETS];
+// Tickets of the last-block reductions, one bank per "reduction lane": kernels of one lane must be stream-ordered among themselves,
+// different lanes may run concurrently (the drop-in generator runs its reference-encoder / hyper-network branch on a second stream
+// next to the flow / warp branch; each stream selects its own lane with fsv_set_reduction_lane, a thread-local host setting).
+#define RED_LANES 4
+__device__ unsigned int g_red_ticket[RED_LANES][RED_MAX_TICKETS];
+static thread_local int t_red_lane = 0;
+extern "C" int fsv_set_reduction_lane(int lane) {
+    FSV_REQUIRE(lane >= 0 && lane < RED_LANES, "set_reduction_lane: lane must be in [0, %d)", RED_LANES);
+    t_red_lane = lane;
+    return FSV_OK;
+}
 
 // Generic two-value per-(group, channel) reduction over the rows of an NHWC slice: f(row, c) -> float2.
 // grid (row blocks, 32-channel blocks, groups), block 32 x 8.  Every block leaves its fp64 partials in `part`; the last
@@ -23,7 +33,7 @@ __device__ unsigned int g_red_ticket[RED_MAX_TICKETS];
 // result does not depend on block scheduling.
 template <class F, class E>
 __global__ void __launch_bounds__(RED_TX * RED_TY) k_chan_reduce2(F f, E e, long long rows_per_group, long long rows_per_block, int C,
-                                                                  double* part) {
+                                                                  double* part, int lane) {
     __shared__ double s_a[RED_TY][RED_TX], s_b[RED_TY][RED_TX];
     __shared__ int s_last;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -59,7 +69,7 @@ __global__ void __launch_bounds__(RED_TX * RED_TY) k_chan_reduce2(F f, E e, long
     __threadfence();
     __syncthreads();
     if (tx == 0 && ty == 0) {
-        unsigned int* tk = &g_red_ticket[g * gridDim.y + blockIdx.y];
+        unsigned int* tk = &g_red_ticket[lane][g * gridDim.y + blockIdx.y];
         unsigned int t = atomicAdd(tk, 1u);
         s_last = (t == gridDim.x - 1);
         if (s_last) *tk = 0u;
@@ -109,7 +119,7 @@ static int launch_reduce2(F f, E e, int groups, long long rows_per_group, int C,
     reduce_geometry(groups, rows_per_group, C, &rb, &rpb);
     dim3 grid(rb, fsv_cdiv(C, RED_TX), groups);
     dim3 block(RED_TX, RED_TY);
-    k_chan_reduce2<<<grid, block, 0, st>>>(f, e, rows_per_group, rpb, C, work);
+    k_chan_reduce2<<<grid, block, 0, st>>>(f, e, rows_per_group, rpb, C, work, t_red_lane);
     FSV_CHECK_LAUNCH(name);
     return FSV_OK;
 }

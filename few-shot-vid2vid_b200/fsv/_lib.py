@@ -69,6 +69,7 @@ SIGNATURES = {
     'fsv_conv2d_wgrad_tc_workspace': [_CD],
     'fsv_conv2d_wgrad_tc': [_CD, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
     'fsv_norm_work_doubles': [c_int, c_int, c_ll],
+    'fsv_set_reduction_lane': [c_int],
     'fsv_norm_stats': [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     'fsv_norm_stats_finalize': [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_float, c_float, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
     'fsv_norm_finalize': [c_vp, c_vp, c_int, c_int, c_double, c_double, c_float, c_float, c_vp, c_vp, c_int, c_vp, c_vp, c_vp],

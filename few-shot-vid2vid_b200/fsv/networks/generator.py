@@ -398,11 +398,19 @@ class FewShotGenerator(BaseNetwork):
         nd = self.n_downsample_G
         label_n = ops.to_nhwc(label)
         atn_vis = ref_idx = None
+        branch = None
         if n == 1:
             lref_pick, iref_pick = label_refs[:, 0], img_refs[:, 0]
             lref_n = ops.to_nhwc(lref_pick)
             iref_n = ops.to_nhwc(iref_pick)
-            x, enc_label, norm_w = self.weight_generation(iref_n, lref_n, label_n, t=t)
+            if getattr(ops, 'BRANCH_STREAMS', False) and self.warp_ref and label_n.is_cuda:
+                # reference encoders -> hyper-network -> label embedding on a second stream, concurrent with the flow / warp / image
+                # embedding below (independent until the main branch needs both); joined before the first SPADE block
+                branch = ops.branch_fork(label_n, lref_n, iref_n)
+                with torch.cuda.stream(branch):
+                    x, enc_label, norm_w = self.weight_generation(iref_n, lref_n, label_n, t=t)
+            else:
+                x, enc_label, norm_w = self.weight_generation(iref_n, lref_n, label_n, t=t)
         else:
             # K reference images: encode all b*n, merge by attention, warp the most-attended one (generator.py:396-400,425)
             hh, ww = img_refs.shape[3], img_refs.shape[4]
@@ -444,6 +452,9 @@ class FewShotGenerator(BaseNetwork):
                 enc_label[i] = [enc_label[i], emb_ref[i] if emb_ref is not None else None,
                                 emb_prev[i] if emb_prev is not None else None]
 
+        if branch is not None:
+            flats = [f[0] for nw in (norm_w or []) for f in nw] if norm_w else []
+            ops.branch_join(branch, x, *[m for e in enc_label for m in (e if isinstance(e, list) else [e]) if m is not None], *flats)
         # ---- main branch (generator.py:199-207); the x2 upsample between blocks is folded into the next block
         for i in range(nd, -1, -1):
             nw = norm_w[i] if (self.adap_spade and i < self.n_adaptive_layers) else None

@@ -73,8 +73,44 @@ def _off(t, off_floats):
     return c_vp(t.data_ptr() + 4 * int(off_floats))
 
 
+# Independent branches of a network's forward run on a second stream (the generator's reference-encoder / hyper-network / label-
+# embedding branch next to its flow / warp / image-embedding branch): their kernels are small and latency-bound, so the two
+# chains overlap almost perfectly.  autograd replays each node's backward on the stream its forward ran on, so the backward
+# pass overlaps the same way.  The one-launch reductions keep their tickets in per-lane banks (fsv_set_reduction_lane): the
+# branch stream uses lane 1.  FSV_BRANCH_STREAMS=0 keeps the forward on one stream.
+BRANCH_STREAMS = os.environ.get('FSV_BRANCH_STREAMS', '1') != '0'
+_BRANCH, _LANES = {}, {}
+_LANE_FNS = ('fsv_norm_stats', 'fsv_norm_stats_finalize', 'fsv_norm_apply_bwd', 'fsv_spade_norm_bwd')
+
+
+def branch_fork(*tensors):
+    """-> the branch stream of the current device, waiting for everything enqueued on the current stream so far."""
+    dev = torch.cuda.current_device()
+    s2 = _BRANCH.get(dev)
+    if s2 is None:
+        s2 = _BRANCH[dev] = torch.cuda.Stream(device=dev)
+        _LANES[s2.cuda_stream] = 1
+    s2.wait_stream(torch.cuda.current_stream())
+    for t in tensors:
+        if t is not None:
+            t.record_stream(s2)
+    return s2
+
+
+def branch_join(s2, *tensors):
+    """current stream waits for the branch; ``tensors`` (allocated on the branch stream, consumed on the current one) are registered
+    with the allocator."""
+    cur = torch.cuda.current_stream()
+    cur.wait_stream(s2)
+    for t in tensors:
+        if t is not None:
+            t.record_stream(cur)
+
+
 def _call(fn, *args):
     LAUNCHES[0] += 1
+    if _LANES and fn.__name__ in _LANE_FNS:
+        lib.fsv_set_reduction_lane(_LANES.get(torch.cuda.current_stream().cuda_stream, 0))
     check(fn(*args), fn.__name__)
 
 

@@ -124,6 +124,9 @@ int fsv_conv2d_wgrad_tc(const fsv_conv_desc* d, const float* x, const float* dy,
  * (group, 32-channel block) adds them in a fixed order (deterministic; no memsets, no float atomics).
  * fsv_norm_work_doubles: doubles of workspace such a reduction needs (rows_per_group = N*HW for batch, HW for instance). */
 long long fsv_norm_work_doubles(int groups, int C, long long rows_per_group);
+/* The reductions' tickets come in 4 independent banks ("lanes"): calls issued under different lanes may run concurrently on
+ * different streams; calls of one lane must be stream-ordered.  Thread-local host setting, default lane 0. */
+int fsv_set_reduction_lane(int lane);
 /* per-(group, channel) sum and sum of squares of an NHWC slice; groups = 1 (batch) or N (instance).
  * Outputs are DOUBLE [groups*C]; work: fsv_norm_work_doubles(groups, C, rows_per_group) doubles. */
 int fsv_norm_stats(const float* x, int N, int HW, int C, int ld, int coff, int mode, double* sum, double* sumsq, double* work,
