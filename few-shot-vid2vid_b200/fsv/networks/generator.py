@@ -6,9 +6,14 @@ result (generator.py:181,229), same attribute / state_dict names, same ``init_te
 and eval-mode weight cache.  Internally activations are NHWC fp32 and every op is a call into
 libfsv_b200.so; boundary tensors are NCHW like the reference (outputs are NCHW-shaped views).
 
-In scope (SURVEY.md section 8a): ``--adaptive_spade`` (+ ``--warp_ref``, ``--spade_combine``),
-``use_label_ref='mul'``, ``netS='encoderdecoder'``, ``sc_arch='unet'``, K=1 reference image,
-the temporal (``warp_prev``) inputs.  Out-of-scope options raise NotImplementedError.
+In scope (SURVEY.md section 8a/8f): ``--adaptive_spade`` (+ ``--warp_ref``, ``--spade_combine``),
+``use_label_ref='mul'``, ``netS='encoderdecoder'``, ``sc_arch='unet'``, K >= 1 reference images (``n_shot``: attention
+merge + picked reference, generator.py:298-316), the temporal (``warp_prev``) inputs, face / pose / street label widths.
+Out-of-scope options raise NotImplementedError.
+
+Execution structure of a forward (all capturable into one CUDA graph): one grouped spectral-norm launch triple up front
+(layers.SpectralPlanner); the reference-encoder / hyper-network / label-embedding branch on a second stream concurrent with
+the flow / warp / image-embedding branch (ops.branch_fork / branch_join); then the SPADE main branch.
 """
 import torch
 import torch.nn as nn

@@ -1,9 +1,7 @@
-"""Hardware checks for kernels that are NOT on the default path yet (round-2 candidates written after the round-1 GPU
-budget was spent).  Skipped unless FSV_TEST_EXPERIMENTAL=1: they have not run on a B200 yet, so they must not gate the
-suite; the first GPU session of round 2 runs them (under `timeout`) before anything selects those kernels by default.
-
-    FSV_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -m gpu -q
-"""
+"""Network geometries beyond the face goldens (pose-like, street-like, K = 2 attention) against the reference's own outputs, and the
+non-default kernel variants (one-tile-per-CTA tcgen05 conv, per-module spectral norm, single-stream execution) through the
+tensor-core / network test files in a subprocess (the switches are read once per process).  All of these ran green on the B200 in
+round 2 (they were opt-in bring-up tests at the end of round 1)."""
 import os
 import subprocess
 import sys
@@ -11,17 +9,16 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('FSV_TEST_EXPERIMENTAL') != '1',
-                                 reason='experimental kernels: set FSV_TEST_EXPERIMENTAL=1 (round-2 bring-up)')]
+pytestmark = pytest.mark.gpu
 
 
-def test_persistent_conv_kernel_matches_default_path():
-    """k_conv_tc_p (persistent CTAs, double-buffered TMEM accumulator; conv_tc.cu) against the default k_conv_tc through
-    the whole tensor-core test file: the env switch is read once per process, hence the subprocess."""
-    env = dict(os.environ, FSV_TC_PERSIST='1')
-    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_tc.py'), '-m', 'gpu', '-q', '-x',
-                        '--timeout', '120', '-p', 'no:cacheprovider'], env=env, capture_output=True, text=True, timeout=600)
+@pytest.mark.parametrize('env', [{'FSV_TC_PERSIST': '0'}, {'FSV_GROUP_SPECTRAL': '0', 'FSV_WGRAD_SIDE': '0', 'FSV_BRANCH_STREAMS': '0', 'FSV_TC_BN_OCC': '0'}])
+def test_non_default_kernel_variants(env):
+    """FSV_TC_PERSIST=0: k_conv_tc (one tile per CTA) instead of the persistent double-buffered k_conv_tc_p; second case: per-module
+    spectral norm, everything on one stream, no occupancy-aware N tile -- the round-1 execution structure."""
+    files = [os.path.join(ROOT, 'tests', f) for f in ('test_gpu_tc.py', 'test_gpu_nets.py')]
+    r = subprocess.run([sys.executable, '-m', 'pytest'] + files + ['-m', 'gpu', '-q', '-x', '--timeout', '300', '-p', 'no:cacheprovider'],
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
@@ -29,7 +26,7 @@ def test_persistent_conv_kernel_matches_default_path():
 def test_generator_other_geometries_vs_reference_golden(name):
     """The drop-in generator in the pose-like (6-channel, portrait H = 2W, warp + spade_combine) and street-like (wide
     W = 2H, no flow branch) configurations against the reference's own outputs (tests/golden/g_variants_tiny.npz, pinned
-    for the oracle on CPU in test_oracle_golden.py).  Written without GPU access at the end of round 1."""
+    for the oracle on CPU in test_oracle_golden.py)."""
     import json
     from argparse import Namespace
     import torch
@@ -69,7 +66,7 @@ def test_generator_other_geometries_vs_reference_golden(name):
 def test_generator_two_reference_images_vs_reference_golden():
     """K = 2 attention path of the drop-in generator (attention GEMMs as per-sample 1x1 convs + channel softmax of the
     C ABI) against the reference (tests/golden/g_kshot_tiny.npz; the oracle is pinned to the same file on CPU).
-    Written without GPU access at the end of round 1."""
+    """
     import torch
     from fsv import networks, ops
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
