@@ -14,7 +14,7 @@ timeout 900 python bench.py --steps 10 --warmup 3 --breakdown gpurun_out/bd3_pos
 # ncu: launch list of one eager step (cold-cache, serialised: shares only), then full captures of the dominant kernels
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 9000 --csv --log-file gpurun_out/launches_r2.csv \
     python bench.py --quick --no-graph --steps 1 --warmup 1 > gpurun_out/ncu_launch_r2.log 2>&1; echo "ncu launch list rc=$?"; tail -1 gpurun_out/ncu_launch_r2.log
-for spec in "k_conv_tc_p:4:3:prof_conv_tc_r2" "k_spade_tc:20:2:prof_spade_tc_r2" "k_wgrad_tc_mn:30:2:prof_wgrad_tc_r2"; do
+for spec in "k_conv_tc_p:4:3:prof_conv_tc_r2" "k_spade_tc:14:4:prof_spade_tc_r2" "k_wgrad_tc_mn:30:2:prof_wgrad_tc_r2"; do
     IFS=: read -r kern skip cnt out <<< "$spec"
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kern -s $skip -c $cnt -o gpurun_out/$out -f \
         python bench.py --quick --no-graph --steps 1 --warmup 0 > gpurun_out/ncu_$out.log 2>&1
