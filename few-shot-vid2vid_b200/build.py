@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'fsv', 'libfsv_b200.so')
-SOURCES = ['core.cu', 'layout.cu', 'norm.cu', 'conv_simt.cu', 'conv_tc.cu', 'wgrad_tc.cu', 'conv_dispatch.cu', 'thin.cu', 'spade.cu', 'spade_tc.cu', 'warp.cu', 'softmax.cu', 'spectral.cu', 'preproc.cu', 'optim.cu']
+SOURCES = ['core.cu', 'layout.cu', 'norm.cu', 'conv_simt.cu', 'conv_tc.cu', 'wgrad_tc.cu', 'conv_dispatch.cu', 'thin.cu', 'spade.cu', 'spade_tc.cu', 'warp.cu', 'softmax.cu', 'spectral.cu', 'preproc.cu', 'optim.cu', 'losses.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math' if False else '-DFSV_NO_FAST_MATH',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default']

@@ -38,6 +38,11 @@ class SnItem(ctypes.Structure):
                 ('out_off', c_ll), ('wt_off', c_ll), ('uvs_off', c_ll), ('work_off', c_ll)]
 
 
+class FlowMaskDesc(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ('warp0', 'mask0', 'warp1', 'mask1', 'tgt', 'fake', 'ref_body_warp', 'body', 'ref_fg_warp', 'fg', 'face_avg',
+                                     'fg_diff')] + [('B', c_int), ('H', c_int), ('W', c_int)]
+
+
 class AdamItem(ctypes.Structure):
     _fields_ = [('param', c_vp), ('grad', c_vp), ('exp_avg', c_vp), ('exp_avg_sq', c_vp), ('numel', c_ll)]
 
@@ -93,6 +98,11 @@ SIGNATURES = {
     'fsv_spectral_group_fwd': [c_vp, c_vp, c_vp, c_int, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
     'fsv_adam_chunks': [c_ll],
     'fsv_adam_step': [c_vp, c_vp, c_ll, c_vp, c_float, c_float, c_float, c_float, c_vp],
+    'fsv_flow_mask_loss_work_doubles': [],
+    'fsv_flow_mask_loss_fwd': [c_vp, c_vp, c_vp, c_vp],
+    'fsv_flow_mask_loss_bwd': [c_vp] * 10 + [c_vp],
+    'fsv_halves_l1_fwd': [c_vp, c_ll, c_vp, c_vp, c_vp],
+    'fsv_halves_l1_bwd': [c_vp, c_ll, c_vp, c_vp, c_vp],
     'fsv_fg_mask': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_float, c_vp],
     'fsv_face_mask_avg15': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp],
     'fsv_part_masks': [c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp],
@@ -115,6 +125,7 @@ def _load():
     lib.fsv_spectral_workspace.restype = c_ll
     lib.fsv_norm_work_doubles.restype = c_ll
     lib.fsv_adam_chunks.restype = c_ll
+    lib.fsv_flow_mask_loss_work_doubles.restype = c_ll
     lib.fsv_last_error.argtypes = []
     lib.fsv_last_error.restype = ctypes.c_char_p
     return lib

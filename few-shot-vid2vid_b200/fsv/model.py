@@ -84,22 +84,6 @@ def _gan_loss(preds, target_is_real):
     return loss / len(preds)
 
 
-def _feat_match(pred_real, pred_fake, lambda_feat):
-    """loss_collector.py:206-215."""
-    num_d = len(pred_fake)
-    loss = 0
-    for i in range(num_d):
-        for j in range(len(pred_fake[i]) - 1):
-            loss = loss + F.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) / num_d
-    return loss * lambda_feat
-
-
-def _masked_l1(a, b, m):
-    """loss.py:130-138 MaskedL1Loss."""
-    m = m.expand_as(a)
-    return F.l1_loss(a * m, b * m)
-
-
 def _split(pred):
     """base_model.py:141-147 divide_pred."""
     fake = [[t[:t.size(0) // 2] for t in p] for p in pred]
@@ -260,11 +244,19 @@ class Vid2VidStep:
         pf, pr = _split(pred)
         if for_discriminator:
             return [_gan_loss(pr, True), _gan_loss(pf, False)]
-        return [_gan_loss(pf, True), self._gan_feat(pr, pf)]
+        return [_gan_loss(pf, True), self._gan_feat(pred)]
 
-    def _gan_feat(self, pr, pf):
-        z = pf[0][0].new_zeros(1)
-        return z if self.opt.no_ganFeat_loss else z + _feat_match(pr, pf, self.opt.lambda_feat)
+    def _gan_feat(self, pred):
+        """loss_collector.py:206-215 on the UNSPLIT predictions (batch [fake ; real]): one fused L1 per feature map."""
+        z = pred[0][0].new_zeros(1)
+        if self.opt.no_ganFeat_loss:
+            return z
+        num_d = len(pred)
+        loss = z
+        for p in pred:
+            for f in p[:-1]:
+                loss = loss + ops.halves_l1(f.permute(0, 2, 3, 1)) / num_d
+        return loss * self.opt.lambda_feat
 
     def _face_boxes(self, c, r):
         """face_refiner.py:52-83 via fsv_face_bbox.  Target box from tgt_label; reference box from the reference label AS
@@ -296,11 +288,12 @@ class Vid2VidStep:
         real_region, ref_region = r['face_static']
         fake_region = ops.crop_resize(fake, tb, S)                                   # NHWC (B, S, S, 3)
         x = ops.cat_channels(torch.cat([ref_region, ref_region], 0), torch.cat([fake_region, real_region], 0))
-        pf, pr = _split(self.netDf.forward_nhwc(x))
+        pred_f = self.netDf.forward_nhwc(x)
+        pf, pr = _split(pred_f)
         lam = self.opt.lambda_face
         if for_discriminator:
             return [_gan_loss(pr, True) * lam, _gan_loss(pf, False) * lam]
-        g_gan, g_feat = _gan_loss(pf, True) * lam, self._gan_feat(pr, pf) * lam
+        g_gan, g_feat = _gan_loss(pf, True) * lam, self._gan_feat(pred_f) * lam
         g_feat = g_feat + F.l1_loss(fake_region, real_region) * self.opt.lambda_feat       # + criterionVGG * lambda_vgg == 0 (--no_vgg_loss)
         return [g_gan, g_feat]
 
@@ -316,10 +309,11 @@ class Vid2VidStep:
         if t != self.tD:
             raise NotImplementedError('temporal discriminator with n_frames_G != n_frames_D')
         x = torch.cat([fake_all.reshape(bs, ch * t, h, w), real_all.reshape(bs, ch * t, h, w)], dim=0)
-        pf, pr = _split(self.netDT(x))
+        pred_t = self.netDT(x)
+        pf, pr = _split(pred_t)
         if for_discriminator:
             return [_gan_loss(pr, True), _gan_loss(pf, False)]
-        return [_gan_loss(pf, True) * self.opt.lambda_temp, self._gan_feat(pr, pf) * self.opt.lambda_temp]
+        return [_gan_loss(pf, True) * self.opt.lambda_temp, self._gan_feat(pred_t) * self.opt.lambda_temp]
 
     # -------------------------------------------------------------------------------------------- the two steps
     def discriminator_losses(self, batch, c=None):
@@ -344,42 +338,29 @@ class Vid2VidStep:
             g = self._discriminate(c, r, fake, False) + self._discriminate_face(c, r, fake, False)
         tgt = c['tgt_image']
 
-        # ---- flow losses (loss_collector.py:131-163): F_Flow = 0 (--no_flow_gt)
-        f_warp = z
-        for k in (0, 1):
-            if flow[k] is not None:
-                f_warp = f_warp + F.l1_loss(warp[k], tgt)
-        body_diff = None
-        if self.pose and flow[0] is not None:
-            flow_ref = flow[0].permute(0, 2, 3, 1)                                  # NHWC view of the generator's NHWC flow
+        # ---- flow + mask losses (loss_collector.py:131-204; F_Flow = 0 under --no_flow_gt): ONE fused pass forward, one backward
+        # (ops.flow_mask_losses).  Frame tensors are handed over as NHWC (the generator's native layout; its NCHW outputs are views).
+        nhwc = lambda t: None if t is None else t.permute(0, 2, 3, 1)   # noqa: E731
+        pose_terms = self.pose and flow[0] is not None
+        rbw = body = rfw = fg = None
+        if pose_terms:
+            flow_ref = nhwc(flow[0])
             body = ops.part_masks(c['tgt_label'])                                   # (B, H, W, 9)
-            ref_body = ops.part_masks(r['ref_label_valid'])
-            ref_body_warp = ops.warp_concat(ref_body, flow_ref, None)
-            f_warp = f_warp + F.l1_loss(ref_body_warp, body)
+            rbw = ops.warp_concat(ops.part_masks(r['ref_label_valid']), flow_ref, None)   # resample(ref_body_mask, flow) (:144-145)
             if self.has_fg:
-                fg, ref_fg = c['fg_mask'], r['ref_fg_mask_v']
-                ref_fg_warp = ops.warp_concat(ref_fg.permute(0, 2, 3, 1), flow_ref, None)
-                f_warp = f_warp + F.l1_loss(ref_fg_warp.permute(0, 3, 1, 2), fg)
-            body_diff = torch.sum(abs(ref_body_warp - body), dim=3, keepdim=True).permute(0, 3, 1, 2)
-        f_warp = f_warp * opt.lambda_flow
-
-        # ---- mask losses (loss_collector.py:165-204)
-        f_mask = z
-        for k in (0, 1):
-            if fmask[k] is not None:
-                conf = torch.clamp(1 - torch.sum(abs(warp[k] - tgt), dim=1, keepdim=True), 0, 1)
-                f_mask = f_mask + _masked_l1(fmask[k], torch.zeros_like(fmask[k]), conf)
-                f_mask = f_mask + _masked_l1(fmask[k], torch.ones_like(fmask[k]), 1 - conf)
-        if self.pose and getattr(self.netG, 'warp_ref', False):
-            m0 = fmask[0]
-            face_avg = ops.face_mask_avg15(c['tgt_label'])
-            f_mask = f_mask + _masked_l1(m0, torch.zeros_like(m0), face_avg)
-            if opt.spade_combine:
-                f_mask = f_mask + _masked_l1(fake, warp[0].detach(), face_avg)
-            fg_diff = ((r['ref_fg_mask'] - c['fg_mask']) > 0).float()               # the masks of generate_images (vid2vid_model.py:95-96)
-            f_mask = f_mask + _masked_l1(m0, torch.ones_like(m0), fg_diff)
-            f_mask = f_mask + _masked_l1(m0, torch.ones_like(m0), body_diff)
-        f_mask = f_mask * opt.lambda_mask
+                fg = nhwc(c['fg_mask'])
+                rfw = ops.warp_concat(nhwc(r['ref_fg_mask_v']), flow_ref, None)            # (:148-150)
+        face_avg = fg_diff = fake_t = None
+        if self.pose and getattr(self.netG, 'warp_ref', False) and fmask[0] is not None:
+            face_avg = nhwc(ops.face_mask_avg15(c['tgt_label']))                    # (:176-179)
+            fg_diff = nhwc(((r['ref_fg_mask'] - c['fg_mask']) > 0).float())        # the masks of generate_images (vid2vid_model.py:95-96)
+            fake_t = nhwc(fake) if opt.spade_combine else None
+        if flow[0] is None and flow[1] is None:
+            f_warp = f_mask = z
+        else:
+            fm = ops.flow_mask_losses(nhwc(warp[0]), nhwc(fmask[0]), nhwc(warp[1]), nhwc(fmask[1]), tgt, fake_t, rbw, body, rfw, fg, face_avg, fg_diff)
+            f_warp = fm[0:1] * opt.lambda_flow
+            f_mask = fm[1:2] * opt.lambda_mask
 
         vals = [g[0], g[1], z, g[2], g[3], gt[0], gt[1], z, f_warp, f_mask]
         return dict(zip(LOSS_NAMES_G, vals)), fake, prevs_new

@@ -1137,3 +1137,80 @@ class DInputFn(torch.autograd.Function):
 
 def d_input(base, fake, coff):
     return DInputFn.apply(base, fake, coff)
+
+
+# --------------------------------------------------------------------------- fused generator-step losses
+class FlowMaskLossFn(torch.autograd.Function):
+    """loss_collector.py:131-204 in one forward and one backward pass over the frame (csrc/losses.cu).  Inputs (None = absent):
+    warp0, mask0, warp1, mask1 (NHWC), tgt (NCHW), fake (NHWC), ref_body_warp, body (NHWC, 9 ch), ref_fg_warp, fg, face_avg, fg_diff
+    (one channel).  -> tensor (2,) = [F_Warp / lambda_flow, F_Mask / lambda_mask]."""
+
+    NAMES = ('warp0', 'mask0', 'warp1', 'mask1', 'tgt', 'fake', 'ref_body_warp', 'body', 'ref_fg_warp', 'fg', 'face_avg', 'fg_diff')
+
+    @staticmethod
+    def forward(ctx, *ts):
+        ts = [_c(t.detach()) if t is not None else None for t in ts]
+        tgt = ts[4]
+        b, _, h, w = tgt.shape
+        d = _lib.FlowMaskDesc()
+        for name, t in zip(FlowMaskLossFn.NAMES, ts):
+            setattr(d, name, None if t is None else t.data_ptr())
+        d.B, d.H, d.W = b, h, w
+        out = torch.empty(2, device=tgt.device, dtype=torch.float32)
+        work = torch.empty(int(lib.fsv_flow_mask_loss_work_doubles()), device=tgt.device, dtype=torch.float64)
+        _call(lib.fsv_flow_mask_loss_fwd, ctypes.byref(d), ptr(out), ptr(work), stream())
+        ctx.save_for_backward(*[t for t in ts if t is not None])
+        ctx.present = [t is not None for t in ts]
+        ctx.dims = (b, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        it = iter(ctx.saved_tensors)
+        ts = [next(it) if pr else None for pr in ctx.present]
+        b, h, w = ctx.dims
+        d = _lib.FlowMaskDesc()
+        for name, t in zip(FlowMaskLossFn.NAMES, ts):
+            setattr(d, name, None if t is None else t.data_ptr())
+        d.B, d.H, d.W = b, h, w
+        gout = _c(gout)
+        dev = gout.device
+
+        def buf(t, want=True):
+            return torch.empty_like(t) if (t is not None and want) else None
+        dw0, dm0, dw1, dm1 = buf(ts[0]), buf(ts[1]), buf(ts[2]), buf(ts[3])
+        dfake = buf(ts[5], ts[10] is not None)
+        drbw, drfw = buf(ts[6]), buf(ts[8])
+        _call(lib.fsv_flow_mask_loss_bwd, ctypes.byref(d), ptr(gout), _off(gout, 1), ptr(dw0), ptr(dw1), ptr(dm0), ptr(dm1), ptr(dfake), ptr(drbw),
+              ptr(drfw), stream())
+        return dw0, dm0, dw1, dm1, None, dfake, drbw, None, drfw, None, None, None
+
+
+def flow_mask_losses(warp0, mask0, warp1, mask1, tgt, fake, ref_body_warp, body, ref_fg_warp, fg, face_avg, fg_diff):
+    return FlowMaskLossFn.apply(warp0, mask0, warp1, mask1, tgt, fake, ref_body_warp, body, ref_fg_warp, fg, face_avg, fg_diff)
+
+
+class HalvesL1Fn(torch.autograd.Function):
+    """mean |x[:B] - x[B:].detach()| for a contiguous tensor whose first dimension is the batch [fake ; real] (loss_collector.py:206-215)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        half = x.numel() // 2
+        out = torch.empty(1, device=x.device, dtype=torch.float32)
+        work = torch.empty(1024, device=x.device, dtype=torch.float64)
+        _call(lib.fsv_halves_l1_fwd, ptr(x), half, ptr(out), ptr(work), stream())
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _c(g)
+        dx = torch.empty_like(x)
+        _call(lib.fsv_halves_l1_bwd, ptr(x), x.numel() // 2, ptr(g), ptr(dx), stream())
+        return dx
+
+
+def halves_l1(x):
+    return HalvesL1Fn.apply(x)

@@ -261,6 +261,24 @@ long long fsv_adam_chunks(long long numel);
 int fsv_adam_step(const fsv_adam_item* items_dev, const int* chunks_dev, long long nchunks, float* step_dev, float lr,
                   float beta1, float beta2, float eps, void* stream);
 
+/* ------------------------------------------------------------------ fused generator-step losses (loss_collector.py:131-215) */
+/* Flow / mask losses in one pass (see csrc/losses.cu for the formulas).  All frame tensors NHWC contiguous except tgt (NCHW);
+ * absent inputs are NULL: warp1/mask1 (no previous-frame branch), fake + face_avg + fg_diff (non-pose), ref_body_warp/body,
+ * ref_fg_warp/fg.  out2 = {F_Warp / lambda_flow, F_Mask / lambda_mask}; work: fsv_flow_mask_loss_work_doubles() doubles. */
+typedef struct fsv_flow_mask_desc {
+    const float *warp0, *mask0, *warp1, *mask1, *tgt, *fake, *ref_body_warp, *body, *ref_fg_warp, *fg, *face_avg, *fg_diff;
+    int B, H, W;
+} fsv_flow_mask_desc;
+long long fsv_flow_mask_loss_work_doubles(void);
+int fsv_flow_mask_loss_fwd(const fsv_flow_mask_desc* d, float* out2, double* work, void* stream);
+/* g_warp / g_mask: device scalars = d(total loss)/d(out2[0]), d(total loss)/d(out2[1]) */
+int fsv_flow_mask_loss_bwd(const fsv_flow_mask_desc* d, const float* g_warp, const float* g_mask, float* dwarp0, float* dwarp1,
+                           float* dmask0, float* dmask1, float* dfake, float* dref_body_warp, float* dref_fg_warp, void* stream);
+/* Feature matching (loss_collector.py:206-215): x = one discriminator feature for the batch [fake ; real] (contiguous, `half`
+ * elements per half); out[0] = mean |x[:half] - x[half:]|; backward writes g * sign / half into dx[:half] and zeros into dx[half:]. */
+int fsv_halves_l1_fwd(const float* x, long long half, float* out, double* work, void* stream);
+int fsv_halves_l1_bwd(const float* x, long long half, const float* g, float* dx, void* stream);
+
 /* ------------------------------------------------------------------ pose label preprocessing + face region */
 /* (MaxPool2d(15, stride 1, pad 7)(plane) > thr).float(): get_fg_mask, models/input_process.py:52-61.  plane n starts at
  * label + n*n_stride (pass the address of channel 2 of an NCHW label and n_stride = C*H*W); out (N, H, W). */

@@ -255,3 +255,42 @@ class SpectralGroup:
 def spectral_group_weights(group, training, eps, w_origs):
     ws = [spectral_weight(w, u, v, training, eps) for w, u, v, _ in group.entries]
     return ws, [None] * group.n
+
+
+
+# ------------------------------------------------------------------ fused generator-step losses: the reference formulas in torch
+def _masked_l1(a, b, m):
+    m = m.expand_as(a)
+    return F.l1_loss(a * m, b * m)
+
+
+def flow_mask_losses(warp0, mask0, warp1, mask1, tgt, fake, ref_body_warp, body, ref_fg_warp, fg, face_avg, fg_diff):
+    """loss_collector.py:131-204 (values before the lambda factors); frame tensors NHWC, tgt NCHW."""
+    tg = tgt.permute(0, 2, 3, 1)
+    f_warp = tgt.new_zeros(())
+    f_mask = tgt.new_zeros(())
+    for wp, m in ((warp0, mask0), (warp1, mask1)):
+        if wp is None:
+            continue
+        f_warp = f_warp + F.l1_loss(wp, tg)
+        conf = torch.clamp(1 - torch.sum(abs(wp - tg), dim=3, keepdim=True), 0, 1)
+        f_mask = f_mask + _masked_l1(m, torch.zeros_like(m), conf) + _masked_l1(m, torch.ones_like(m), 1 - conf)
+    body_diff = None
+    if ref_body_warp is not None:
+        f_warp = f_warp + F.l1_loss(ref_body_warp, body)
+        body_diff = torch.sum(abs(ref_body_warp - body), dim=3, keepdim=True)
+    if ref_fg_warp is not None:
+        f_warp = f_warp + F.l1_loss(ref_fg_warp, fg)
+    if face_avg is not None:
+        f_mask = f_mask + _masked_l1(mask0, torch.zeros_like(mask0), face_avg)
+        if fake is not None:
+            f_mask = f_mask + _masked_l1(fake, warp0.detach(), face_avg)
+        f_mask = f_mask + _masked_l1(mask0, torch.ones_like(mask0), fg_diff)
+        if body_diff is not None:
+            f_mask = f_mask + _masked_l1(mask0, torch.ones_like(mask0), body_diff)
+    return torch.stack([f_warp, f_mask])
+
+
+def halves_l1(x):
+    b = x.shape[0] // 2
+    return F.l1_loss(x[:b], x[b:].detach()).view(1)

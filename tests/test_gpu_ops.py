@@ -509,3 +509,57 @@ def test_own_adam_matches_torch_adam_eager_and_graphed():
     for a, b in zip(pa, pb):
         assert rel_err(a, b) < 1e-6
     assert float(oa.state[pa[0]]['step']) == 5
+
+
+@pytest.mark.parametrize('case', ['face', 'temporal', 'pose', 'pose_no_combine'])
+def test_fused_flow_mask_losses_vs_reference_formulas(case):
+    """fsv_flow_mask_loss_fwd/bwd (one pass each) against the reference's formulas written out in torch (tests/mock_ops.py:
+    loss_collector.py:131-204 term by term) on the same GPU tensors, float64 for the check: both loss values and every gradient."""
+    from fsv import ops
+    import mock_ops
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 2, 48, 40
+    rnd = lambda *s: torch.rand(*s, generator=g)                      # noqa: E731
+    tgt = rnd(B, 3, H, W) * 2 - 1
+    mk = lambda c, lo=-1.0, hi=1.0: (rnd(B, H, W, c) * (hi - lo) + lo)   # noqa: E731
+    # warped frames close to the target on part of the image so that conf covers 0, (0, 1) and 1
+    near = tgt.permute(0, 2, 3, 1) + (rnd(B, H, W, 3) - 0.5) * 0.3
+    w0 = torch.where(rnd(B, H, W, 1) < 0.5, near, mk(3))
+    w1 = torch.where(rnd(B, H, W, 1) < 0.5, near, mk(3)) if case == 'temporal' else None
+    m0, m1 = mk(1, 0.0, 1.0), (mk(1, 0.0, 1.0) if case == 'temporal' else None)
+    pose = case.startswith('pose')
+    fake = mk(3) if case == 'pose' else None
+    body = (rnd(B, H, W, 9) < 0.2).float() if pose else None
+    rbw = mk(9, 0.0, 1.0) if pose else None
+    fgm = (rnd(B, H, W, 1) < 0.5).float() if pose else None
+    rfw = mk(1, 0.0, 1.0) if pose else None
+    fa = mk(1, 0.0, 1.0) if pose else None
+    fgd = (rnd(B, H, W, 1) < 0.3).float() if pose else None
+    args = [w0, m0, w1, m1, tgt, fake, rbw, body, rfw, fgm, fa, fgd]
+    need = [True, True, True, True, False, True, True, False, True, False, False, False]
+    ref_in = [None if t is None else t.double().requires_grad_(n) for t, n in zip(args, need)]
+    ref = mock_ops.flow_mask_losses(*ref_in)
+    coef = torch.tensor([3.0, 7.0], dtype=torch.float64)
+    (ref * coef).sum().backward()
+    gpu_in = [None if t is None else t.cuda().requires_grad_(n) for t, n in zip(args, need)]
+    out = ops.flow_mask_losses(*gpu_in)
+    assert rel_err(out, ref.detach()) < 1e-5
+    (out * coef.float().cuda()).sum().backward()
+    for a, b, n in zip(gpu_in, ref_in, need):
+        if a is not None and n:
+            assert b.grad is not None and a.grad is not None
+            assert grad_err(a.grad, b.grad, floor=1e-9) < 1e-4
+
+
+def test_fused_feature_matching_halves_l1():
+    from fsv import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(6, 9, 11, 32, generator=g)
+    xr = x.double().requires_grad_(True)
+    ref = torch.nn.functional.l1_loss(xr[:3], xr[3:].detach())
+    (ref * 2.5).backward()
+    xg = x.cuda().requires_grad_(True)
+    out = ops.halves_l1(xg)
+    assert rel_err(out, ref.detach().view(1)) < 1e-6
+    (out * 2.5).sum().backward()
+    assert grad_err(xg.grad, xr.grad, floor=1e-12) < 1e-5
