@@ -23,6 +23,7 @@ def child(impl, size, K, frames):
     import synth
     opt = refenv.parse_opt('face', size, size, 1, extra=['--n_shot', str(K)] if K > 1 else [], gpu=True, train=False)
     opt.isTrain = False
+    opt.for_face = False                      # set by BaseModel.define_networks in the reference (base_model.py:172)
     if impl == 'fsv':
         from fsv import networks
     else:
