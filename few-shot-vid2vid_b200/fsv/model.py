@@ -316,22 +316,25 @@ class Vid2VidStep:
         return [_gan_loss(pf, True) * self.opt.lambda_temp, self._gan_feat(pred_t) * self.opt.lambda_temp]
 
     # -------------------------------------------------------------------------------------------- the two steps
-    def discriminator_losses(self, batch, c=None):
-        """vid2vid_model.py:106-128.  -> dict in LOSS_NAMES_D order (absent temporal terms omitted, like the reference's list)."""
+    def discriminator_losses(self, batch, c=None, gen=None):
+        """vid2vid_model.py:106-128.  -> dict in LOSS_NAMES_D order (absent temporal terms omitted, like the reference's list).
+        ``gen``: the result of ``generate(c)`` under no_grad when the caller already ran it (trainer: on another stream)."""
         c = self.prepare(batch) if c is None else c
-        with torch.no_grad():
-            fake, _, _, _, r, _, _ = self.generate(c)
+        if gen is None:
+            with torch.no_grad():
+                gen = self.generate(c)
+        fake, r = gen[0], gen[4]
         fake = fake.detach()
         d = self._discriminate(c, r, fake, True) + self._discriminate_face(c, r, fake, True)
         t = self._temporal_gan(c, fake, True)
         names = LOSS_NAMES_D[:4] + (LOSS_NAMES_D[4:] if t else [])
         return dict(zip(names, d + (t or [])))
 
-    def generator_losses(self, batch, c=None):
-        """vid2vid_model.py:62-104.  -> (dict in LOSS_NAMES_G order, fake image, prevs_new)."""
+    def generator_losses(self, batch, c=None, gen=None):
+        """vid2vid_model.py:62-104.  -> (dict in LOSS_NAMES_G order, fake image, prevs_new).  ``gen``: a ``generate(c)`` result (with grad)."""
         opt = self.opt
         c = self.prepare(batch) if c is None else c
-        fake, flow, fmask, warp, r, prevs_new, _ = self.generate(c)
+        fake, flow, fmask, warp, r, prevs_new, _ = self.generate(c) if gen is None else gen
         z = fake.new_zeros(1)
         with _frozen(self.d_modules()):
             gt = self._temporal_gan(c, fake, False)

@@ -83,13 +83,21 @@ _BRANCH, _LANES = {}, {}
 _LANE_FNS = ('fsv_norm_stats', 'fsv_norm_stats_finalize', 'fsv_norm_apply_bwd', 'fsv_spade_norm_bwd')
 
 
-def branch_fork(*tensors):
-    """-> the branch stream of the current device, waiting for everything enqueued on the current stream so far."""
-    dev = torch.cuda.current_device()
-    s2 = _BRANCH.get(dev)
+def aux_stream(index):
+    """Auxiliary stream ``index`` (1 = generator branch, 2 = discriminator step) of the current device; its one-launch reductions use
+    ticket lane ``index``."""
+    key = (torch.cuda.current_device(), index)
+    s2 = _BRANCH.get(key)
     if s2 is None:
-        s2 = _BRANCH[dev] = torch.cuda.Stream(device=dev)
-        _LANES[s2.cuda_stream] = 1
+        s2 = _BRANCH[key] = torch.cuda.Stream(device=key[0])
+        _LANES[s2.cuda_stream] = index
+    return s2
+
+
+def branch_fork(*tensors, index=1):
+    """-> auxiliary stream ``index``, made to wait for everything enqueued on the current stream so far; ``tensors`` (allocated on the
+    current stream, about to be read on the auxiliary one) are registered with the allocator."""
+    s2 = aux_stream(index)
     s2.wait_stream(torch.cuda.current_stream())
     for t in tensors:
         if t is not None:

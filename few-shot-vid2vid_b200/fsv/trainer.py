@@ -57,12 +57,31 @@ def loss_backward(losses, optimizer, grad_sync=None):
     return loss
 
 
+# The discriminator update (D / face D / temporal D forward, backward, Adam) only needs the no-grad frame; the generator update's own
+# generator forward needs neither it nor the new discriminator weights until its discriminator forward.  With FSV_DSTEP_STREAM=1 the
+# discriminator update runs on a second stream concurrently with that generator forward (a parallel branch of the CUDA graph).
+DSTEP_STREAM = os.environ.get('FSV_DSTEP_STREAM', '0') != '0'
+
+
 def train_iteration(step, optG, optD, batch, sync_G=None, sync_D=None):
     """train.py:58-62 for one frame: discriminator update, then generator update.  -> (d_losses, g_losses, fake, prevs_new)"""
+    from . import ops
     c = step.prepare(batch)
-    d_losses = step.discriminator_losses(batch, c)
-    loss_backward(d_losses, optD, sync_D)
-    g_losses, fake, prevs = step.generator_losses(batch, c)
+    if not (DSTEP_STREAM and batch['tgt_image'].is_cuda):
+        d_losses = step.discriminator_losses(batch, c)
+        loss_backward(d_losses, optD, sync_D)
+        g_losses, fake, prevs = step.generator_losses(batch, c)
+        loss_backward(g_losses, optG, sync_G)
+        return d_losses, g_losses, fake, prevs
+    with torch.no_grad():
+        gen_d = step.generate(c)                      # generator forward #1 (spectral u/v, BN statistics advance): main stream
+    s3 = ops.branch_fork(gen_d[0], index=2)
+    with torch.cuda.stream(s3):
+        d_losses = step.discriminator_losses(batch, c, gen=gen_d)
+        loss_backward(d_losses, optD, sync_D)
+    gen_g = step.generate(c)                          # generator forward #2, concurrent with the discriminator update
+    ops.branch_join(s3, *d_losses.values())           # the new discriminator weights are needed from here on
+    g_losses, fake, prevs = step.generator_losses(batch, c, gen=gen_g)
     loss_backward(g_losses, optG, sync_G)
     return d_losses, g_losses, fake, prevs
 
