@@ -221,7 +221,10 @@ def run_fsv(args):
     rank, world, local_rank = parallel.init_from_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    torch.cuda.set_stream(torch.cuda.Stream())      # everything (eager, capture, replay, timing events) on one non-default stream
+    # the compute stream (eager, capture, replay, timing events): non-default, and HIGH priority so that the critical path (forward and
+    # data-gradient chains) is scheduled ahead of the side streams' weight-gradient / branch kernels it overlaps with
+    prio = int(os.environ.get('FSV_MAIN_PRIORITY', '-1'))
+    torch.cuda.set_stream(torch.cuda.Stream(priority=prio))
     wl = WORKLOADS[args.workload]
     batch = wl['batch'] if args.batch is None else args.batch
     opt = make_opt(args.workload)
