@@ -189,3 +189,31 @@ extern "C" int fsv_act_bwd(const float* y, const float* dy, float* g, long long 
     FSV_CHECK_LAUNCH("act_bwd");
     return FSV_OK;
 }
+
+
+// Pre-summed weights of the upsample-collapsed convolution (conv_tc.cu: fsv_conv2d_fwd_tc_up2): conv3x3 over a nearest-x2-upsampled
+// image equals, per output parity (p, q), a 2x2-tap convolution of the source image whose tap (a, b) sums the 3x3 taps that land on
+// the same source pixel: even rows: {r0} | {r1, r2}; odd rows: {r0, r1} | {r2}.  w (Cout, 3, 3, Cin) -> w4 (Cout, 2, 2, 2, 2, Cin).
+// (Replaces a torch.einsum = six tiny cuBLAS GEMMs per forward.)
+__global__ void k_up2_weights(const float* __restrict__ w, float* __restrict__ w4, long long cout, int cin) {
+    const long long total = cout * 16 * cin;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cin);
+        long long t = i / cin;
+        const int b = (int)(t & 1), a = (int)((t >> 1) & 1), q = (int)((t >> 2) & 1), p = (int)((t >> 3) & 1);
+        const long long o = t >> 4;
+        // rows r contributing to tap a of parity p: p=0: a=0 -> {0}, a=1 -> {1,2};  p=1: a=0 -> {0,1}, a=1 -> {2}
+        const int r0 = p == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), r1 = p == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+        const int s0 = q == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), s1 = q == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+        float acc = 0.f;
+        for (int r = r0; r <= r1; ++r)
+            for (int s2 = s0; s2 <= s1; ++s2) acc += w[((o * 3 + r) * 3 + s2) * cin + c];
+        w4[i] = acc;
+    }
+}
+extern "C" int fsv_up2_weights(const float* w, float* w4, int Cout, int Cin, void* stream) {
+    FSV_REQUIRE(w && w4 && Cout > 0 && Cin > 0, "up2_weights: bad args");
+    k_up2_weights<<<stream_grid((long long)Cout * 16 * Cin, 256), 256, 0, (cudaStream_t)stream>>>(w, w4, Cout, Cin);
+    FSV_CHECK_LAUNCH("up2_weights");
+    return FSV_OK;
+}

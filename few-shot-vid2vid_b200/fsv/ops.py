@@ -359,10 +359,8 @@ class Conv2dFn(torch.autograd.Function):
         if up == 2 and d.use_tc != 0 and cfg.get('w_off', 0) == 0 and lib.fsv_conv2d_fwd_tc_up2_eligible(ctypes.byref(d)):
             # conv3x3(up2(x)) == four 2x2-tap convs of x (one per output parity) with row/column-summed weights:
             # no 4x intermediate and 4/9 of the MACs.  Weight prep is a tiny parameter-side einsum.
-            with torch.no_grad():
-                w33 = wbase.reshape(d.Cout, 3, 3, d.Cin)
-                sel = _up2_selector(x.device)                                   # (parity, tap a, kernel row r)
-                w4 = torch.einsum('par,qbs,orsc->opqabc', sel, sel, w33).reshape(d.Cout, 16, d.Cin).contiguous()
+            w4 = torch.empty((d.Cout, 16, d.Cin), device=x.device, dtype=torch.float32)
+            _call(lib.fsv_up2_weights, ptr(wbase), ptr(w4), d.Cout, d.Cin, stream())
             _call(lib.fsv_conv2d_fwd_tc_up2, ctypes.byref(d), ptr(x), ptr(w4), None if bbase is None else _off(bbase, cfg.get('b_off', 0)),
                   ptr(residual), ptr(y), stream())
             done = True

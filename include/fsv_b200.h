@@ -104,6 +104,8 @@ int fsv_conv2d_tc_eligible(const fsv_conv_desc* d);
  * per output parity) with host-pre-summed weights w4[co][ph][pw][a][b][ci] (Cout,16,Cin); d describes the conv at the
  * upsampled resolution with up = 2.  4/9 of the MACs of Upsample -> Conv2d (generator.py:484,537). */
 int fsv_conv2d_fwd_tc_up2_eligible(const fsv_conv_desc* d);
+/* w (Cout, 3, 3, Cin) OHWI -> the pre-summed w4 (Cout, 16, Cin) fsv_conv2d_fwd_tc_up2 takes */
+int fsv_up2_weights(const float* w, float* w4, int Cout, int Cin, void* stream);
 int fsv_conv2d_fwd_tc_up2(const fsv_conv_desc* d, const float* x, const float* w4, const float* bias,
                           const float* residual, float* y, void* stream);
 /* Data gradient on the tcgen05/TMA kernel.  wt is the weight with its channel axes swapped: wt[ci][r][s][co]
