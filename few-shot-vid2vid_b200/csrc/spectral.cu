@@ -241,30 +241,34 @@ __global__ void __launch_bounds__(SN_THREADS) k_sn_scale_t(const float* __restri
 }
 
 // backward phase 1: c = sum dW_sn * W_sn  (both OHWI, contiguous)
-__global__ void __launch_bounds__(SN_THREADS) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, long long total,
-                                                       float* part, float* __restrict__ c_out) {
+__device__ __forceinline__ void sn_dot_body(const float* __restrict__ a, const float* __restrict__ b, long long total, float* part,
+                                            float* __restrict__ c_out, int blk, int nblk, unsigned int* ticket) {
     __shared__ float sh[SN_THREADS / 32];
     __shared__ int flag;
     float acc = 0.f;
-    for (long long i = (long long)blockIdx.x * SN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * SN_THREADS)
+    for (long long i = (long long)blk * SN_THREADS + threadIdx.x; i < total; i += (long long)nblk * SN_THREADS)
         acc = fmaf(a[i], b[i], acc);
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) part[blockIdx.x] = acc;
-    if (!last_block(&g_sn_ticket[2], gridDim.x, &flag)) return;
+    if (threadIdx.x == 0) part[blk] = acc;
+    if (!last_block(ticket, nblk, &flag)) return;
     const volatile float* pv = part;
     float t = 0.f;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += SN_THREADS) t += pv[i];
+    for (int i = threadIdx.x; i < nblk; i += SN_THREADS) t += pv[i];
     t = block_sum(t, sh);
     if (threadIdx.x == 0) *c_out = t;
 }
+__global__ void __launch_bounds__(SN_THREADS) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, long long total,
+                                                       float* part, float* __restrict__ c_out) {
+    sn_dot_body(a, b, total, part, c_out, blockIdx.x, gridDim.x, &g_sn_ticket[2]);
+}
 
 // backward phase 2: dW (R, Cin, taps) = (dW_sn (R, taps, Cin) - c u v^T) / sigma; same tiling as k_sn_scale, transposing back
-__global__ void __launch_bounds__(SN_CI) k_sn_bwd(const float* __restrict__ dws, const float* __restrict__ u, const float* __restrict__ v,
-                                                  const float* __restrict__ sigma, const float* __restrict__ c, int Cin, int taps,
-                                                  float* __restrict__ dw) {
+__device__ __forceinline__ void sn_bwd_body(const float* __restrict__ dws, const float* __restrict__ u, const float* __restrict__ v,
+                                            const float* __restrict__ sigma, const float* __restrict__ c, int Cin, int taps,
+                                            float* __restrict__ dw, int bx, int by) {
     __shared__ float sm[SN_CI * (SN_MAXTAPS + 1)];
     float inv = 1.f / *sigma;
-    int r = blockIdx.y, ci0 = blockIdx.x * SN_CI;
+    int r = by, ci0 = bx * SN_CI;
     int nci = min(SN_CI, Cin - ci0);
     size_t K = (size_t)Cin * taps;
     float cu = *c * u[r];
@@ -285,6 +289,11 @@ __global__ void __launch_bounds__(SN_CI) k_sn_bwd(const float* __restrict__ dws,
         int j = e / taps, t = e - j * taps;
         dst[e] = (sm[j * tp + t] - cu * vv[e]) * inv;
     }
+}
+__global__ void __launch_bounds__(SN_CI) k_sn_bwd(const float* __restrict__ dws, const float* __restrict__ u, const float* __restrict__ v,
+                                                  const float* __restrict__ sigma, const float* __restrict__ c, int Cin, int taps,
+                                                  float* __restrict__ dw) {
+    sn_bwd_body(dws, u, v, sigma, c, Cin, taps, dw, blockIdx.x, blockIdx.y);
 }
 
 
@@ -338,7 +347,7 @@ __global__ void __launch_bounds__(SN_THREADS) k_sng_scale(const fsv_sn_item* __r
 
 extern "C" int fsv_spectral_group_plan(fsv_sn_item* items, int n, long long* totals) {
     FSV_REQUIRE(items && totals && n > 0, "spectral_group_plan: bad args");
-    long long out = 0, work = 0, tick = 0, b1 = 0, b2 = 0, b3 = 0;
+    long long out = 0, work = 0, tick = 0, b1 = 0, b2 = 0, b3 = 0, bwork = 0, bb1 = 0, bb2 = 0;
     for (int i = 0; i < n; ++i) {
         fsv_sn_item& it = items[i];
         FSV_REQUIRE(it.R > 0 && it.R <= 65535 && it.Cin > 0 && it.taps > 0 && it.taps <= SN_MAXTAPS, "spectral_group_plan: bad dims in item %d", i);
@@ -353,12 +362,20 @@ extern "C" int fsv_spectral_group_plan(fsv_sn_item* items, int n, long long* tot
         it.wt_off = out; if (it.want_wt) out += (rk + 3) / 4 * 4;
         it.uvs_off = out; out += ((long long)it.K + it.R + 1 + 3) / 4 * 4;     // [v | u | sigma], 16-byte aligned slots
         it.work_off = work; work += ((long long)it.rs * it.K + it.R + it.nchunks + 3) / 4 * 4;
-        it.ticket_off = (int)tick; tick += it.nchunks + 1;
+        it.ticket_off = (int)tick; tick += it.nchunks + 2;      // phase-1 tickets per chunk, one for phase 2, one for the backward dot
         it.blk1 = (int)b1; b1 += (long long)it.nchunks * it.rs;
         it.blk2 = (int)b2; b2 += it.nblk2;
         it.blk3 = (int)b3; b3 += it.nblk3;
+        long long nb1 = (rk + SN_THREADS * 4 - 1) / (SN_THREADS * 4);
+        const long long cap = 2LL * fsv_sm_count();
+        if (nb1 > cap) nb1 = cap;
+        it.nb1 = (int)nb1;
+        it.nb2 = fsv_cdiv(it.Cin, SN_CI) * it.R;
+        it.bwd_work_off = bwork; bwork += (nb1 + 1 + 3) / 4 * 4;
+        bb1 += it.nb1; bb2 += it.nb2;
     }
     totals[0] = out; totals[1] = work; totals[2] = tick; totals[3] = b1; totals[4] = b2; totals[5] = b3;
+    totals[6] = bwork; totals[7] = bb1; totals[8] = bb2;
     return FSV_OK;
 }
 
@@ -378,6 +395,44 @@ extern "C" int fsv_spectral_group_fwd(const fsv_sn_item* items_dev, const int* m
     const size_t sm = (size_t)32 * 33 * 9 * sizeof(float) > (size_t)16 * 33 * 17 * sizeof(float) ? (size_t)32 * 33 * 9 * sizeof(float) : (size_t)16 * 33 * 17 * sizeof(float);
     k_sng_scale<<<(unsigned)b3, SN_THREADS, sm, st>>>(items_dev, map + b1 + b2, out, emit_wt);
     FSV_CHECK_LAUNCH("spectral_group_scale");
+    return FSV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ grouped backward
+// dW_orig of every spectral weight of a group in TWO launches.  The incoming dW_sn tensors are whatever the conv weight-gradient
+// kernels allocated, so their addresses come in a per-call device table `dws` (NULL = this weight received no gradient: skipped);
+// W_sn / [v|u|sigma] are read from the forward's arena, dW_orig goes to a per-call arena at the forward arena's out_off offsets.
+__global__ void __launch_bounds__(SN_THREADS) k_sng_dot(const fsv_sn_item* __restrict__ items, const int2* __restrict__ map,
+                                                        const float* const* __restrict__ dws, const float* __restrict__ out, float* work,
+                                                        unsigned int* tickets) {
+    const int2 m = map[blockIdx.x];
+    const fsv_sn_item it = items[m.x];
+    const float* g = dws[m.x];
+    if (g == nullptr) return;
+    float* w = work + it.bwd_work_off;
+    sn_dot_body(g, out + it.out_off, (long long)it.R * it.K, w, w + it.nb1, m.y, it.nb1, tickets + it.ticket_off + it.nchunks + 1);
+}
+__global__ void __launch_bounds__(SN_CI) k_sng_bwd(const fsv_sn_item* __restrict__ items, const int2* __restrict__ map,
+                                                   const float* const* __restrict__ dws, const float* __restrict__ out, const float* __restrict__ work,
+                                                   float* __restrict__ dw_arena) {
+    const int2 m = map[blockIdx.x];
+    const fsv_sn_item it = items[m.x];
+    const float* g = dws[m.x];
+    if (g == nullptr) return;
+    const float* uvs = out + it.uvs_off;
+    const int gx = (it.Cin + SN_CI - 1) / SN_CI;
+    sn_bwd_body(g, uvs + it.K, uvs, uvs + it.K + it.R, work + it.bwd_work_off + it.nb1, it.Cin, it.taps, dw_arena + it.out_off, m.y % gx, m.y / gx);
+}
+
+extern "C" int fsv_spectral_group_bwd(const fsv_sn_item* items_dev, const int* map_bwd_dev, const long long* totals_bwd, const float* const* dws_dev,
+                                      const float* out, float* dw_arena, float* work, unsigned int* tickets, void* stream) {
+    FSV_REQUIRE(items_dev && map_bwd_dev && totals_bwd && dws_dev && out && dw_arena && work && tickets, "spectral_group_bwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int2* map = reinterpret_cast<const int2*>(map_bwd_dev);
+    k_sng_dot<<<(unsigned)totals_bwd[1], SN_THREADS, 0, st>>>(items_dev, map, dws_dev, out, work, tickets);
+    FSV_CHECK_LAUNCH("spectral_group_dot");
+    k_sng_bwd<<<(unsigned)totals_bwd[2], SN_CI, 0, st>>>(items_dev, map + totals_bwd[1], dws_dev, out, work, dw_arena);
+    FSV_CHECK_LAUNCH("spectral_group_bwd");
     return FSV_OK;
 }
 

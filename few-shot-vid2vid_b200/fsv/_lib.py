@@ -35,7 +35,7 @@ class SnItem(ctypes.Structure):
     _fields_ = [('w_orig', c_vp), ('u', c_vp), ('v', c_vp), ('R', c_int), ('Cin', c_int), ('taps', c_int), ('want_wt', c_int),
                 ('K', c_int), ('nchunks', c_int), ('rs', c_int), ('rps', c_int), ('nblk2', c_int), ('nblk3', c_int), ('ticket_off', c_int),
                 ('blk1', c_int), ('blk2', c_int), ('blk3', c_int),
-                ('out_off', c_ll), ('wt_off', c_ll), ('uvs_off', c_ll), ('work_off', c_ll)]
+                ('out_off', c_ll), ('wt_off', c_ll), ('uvs_off', c_ll), ('work_off', c_ll), ('nb1', c_int), ('nb2', c_int), ('bwd_work_off', c_ll)]
 
 
 class FlowMaskDesc(ctypes.Structure):
@@ -97,6 +97,7 @@ SIGNATURES = {
     'fsv_spectral_bwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     'fsv_spectral_group_plan': [c_vp, c_int, c_vp],
     'fsv_spectral_group_fwd': [c_vp, c_vp, c_vp, c_int, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
+    'fsv_spectral_group_bwd': [c_vp] * 9,
     'fsv_adam_chunks': [c_ll],
     'fsv_adam_step': [c_vp, c_vp, c_ll, c_vp, c_float, c_float, c_float, c_float, c_vp],
     'fsv_flow_mask_loss_work_doubles': [],

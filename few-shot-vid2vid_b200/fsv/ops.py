@@ -517,6 +517,8 @@ def guard_param(p):
 
 # emit the channel-swapped copy of a spectral weight for the tcgen05 data gradient from the spectral kernel itself
 SPECTRAL_EMIT_WT = True
+# the spectral backward of a whole group in two launches (fsv_spectral_group_bwd); 0 = one pair of launches per weight
+GROUP_SPECTRAL_BWD = os.environ.get('FSV_GROUP_SPECTRAL_BWD', '1') != '0'
 
 
 class SpectralWeightFn(torch.autograd.Function):
@@ -588,7 +590,7 @@ class SpectralGroup:
             it.R, it.Cin = w.shape[0], w.shape[1]
             it.taps = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
             it.want_wt = 1 if want else 0
-        self.totals = (_lib.c_ll * 6)()
+        self.totals = (_lib.c_ll * 9)()
         check(lib.fsv_spectral_group_plan(ctypes.byref(items), n, ctypes.byref(self.totals)), 'fsv_spectral_group_plan')
         self.items = [dict(R=it.R, Cin=it.Cin, taps=it.taps, K=it.K, want_wt=bool(it.want_wt), out_off=it.out_off, wt_off=it.wt_off,
                            uvs_off=it.uvs_off) for it in items]
@@ -599,6 +601,18 @@ class SpectralGroup:
             loc = np.concatenate([np.arange(c, dtype=np.int32) for c in cnt])
             maps.append(np.stack([idx, loc], axis=1))
         self.map_dev = torch.from_numpy(np.ascontiguousarray(np.concatenate(maps, axis=0))).to(self.dev)
+        bmaps = []
+        for cnt in ([it.nb1 for it in items], [it.nb2 for it in items]):
+            idx = np.repeat(np.arange(n, dtype=np.int32), cnt)
+            loc = np.concatenate([np.arange(c, dtype=np.int32) for c in cnt])
+            bmaps.append(np.stack([idx, loc], axis=1))
+        self.map_bwd_dev = torch.from_numpy(np.ascontiguousarray(np.concatenate(bmaps, axis=0))).to(self.dev)
+        self.totals_bwd = (_lib.c_ll * 3)(self.totals[6], self.totals[7], self.totals[8])
+        # gradient-pointer tables of the grouped backward: [0] for eager calls, one more per CUDA-graph capture (see optim.Adam._table)
+        self.ptr_staging = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(4)]
+        self.ptr_dev = [torch.empty(n, dtype=torch.int64, device=self.dev) for _ in range(4)]
+        self.ptr_used = 1
+        self.ptr_event = None
         self.items_dev = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.dev)
         self.tickets = torch.zeros(int(self.totals[2]) + 1, device=self.dev, dtype=torch.int32)
         torch.cuda.current_stream().synchronize()
@@ -636,21 +650,48 @@ class GroupSpectralFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         group, out = ctx.group, ctx.arena
-        res = []
         side = side_fork(out, *grads) if (WGRAD_SIDE_STREAM and not on_side_stream()) else None
         with torch.cuda.stream(side) if side is not None else _NullCtx():
             st = stream()
-            for i, (it, shp) in enumerate(zip(group.items, group.shapes)):
-                g = grads[i]
-                if g is None:
-                    res.append(None)
-                    continue
-                g = _c(g)
-                R, Cin, K, taps = it['R'], it['Cin'], it['K'], it['taps']
-                dw = torch.empty(shp, device=g.device, dtype=torch.float32)
-                work = torch.empty(lib.fsv_spectral_workspace(R, K) // 4, device=g.device, dtype=torch.float32)
-                _call(lib.fsv_spectral_bwd, ptr(g), _off(out, it['out_off']), _off(out, it['uvs_off']), R, Cin, taps, ptr(dw), ptr(work), st)
-                res.append(dw)
+            gs = [None if g is None else _c(g) for g in grads[:group.n]]
+            if not GROUP_SPECTRAL_BWD:
+                res = []
+                for g, it, shp in zip(gs, group.items, group.shapes):
+                    if g is None:
+                        res.append(None)
+                        continue
+                    R, Cin, K, taps = it['R'], it['Cin'], it['K'], it['taps']
+                    dw = torch.empty(shp, device=g.device, dtype=torch.float32)
+                    work = torch.empty(lib.fsv_spectral_workspace(R, K) // 4, device=g.device, dtype=torch.float32)
+                    _call(lib.fsv_spectral_bwd, ptr(g), _off(out, it['out_off']), _off(out, it['uvs_off']), R, Cin, taps, ptr(dw), ptr(work), st)
+                    res.append(dw)
+                return (None, None, None, None) + tuple(res)
+            # two launches for the whole group: the dW_sn addresses of this call go to the device through a pinned staging buffer (eager
+            # calls reuse slot 0; a call made during CUDA-graph capture takes a slot of its own, which the graph's copy node keeps reading)
+            slot = 0
+            if torch.cuda.is_current_stream_capturing():
+                if group.ptr_used >= len(group.ptr_staging):
+                    raise _lib.FsvError('spectral group: too many CUDA-graph captures of one plan')
+                slot = group.ptr_used
+                group.ptr_used += 1
+            host = group.ptr_staging[slot]
+            if slot == 0 and group.ptr_event is not None:
+                group.ptr_event.synchronize()          # the previous eager call's copy out of this staging buffer has long finished; make it certain
+            for i, g in enumerate(gs):
+                host[i] = 0 if g is None else g.data_ptr()
+            group.ptr_dev[slot].copy_(host, non_blocking=True)
+            if slot == 0:
+                group.ptr_event = torch.cuda.Event()
+                group.ptr_event.record()
+            dw_arena = torch.empty(int(group.totals[0]) + 4, device=out.device, dtype=torch.float32)
+            work = torch.empty(int(group.totals[6]) + 4, device=out.device, dtype=torch.float32)
+            _call(lib.fsv_spectral_group_bwd, ptr(group.items_dev), ptr(group.map_bwd_dev), ctypes.byref(group.totals_bwd), ptr(group.ptr_dev[slot]), ptr(out),
+                  ptr(dw_arena), ptr(work), ptr(group.tickets), st)
+            res = [None if g is None else dw_arena[it['out_off']:it['out_off'] + it['R'] * it['K']].view(shp)
+                   for g, it, shp in zip(gs, group.items, group.shapes)]
+            for g in gs:
+                if g is not None and side is not None:
+                    g.record_stream(side)
         return (None, None, None, None) + tuple(res)
 
 

@@ -73,8 +73,13 @@ class Adam(torch.optim.Optimizer):
                 raise _lib.FsvError('fsv Adam: more than %d CUDA-graph captures of one optimizer' % (self.N_STAGING - 1))
             slot = tab['used']
             tab['used'] += 1
+        if slot == 0 and tab.get('event') is not None:
+            tab['event'].synchronize()             # the previous eager step's copy out of this staging buffer is done (certainly, not just likely)
         ctypes.memmove(tab['staging'][slot].data_ptr(), ctypes.addressof(items), ctypes.sizeof(items))
         tab['dev_tables'][slot].copy_(tab['staging'][slot], non_blocking=True)
+        if slot == 0:
+            tab['event'] = torch.cuda.Event()
+            tab['event'].record()
         tab['key'], tab['slot'], tab['captured'] = key, slot, capturing
         tab['items_dev'] = tab['dev_tables'][slot]
         return tab

@@ -236,7 +236,7 @@ int fsv_spectral_bwd(const float* dw_ohwi, const float* w_sn_ohwi, const float* 
 
 /* Grouped forward: every spectral weight a network touches in one forward pass in THREE launches (one per phase).
  * Fill w_orig/u/v/R/Cin/taps/want_wt of each item, call fsv_spectral_group_plan (host; fills the derived fields and
- * totals[6] = {out floats, work floats, ticket words, phase-1 blocks, phase-2 blocks, phase-3 blocks}), upload the items and a
+ * totals[9], see below), upload the items and a
  * block map ([(item, local block)] for the three phases back to back, int32 pairs) once, and keep a zero-initialised ticket
  * buffer per plan.  Per call pass freshly allocated `out` / `work` arenas: item i's W_sn lives at out + out_off (OHWI), its
  * channel-swapped copy at out + wt_off (when want_wt and emit_wt), [v | u | sigma] at out + uvs_off. */
@@ -246,8 +246,16 @@ typedef struct fsv_sn_item {
     /* derived by fsv_spectral_group_plan */
     int K, nchunks, rs, rps, nblk2, nblk3, ticket_off, blk1, blk2, blk3;
     long long out_off, wt_off, uvs_off, work_off;
+    int nb1, nb2;               /* backward: blocks of the dot phase / the transpose phase */
+    long long bwd_work_off;     /* float offset into the backward work arena (nb1 partials + the scalar c) */
 } fsv_sn_item;
+/* totals[9] = {out floats, work floats, ticket words, fwd phase-1/2/3 blocks, bwd work floats, bwd phase-1 / phase-2 blocks} */
 int fsv_spectral_group_plan(fsv_sn_item* items, int n, long long* totals);
+/* Grouped backward (u, v constants): dw_arena + out_off(i) <- (dW_sn_i - (sum dW_sn_i * W_sn_i) u v^T) / sigma in weight_orig layout, for every
+ * item whose entry in the device pointer table dws_dev is non-NULL; `out` is the forward's arena; map_bwd_dev = [(item, local block)] of
+ * the two phases back to back; totals_bwd = {work floats, phase-1 blocks, phase-2 blocks} (= totals + 6). */
+int fsv_spectral_group_bwd(const fsv_sn_item* items_dev, const int* map_bwd_dev, const long long* totals_bwd, const float* const* dws_dev,
+                           const float* out, float* dw_arena, float* work, unsigned int* tickets, void* stream);
 int fsv_spectral_group_fwd(const fsv_sn_item* items_dev, const int* map_dev, const long long* totals, int power, float eps,
                            int emit_wt, float* out, float* work, unsigned int* tickets, void* stream);
 

@@ -461,11 +461,17 @@ def test_spectral_group_equals_per_weight_calls(training):
     ws, _ = ops.spectral_group_weights(group, training, 1e-12, [e[0] for e in ents])
     rs = [ops.spectral_weight(w1, u1, v1, training) for (w1, u1, v1, _) in singles]
     gs = [torch.randn(o.shape, generator=g).cuda() for o in ws]
-    ga = torch.autograd.grad(sum((o * q).sum() for o, q in zip(ws[:-1], gs[:-1])), [e[0] for e in ents], allow_unused=True)
     gb = torch.autograd.grad(sum((o * q).sum() for o, q in zip(rs[:-1], gs[:-1])), [s[0] for s in singles], allow_unused=True)
-    assert ga[-1] is None and gb[-1] is None                  # a weight whose output was not used gets no gradient
-    for a, b in zip(ga[:-1], gb[:-1]):
-        assert torch.equal(a, b)
+    for grouped_bwd in (True, False):                         # fsv_spectral_group_bwd (two launches) / per-weight fsv_spectral_bwd
+        ops.GROUP_SPECTRAL_BWD = grouped_bwd
+        try:
+            ga = torch.autograd.grad(sum((o * q).sum() for o, q in zip(ws[:-1], gs[:-1])), [e[0] for e in ents], allow_unused=True, retain_graph=True)
+        finally:
+            ops.GROUP_SPECTRAL_BWD = True
+        torch.cuda.synchronize()
+        assert ga[-1] is None and gb[-1] is None              # a weight whose output was not used gets no gradient
+        for a, b in zip(ga[:-1], gb[:-1]):
+            assert torch.equal(a, b)
 
 
 def test_own_adam_matches_torch_adam_eager_and_graphed():
