@@ -47,11 +47,29 @@ def child(impl, size, K, frames):
             ts.append(time.perf_counter() - t0)
             prev = [label, out[0].contiguous()]
         return ts
+    torch.cuda.set_stream(torch.cuda.Stream())
     run(3)                  # warm-up (cudnn.benchmark, allocator, plans)
     ts = run(frames)
     steady = sorted(ts[1:])[len(ts[1:]) // 2]
-    print('RESULT ' + json.dumps(dict(impl=impl, size=size, K=K, first_frame_ms=ts[0] * 1e3, steady_ms=steady * 1e3, steady_fps=1.0 / steady,
-                                      peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)), flush=True)
+    rec = dict(impl=impl, size=size, K=K, first_frame_ms=ts[0] * 1e3, steady_ms=steady * 1e3, steady_fps=1.0 / steady)
+    if impl == 'fsv':       # the same steady-state frame replayed from a CUDA graph (fsv.infer.GraphedGenerator)
+        from fsv.infer import GraphedGenerator
+        with torch.no_grad():
+            out = G(label, lref, iref, [None, None], t=0)
+            prev = [label, out[0].contiguous()]
+        gg = GraphedGenerator(G, label, lref, iref, prev)
+        tg = []
+        for _ in range(frames):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            o = gg(label, prev)
+            torch.cuda.synchronize()
+            tg.append(time.perf_counter() - t0)
+            prev = [label, o[0].contiguous()]
+        g = sorted(tg)[len(tg) // 2]
+        rec.update(graph_steady_ms=g * 1e3, graph_steady_fps=1.0 / g)
+    rec['peak_mem_gb'] = torch.cuda.max_memory_allocated() / 2 ** 30
+    print('RESULT ' + json.dumps(rec), flush=True)
 
 
 if __name__ == '__main__':
