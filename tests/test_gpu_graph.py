@@ -66,3 +66,34 @@ def test_graphed_iteration_equals_eager_iteration(dstep_stream):
             assert float((p - q).abs().mean()) < 0.5 * lr, n
     finally:
         tr.DSTEP_STREAM = old
+
+
+def test_graphed_generator_equals_eager_eval_forward():
+    """fsv.infer.GraphedGenerator (steady-state frame, eval mode, cached hyper-weights, previous-frame branch) vs the eager call."""
+    import bench
+    from fsv import networks
+    from fsv.infer import GraphedGenerator
+    opt = bench.make_opt('tiny')
+    opt.gpu_ids = [0]
+    opt.isTrain = False
+    torch.manual_seed(0)
+    G = networks.define_G(opt)
+    G.init_temporal_network()
+    G.cuda().eval()
+    b = {k: v.cuda() for k, v in synth.make('pose', 1, 64, 64, seed=4).items()}
+    label, lref, iref = b['tgt_label'][:, 0], b['ref_label'], b['ref_image']
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.no_grad():
+        o0 = G(label, lref, iref, [None, None], t=0)
+        prev = [label, o0[0].contiguous()]
+        e1 = G(label, lref, iref, prev, t=1)
+        gg = GraphedGenerator(G, label, lref, iref, prev)
+        g1 = gg(label, prev)
+        torch.cuda.synchronize()
+        assert float((g1[0] - e1[0]).abs().max()) < 1e-5
+        prev2 = [label, e1[0].contiguous()]
+        e2 = G(label, lref, iref, prev2, t=2)
+        g2 = gg(label, prev2)
+        torch.cuda.synchronize()
+        assert float((g2[0] - e2[0]).abs().max()) < 1e-5
