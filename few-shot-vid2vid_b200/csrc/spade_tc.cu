@@ -16,6 +16,7 @@
 // hyper-network's flat output (K, C, sample) -- still zero-copy.  gamma/beta never touch HBM.
 // Roofline: HBM, algorithmic bytes 4*(|x|/up^2 + sum|map_i| + |out|) per launch (weights: L2-resident).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 #define SP_STAGES 3
 // channels per CTA: template parameter SP_CB (64, or 32 for the C=32 layer at full resolution)
@@ -305,7 +306,11 @@ static int spade_tc_launch(const fsv_spade_desc* d, const float* x, const float*
         return FSV_ENOTSUP;
     }
     FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)mean) & 15) == 0 && (((uintptr_t)rstd) & 15) == 0, "%s: pointers must be 16-byte aligned", who);
-    const int CB = d->C % 64 == 0 ? 64 : 32;
+    // channels per CTA: 64 where C allows (one fetch of the map tile per 64 channels), or 32 for every layer with FSV_SPADE_CB=32 /
+    // FSV_SPADE_CB_BWD=32 (smaller CTAs: more of them resident per SM; A/B switch)
+    static int force_f = -1, force_b = -1;
+    if (force_f < 0) { const char* e = getenv("FSV_SPADE_CB"); force_f = e ? atoi(e) : 0; const char* e2 = getenv("FSV_SPADE_CB_BWD"); force_b = e2 ? atoi(e2) : 0; }
+    const int CB = (d->C % 64 == 0 && (bwd ? force_b : force_f) != 32) ? 64 : 32;
     SpTcParams p;
     memset(&p, 0, sizeof(p));
     p.nmaps = d->nmaps; p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.up = d->up; p.instance = d->mode == FSV_NORM_INSTANCE; p.act = d->act;
