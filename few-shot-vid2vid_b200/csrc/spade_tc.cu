@@ -38,8 +38,8 @@ struct __align__(64) SpTcParams {
     int dgb_ld[FSV_SPADE_MAX_MAPS];
 };
 
-template <int SP_CB, bool BWD>
-__global__ void __launch_bounds__(192, BWD ? 1 : 2) k_spade_tc(const __grid_constant__ SpTcParams p, const float* __restrict__ x,
+template <int SP_CB, bool BWD, int MINB = (BWD ? 1 : 2)>
+__global__ void __launch_bounds__(192, MINB) k_spade_tc(const __grid_constant__ SpTcParams p, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      float* __restrict__ out, const float* __restrict__ dout,
                                                      float* __restrict__ dxhat) {
@@ -363,11 +363,13 @@ static int spade_tc_launch(const fsv_spade_desc* d, const float* x, const float*
         FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         FSV_CUDA(cudaFuncSetAttribute(k_spade_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        FSV_CUDA(cudaFuncSetAttribute((k_spade_tc<32, false, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     }
     dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->C / CB);
     cudaStream_t st = (cudaStream_t)stream;
     if (!bwd) {
         if (CB == 64) k_spade_tc<64, false><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, out, nullptr, nullptr);
+        else if (force_f == 32) k_spade_tc<32, false, 3><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, out, nullptr, nullptr);   // 3 CTAs / SM
         else k_spade_tc<32, false><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, out, nullptr, nullptr);
     } else {
         if (CB == 64) k_spade_tc<64, true><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, nullptr, dout, dxhat);
