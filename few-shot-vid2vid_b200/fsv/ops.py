@@ -37,22 +37,35 @@ def side_fork(*tensors):
     side = _SIDE.get(dev)
     if side is None:
         side = _SIDE[dev] = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
+    cur = torch.cuda.current_stream()
+    side.wait_stream(cur)
     for t in tensors:
         if t is not None:
             t.record_stream(side)
-    if not _SIDE_DIRTY.get(dev):
-        _SIDE_DIRTY[dev] = True
+    owners = _SIDE_DIRTY.setdefault(dev, [])
+    if not owners:
         torch.autograd.Variable._execution_engine.queue_callback(side_join)
+    if all(o.cuda_stream != cur.cuda_stream for o in owners):
+        owners.append(cur)
     return side
 
 
 def side_join():
-    """current stream waits for the side stream's pending weight-gradient work (no-op when there is none)."""
+    """Every stream that forked weight-gradient work since the last join -- and the current stream -- waits for the side stream.
+    (Making the forking streams wait, not just whatever stream happens to be current in the engine callback, keeps the join correct
+    when a backward pass is driven from a non-default auxiliary stream, e.g. the discriminator update of trainer.train_iteration.)"""
+    if not _SIDE:
+        return                       # no weight-gradient work was ever forked in this process
     dev = torch.cuda.current_device()
-    if _SIDE_DIRTY.get(dev):
-        _SIDE_DIRTY[dev] = False
-        torch.cuda.current_stream().wait_stream(_SIDE[dev])
+    owners = _SIDE_DIRTY.get(dev)
+    if owners:
+        side = _SIDE[dev]
+        cur = torch.cuda.current_stream()
+        for o in owners:
+            o.wait_stream(side)
+        if all(o.cuda_stream != cur.cuda_stream for o in owners):
+            cur.wait_stream(side)
+        _SIDE_DIRTY[dev] = []
 
 
 def on_side_stream():

@@ -51,6 +51,8 @@ def loss_backward(losses, optimizer, grad_sync=None):
     else:
         optimizer.zero_grad()
     loss.backward()
+    from . import ops
+    ops.side_join()                  # (also done by the engine callback; explicit here so the optimizer below is ordered after it for certain)
     if grad_sync is not None:
         grad_sync()
     optimizer.step()
