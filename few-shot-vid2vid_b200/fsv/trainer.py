@@ -60,9 +60,9 @@ def loss_backward(losses, optimizer, grad_sync=None):
 
 
 # The discriminator update (D / face D / temporal D forward, backward, Adam) only needs the no-grad frame; the generator update's own
-# generator forward needs neither it nor the new discriminator weights until its discriminator forward.  With FSV_DSTEP_STREAM=1 the
+# generator forward needs neither it nor the new discriminator weights until its discriminator forward.  By default (FSV_DSTEP_STREAM=0 disables) the
 # discriminator update runs on a second stream concurrently with that generator forward (a parallel branch of the CUDA graph).
-DSTEP_STREAM = os.environ.get('FSV_DSTEP_STREAM', '0') != '0'
+DSTEP_STREAM = os.environ.get('FSV_DSTEP_STREAM', '1') != '0'
 
 
 def train_iteration(step, optG, optD, batch, sync_G=None, sync_D=None):
