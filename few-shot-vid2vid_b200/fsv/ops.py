@@ -1065,12 +1065,62 @@ def softmax_channels(x):
     return SoftmaxChannelsFn.apply(x)
 
 
+class PerSampleMatmulFn(torch.autograd.Function):
+    """y[b, h, w, :] = W_b @ x[b, h, w, :], W_b = flat[b].view(cout, cin): the two GEMMs of the K-shot attention (generator.py:298-316).
+    On the tcgen05 path the forward IS the per-sample data-gradient kernel with the roles of the channel axes swapped
+    (dx[ci'] = sum_co' dy[co'] wt[ci'][co'] with ci' = cout, co' = cin and wt = W as stored), the backward uses the per-sample
+    data-gradient / weight-gradient kernels directly; shapes they do not serve (tiny images, odd widths) and the exact-fp32 mode
+    (CONV_USE_TC = 0) run the SIMT kernels."""
+
+    @staticmethod
+    def forward(ctx, x, flat, cout, cin):
+        x, flat = _c(x), _c(flat)
+        b, h, w, _ = x.shape
+        st = stream()
+        y = torch.empty((b, h, w, cout), device=x.device, dtype=torch.float32)
+        dfw = _conv_desc(b, h, w, cout, cin, 1, 1, 1, 0, 1, ACT_NONE, 1.0, cout * cin, 0, CONV_USE_TC)     # swapped roles (see above)
+        if CONV_USE_TC != 0 and lib.fsv_conv2d_dgrad_tc_eligible(ctypes.byref(dfw)):
+            _call(lib.fsv_conv2d_dgrad_tc, ctypes.byref(dfw), ptr(x), ptr(flat), ptr(y), st)
+        else:
+            d = _conv_desc(b, h, w, cin, cout, 1, 1, 1, 0, 1, ACT_NONE, 1.0, cout * cin, 0, 0)
+            _call(lib.fsv_conv2d_fwd, ctypes.byref(d), ptr(x), ptr(flat), None, None, ptr(y), st)
+        ctx.save_for_backward(x, flat)
+        ctx.dims = (b, h, w, cout, cin)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, flat = ctx.saved_tensors
+        b, h, w, cout, cin = ctx.dims
+        dy = _c(dy)
+        st = stream()
+        d = _conv_desc(b, h, w, cin, cout, 1, 1, 1, 0, 1, ACT_NONE, 1.0, cout * cin, 0, CONV_USE_TC)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if CONV_USE_TC != 0 and lib.fsv_conv2d_dgrad_tc_eligible(ctypes.byref(d)):
+                wt = flat.view(b, cout, cin).transpose(1, 2).contiguous()
+                _call(lib.fsv_conv2d_dgrad_tc, ctypes.byref(d), ptr(dy), ptr(wt), ptr(dx), st)
+            else:
+                d0 = _conv_desc(b, h, w, cin, cout, 1, 1, 1, 0, 1, ACT_NONE, 1.0, cout * cin, 0, 0)
+                _call(lib.fsv_conv2d_dgrad, ctypes.byref(d0), ptr(dy), ptr(flat), ptr(dx), 0, st)
+        if ctx.needs_input_grad[1]:
+            if CONV_USE_TC != 0 and lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(d)):
+                dw = torch.empty_like(flat)
+                ws = torch.empty(int(lib.fsv_conv2d_wgrad_tc_workspace(ctypes.byref(d))) // 4 + 64, device=dy.device, dtype=torch.float32)
+                _call(lib.fsv_conv2d_wgrad_tc, ctypes.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(ws), 0, st)
+            else:
+                dw = torch.zeros_like(flat)
+                d0 = _conv_desc(b, h, w, cin, cout, 1, 1, 1, 0, 1, ACT_NONE, 1.0, cout * cin, 0, 0)
+                _call(lib.fsv_conv2d_wgrad, ctypes.byref(d0), ptr(x), ptr(dy), ptr(dw), None, 1, st)
+        return dx, dw, None, None
+
+
 def per_sample_matmul(x, flat, cout, cin):
     """y[b, h, w, :] = W_b @ x[b, h, w, :] with W_b = flat[b].view(cout, cin): a per-sample 1x1 conv without bias (the two
     GEMMs of the attention module: key^T query and x_ref @ attention).  Gradients flow to both x and flat."""
     assert x.shape[3] == cin and flat.shape[1] == cout * cin
-    cfg = dict(cout=cout, kh=1, kw=1, stride=1, pad=0, up=1, act=ACT_NONE, w_off=0, w_nstride=cout * cin, use_tc=0)
-    return Conv2dFn.apply(x, flat, None, None, cfg)
+    return PerSampleMatmulFn.apply(x, flat, cout, cin)
 
 
 # --------------------------------------------------------------------------- pose label preprocessing + face region

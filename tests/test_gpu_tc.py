@@ -262,3 +262,30 @@ def test_conv_tc_up2_forward_and_grads(N, Hs, Ws, Cin, Cout, act, has_r):
         assert grad_err(xg.grad.permute(0, 3, 1, 2), x.grad) < TOL_TF32
         assert grad_err(wg.grad, w.grad) < TOL_TF32
         assert grad_err(bg.grad, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize('b,h,w,cin,cout', [(2, 32, 32, 64, 128), (1, 16, 32, 128, 96), (2, 8, 8, 32, 64)])
+def test_per_sample_matmul_tensor_core_path(b, h, w, cin, cout):
+    """ops.per_sample_matmul (the K-shot attention GEMMs: per-sample 1x1 conv without bias) on the tcgen05 path -- forward through
+    the per-sample data-gradient kernel with swapped channel roles, backward through the per-sample dgrad / wgrad kernels -- against
+    float64 einsum; the last shape is too small for the TC kernels and checks the SIMT fallback inside the same function."""
+    from fsv import ops
+    g = torch.Generator().manual_seed(b * 100 + cin)
+    x = torch.randn(b, h, w, cin, generator=g)
+    wt = torch.randn(b, cout, cin, generator=g) * 0.1
+    go = torch.randn(b, h, w, cout, generator=g)
+    xr, wr = x.double().requires_grad_(True), wt.double().requires_grad_(True)
+    yr = torch.einsum('bhwc,boc->bhwo', xr, wr)
+    (yr * go.double()).sum().backward()
+    old = ops.CONV_USE_TC
+    ops.CONV_USE_TC = -1
+    try:
+        xg = x.cuda().requires_grad_(True)
+        wg = wt.reshape(b, cout * cin).cuda().requires_grad_(True)
+        yg = ops.per_sample_matmul(xg, wg, cout, cin)
+        (yg * go.cuda()).sum().backward()
+    finally:
+        ops.CONV_USE_TC = old
+    assert rel_err(yg, yr.detach()) < 3e-3
+    assert rel_err(xg.grad, xr.grad) < 3e-3
+    assert rel_err(wg.grad.reshape(b, cout, cin), wr.grad) < 3e-3
