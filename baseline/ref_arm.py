@@ -23,7 +23,7 @@ def _extra(wl):
 
 
 def build(wl, batch, gpu, seed=0):
-    opt = refenv.parse_opt(wl['kind'], wl['H'], wl['W'], batch, extra=_extra(wl), gpu=gpu)
+    opt = refenv.parse_opt(wl['kind'], wl['H'], wl['W'], batch, extra=_extra(wl), gpu=gpu, vgg=bool(wl.get('vgg')))
     if not gpu:
         cpu_mode()
     model, opt_g, opt_d = (refenv.create_model(opt) if gpu else _create_cpu(opt))

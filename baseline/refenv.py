@@ -7,6 +7,8 @@ Environment shims of SURVEY.md section 8c -- none of them edits a reference file
   * with `--no_vgg_loss` the reference's `LossCollector.discriminate_face` still calls `self.criterionVGG`
     (loss_collector.py:82, an AttributeError in the reference): `criterionVGG` is bound to a zero function, which is what
     `--no_vgg_loss` means everywhere else in that file (loss_collector.py:122-129),
+  * `torchvision.models.vgg19(pretrained=True)` (models/networks/vgg.py:16,48; a download) -> the same network with seeded random
+    weights, for runs that keep the VGG loss on,
   * CPU only (tests/golden generation in the build container): device-agnostic `resample` and ByteTensor aliases.
 
 This module imports neither fsv nor oracle.  `patch_networks(define_G, define_D)` is INTEGRATION.md option B: the
@@ -59,6 +61,7 @@ def install_shims(cpu=False):
         torch.optim.Adam = Adam
     if root not in sys.path:
         sys.path.insert(0, root)
+    _shim_vgg()
     if cpu:
         import torch.nn.functional as F
 
@@ -77,6 +80,29 @@ def install_shims(cpu=False):
         reflc.resample = resample_any_device
         refip.torch = _TorchCudaProxy(torch)
     return root
+
+
+def _shim_vgg():
+    """models/networks/vgg.py:16,48 ask torchvision for ImageNet weights (a download; there is no network here): hand back the same
+    VGG19 with seeded random weights -- same architecture and cost, used identically by every arm / test that enables the VGG loss."""
+    try:
+        import torchvision
+    except Exception:
+        return
+    if getattr(torchvision.models.vgg19, '_fsv_offline', False):
+        return
+    real = torchvision.models.vgg19
+
+    def vgg19(pretrained=False, **kw):
+        kw.pop('weights', None)
+        state = torch.get_rng_state()
+        torch.manual_seed(1919)
+        try:
+            return real(weights=None, **kw)
+        finally:
+            torch.set_rng_state(state)
+    vgg19._fsv_offline = True
+    torchvision.models.vgg19 = vgg19
 
 
 class _TorchCudaProxy:
@@ -101,11 +127,11 @@ DATASET_FLAGS = {
 }
 
 
-def parse_opt(kind, H, W, batch, extra=(), gpu=True, train=True, ckpt='/tmp/fsv_ref_ckpt'):
+def parse_opt(kind, H, W, batch, extra=(), gpu=True, train=True, ckpt='/tmp/fsv_ref_ckpt', vgg=False):
     """The reference's own option parser (options/train_options.py) on the BASELINE.json flags of a dataset kind.
     fineSize is the frame WIDTH, aspect_ratio = W / H (fewshot_pose_dataset.py:100, generator.py:83-84)."""
     install_shims(cpu=not gpu)
-    argv = list(DATASET_FLAGS[kind]) + ['--no_flow_gt', '--no_vgg_loss', '--loadSize', str(W), '--fineSize', str(W),
+    argv = list(DATASET_FLAGS[kind]) + ['--no_flow_gt'] + ([] if vgg else ['--no_vgg_loss']) + ['--loadSize', str(W), '--fineSize', str(W),
                                         '--aspect_ratio', repr(W / H), '--batchSize', str(batch), '--checkpoints_dir', ckpt,
                                         '--gpu_ids', '0' if gpu else '-1', '--name', 'fsv_%s_%dx%d' % (kind, H, W)] + list(extra)
     old = sys.argv

@@ -50,6 +50,9 @@ WORKLOADS = {
     # temporal phase (warp_prev: second flow pass, previous-frame embedding, 3-map SPADEs, netDT)
     'face256t': dict(kind='face', H=256, W=256, batch=8, flop=4 * 149.9e9 + 5 * 4.73e9, temporal=True, opt=dict(FACE, fineSize=256, aspect_ratio=1.0)),
     'pose512t': dict(kind='pose', H=512, W=512, batch=2, flop=None, temporal=True, opt=dict(POSE, fineSize=512, aspect_ratio=1.0)),
+    # the same iteration with the perceptual loss on (VGG19 with seeded random weights on both arms: the ImageNet checkpoint is not
+    # obtainable offline); G_VGG on the frame and on the face crops (loss_collector.py:82,122-129)
+    'pose512vgg': dict(kind='pose', H=512, W=512, batch=2, flop=None, vgg=True, opt=dict(POSE, fineSize=512, aspect_ratio=1.0, no_vgg_loss=False)),
     'tiny': dict(kind='pose', H=64, W=64, batch=2, flop=None,
                  opt=dict(POSE, ngf=8, nff=8, ndf=8, n_downsample_G=4, n_adaptive_layers=3, n_blocks_F=2, fineSize=64, aspect_ratio=1.0),
                  ref_extra=['--ngf', '8', '--nff', '8', '--ndf', '8', '--n_downsample_G', '4', '--n_adaptive_layers', '3', '--n_blocks_F', '2']),
@@ -82,8 +85,8 @@ def make_opt(workload):
 
 def describe(workload):
     wl = WORKLOADS[workload]
-    return '%s %s %dx%d %s --no_flow_gt --no_vgg_loss%s' % (workload, wl['kind'], wl['H'], wl['W'], FLAGS[wl['kind']],
-                                                            ' (temporal phase)' if wl.get('temporal') else '')
+    return '%s %s %dx%d %s --no_flow_gt%s%s' % (workload, wl['kind'], wl['H'], wl['W'], FLAGS[wl['kind']], '' if wl.get('vgg') else ' --no_vgg_loss',
+                                                ' (temporal phase)' if wl.get('temporal') else '')
 
 
 def synth_inputs(workload, batch, seed):

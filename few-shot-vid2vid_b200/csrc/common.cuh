@@ -45,6 +45,7 @@ __device__ __forceinline__ float fsv_act(float v, int act) {
     if (act == FSV_ACT_LRELU) return v > 0.f ? v : v * FSV_LRELU_SLOPE;
     if (act == FSV_ACT_TANH) return tanhf(v);
     if (act == FSV_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    if (act == FSV_ACT_RELU) return v > 0.f ? v : 0.f;
     return v;
 }
 // derivative of act expressed through the post-activation value y (before out_scale)
@@ -52,6 +53,7 @@ __device__ __forceinline__ float fsv_act_grad(float y, int act) {
     if (act == FSV_ACT_LRELU) return y > 0.f ? 1.f : FSV_LRELU_SLOPE;
     if (act == FSV_ACT_TANH) return 1.f - y * y;
     if (act == FSV_ACT_SIGMOID) return y * (1.f - y);
+    if (act == FSV_ACT_RELU) return y > 0.f ? 1.f : 0.f;
     return 1.f;
 }
 

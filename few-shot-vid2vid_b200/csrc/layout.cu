@@ -217,3 +217,54 @@ extern "C" int fsv_up2_weights(const float* w, float* w4, int Cout, int Cin, voi
     FSV_CHECK_LAUNCH("up2_weights");
     return FSV_OK;
 }
+
+
+// MaxPool2d(kernel 2, stride 2) on NHWC (VGG19 feature stack of the perceptual loss, vgg.py:45-59).  One thread per output element.
+__global__ void k_maxpool2_fwd(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)N * Ho * Wo * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long p = i / C;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho);
+        const long long n = p / Ho;
+        const float* b = x + ((n * H + 2 * ho) * W + 2 * wo) * C + c;
+        y[i] = fmaxf(fmaxf(b[0], b[C]), fmaxf(b[(long long)W * C], b[(long long)W * C + C]));
+    }
+}
+// dx fully written: every input pixel belongs to at most one window; the gradient goes to the first maximum in window order
+__global__ void k_maxpool2_bwd(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)N * H * W * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long p = i / C;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const long long n = p / H;
+        const int ho = h / 2, wo = w / 2;
+        float g = 0.f;
+        if (ho < Ho && wo < Wo) {
+            const float* b = x + ((n * H + 2 * ho) * W + 2 * wo) * C + c;
+            const float v[4] = {b[0], b[C], b[(long long)W * C], b[(long long)W * C + C]};
+            int arg = 0;
+            for (int k = 1; k < 4; ++k)
+                if (v[k] > v[arg]) arg = k;
+            if (arg == (h & 1) * 2 + (w & 1)) g = dy[((n * Ho + ho) * Wo + wo) * C + c];
+        }
+        dx[i] = g;
+    }
+}
+extern "C" int fsv_maxpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+    FSV_REQUIRE(x && y && N > 0 && H > 1 && W > 1 && C > 0, "maxpool2_fwd: bad dims");
+    k_maxpool2_fwd<<<stream_grid((long long)N * (H / 2) * (W / 2) * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C);
+    FSV_CHECK_LAUNCH("maxpool2_fwd");
+    return FSV_OK;
+}
+extern "C" int fsv_maxpool2_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
+    FSV_REQUIRE(x && dy && dx && N > 0 && H > 1 && W > 1 && C > 0, "maxpool2_bwd: bad dims");
+    k_maxpool2_bwd<<<stream_grid((long long)N * H * W * C, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, N, H, W, C);
+    FSV_CHECK_LAUNCH("maxpool2_bwd");
+    return FSV_OK;
+}

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libfsv_b200.so')
 
 c_int, c_ll, c_float, c_double, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
-ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3, 4
 NORM_BATCH, NORM_INSTANCE = 0, 1
 SPADE_MAX_MAPS = 3
 
@@ -59,6 +59,8 @@ SIGNATURES = {
     'fsv_copy_channels': [c_vp, c_int, c_int, c_vp, c_int, c_int, c_ll, c_int, c_int, c_vp],
     'fsv_upsample2x_fwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     'fsv_upsample2x_bwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    'fsv_maxpool2_fwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    'fsv_maxpool2_bwd': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     'fsv_avgpool3s2_fwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     'fsv_avgpool3s2_bwd': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     'fsv_act_bwd': [c_vp, c_vp, c_vp, c_ll, c_int, c_float, c_vp],

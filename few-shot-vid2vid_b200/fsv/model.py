@@ -21,6 +21,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .networks import define_G, define_D
+from .networks.vgg import VGGLoss
 
 LOSS_NAMES_G = ['G_GAN', 'G_GAN_Feat', 'G_VGG', 'Gf_GAN', 'Gf_GAN_feat', 'GT_GAN', 'GT_GAN_Feat', 'F_Flow', 'F_Warp', 'F_Mask']
 LOSS_NAMES_D = ['D_real', 'D_fake', 'Df_real', 'Df_fake', 'DT_real', 'DT_fake']
@@ -113,7 +114,7 @@ class Vid2VidStep:
     tgt_label (B,1,C,H,W), tgt_image (B,1,3,H,W), ref_label (B,K,C,H,W), ref_image (B,K,3,H,W) and, in the temporal phase,
     prev_label / prev_real / prev_fake (B, n_frames_G-1, C|3, H, W)."""
 
-    def __init__(self, opt, netG=None, netD=None, netDf=None, netDT=None):
+    def __init__(self, opt, netG=None, netD=None, netDf=None, netDT=None, vgg_loss=None):
         self.opt = opt
         self.pose = 'pose' in opt.dataset_mode
         self.has_fg = self.pose
@@ -135,6 +136,12 @@ class Vid2VidStep:
         if self.add_face_D and netDf is None:
             self.netDf = define_D(opt, opt.output_nc * 2, opt.ndf, opt.n_layers_D, opt.norm_D, 'n_layers', 1, not opt.no_ganFeat_loss, gpu_ids=gpu_ids)
         self.netDT = netDT
+        # loss.py:107-128 perceptual loss (absent under --no_vgg_loss): a frozen VGG19 feature stack on the same conv kernels
+        self.vgg_loss = vgg_loss
+        if self.vgg_loss is None and not opt.no_vgg_loss:
+            self.vgg_loss = VGGLoss()
+            if gpu_ids:
+                self.vgg_loss.cuda()
         self.temporal = netDT is not None or getattr(self.netG, 'warp_prev', False)
         self.face_size = int(opt.fineSize / opt.aspect_ratio) // 4                  # face_refiner.py:22
 
@@ -294,7 +301,9 @@ class Vid2VidStep:
         if for_discriminator:
             return [_gan_loss(pr, True) * lam, _gan_loss(pf, False) * lam]
         g_gan, g_feat = _gan_loss(pf, True) * lam, self._gan_feat(pred_f) * lam
-        g_feat = g_feat + F.l1_loss(fake_region, real_region) * self.opt.lambda_feat       # + criterionVGG * lambda_vgg == 0 (--no_vgg_loss)
+        g_feat = g_feat + F.l1_loss(fake_region, real_region) * self.opt.lambda_feat
+        if self.vgg_loss is not None:                                                     # loss_collector.py:82
+            g_feat = g_feat + self.vgg_loss(fake_region.permute(0, 3, 1, 2), real_region.permute(0, 3, 1, 2)) * self.opt.lambda_vgg
         return [g_gan, g_feat]
 
     def _temporal_gan(self, c, fake, for_discriminator):
@@ -365,5 +374,6 @@ class Vid2VidStep:
             f_warp = fm[0:1] * opt.lambda_flow
             f_mask = fm[1:2] * opt.lambda_mask
 
-        vals = [g[0], g[1], z, g[2], g[3], gt[0], gt[1], z, f_warp, f_mask]
+        g_vgg = z if self.vgg_loss is None else z + self.vgg_loss(fake, tgt) * opt.lambda_vgg        # loss_collector.py:122-129
+        vals = [g[0], g[1], g_vgg, g[2], g[3], gt[0], gt[1], z, f_warp, f_mask]
         return dict(zip(LOSS_NAMES_G, vals)), fake, prevs_new

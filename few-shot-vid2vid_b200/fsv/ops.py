@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import lib, check, ptr, stream, ConvDesc, SpadeDesc, PtrArray, c_vp
 
-ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID = _lib.ACT_NONE, _lib.ACT_LRELU, _lib.ACT_TANH, _lib.ACT_SIGMOID
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID, ACT_RELU = _lib.ACT_NONE, _lib.ACT_LRELU, _lib.ACT_TANH, _lib.ACT_SIGMOID, _lib.ACT_RELU
 NORM_BATCH, NORM_INSTANCE = _lib.NORM_BATCH, _lib.NORM_INSTANCE
 
 # global switch for the conv path: -1 auto (tcgen05 when eligible), 0 force SIMT, 1 force tcgen05
@@ -221,7 +221,12 @@ def pack_nhwc(*xs):
 
 
 def to_nhwc(x, pad=True):
-    return ToNHWC.apply(x, pad_channels(x.shape[1]) if pad else x.shape[1])
+    cp = pad_channels(x.shape[1]) if pad else x.shape[1]
+    if cp == x.shape[1] and x.dim() == 4:
+        v = x.permute(0, 2, 3, 1)
+        if v.is_contiguous() and not x.is_contiguous():
+            return v             # already an NCHW-shaped view of an NHWC buffer (a network output fed to another network): zero-copy
+    return ToNHWC.apply(x, cp)
 
 
 def to_nchw(x):
@@ -312,6 +317,32 @@ class AvgPool3s2(torch.autograd.Function):
 
 def avgpool3s2(x):
     return AvgPool3s2.apply(x)
+
+
+class MaxPool2(torch.autograd.Function):
+    """nn.MaxPool2d(2, 2) on NHWC (VGG19 feature stack, vgg.py:45-59)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=torch.float32)
+        _call(lib.fsv_maxpool2_fwd, ptr(x), ptr(y), n, h, w, c, stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _c(dy)
+        n, h, w, c = x.shape
+        dx = torch.empty_like(x)
+        _call(lib.fsv_maxpool2_bwd, ptr(x), ptr(dy), ptr(dx), n, h, w, c, stream())
+        return dx
+
+
+def maxpool2(x):
+    return MaxPool2.apply(x)
 
 
 # --------------------------------------------------------------------------- convolution

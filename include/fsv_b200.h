@@ -40,6 +40,7 @@ extern "C" {
 #define FSV_ACT_LRELU 1    /* LeakyReLU(0.2): architecture.py:15-17 */
 #define FSV_ACT_TANH 2     /* generator.py:211 */
 #define FSV_ACT_SIGMOID 3  /* generator.py:487 conv_mask */
+#define FSV_ACT_RELU 4     /* VGG19 perceptual features: models/networks/vgg.py:45-59 */
 
 /* normalisation grouping */
 #define FSV_NORM_BATCH 0     /* statistics over (N,H,W): SyncBatchNorm local stats, normalization.py:33,80 */
@@ -63,6 +64,10 @@ int fsv_copy_channels(const float* src, int src_ld, int src_coff, float* dst, in
 /* nearest x2 upsample (generator.py:124,207; nn.Upsample(scale_factor=2) generator.py:484,537) and its adjoint */
 int fsv_upsample2x_fwd(const float* x, float* y, int N, int Hs, int Ws, int C, void* stream);
 int fsv_upsample2x_bwd(const float* dy, float* dx, int N, int Hs, int Ws, int C, void* stream);
+/* MaxPool2d(2, 2) of the VGG19 feature stack (vgg.py:48-59; H, W even or odd: floor); bwd routes dy to the arg-max of each window
+ * (first maximum in row-major window order, as ATen) */
+int fsv_maxpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int fsv_maxpool2_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C, void* stream);
 /* AvgPool2d(3, stride 2, pad 1, count_include_pad=False): discriminator.py:28 */
 int fsv_avgpool3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
 int fsv_avgpool3s2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);

@@ -11,7 +11,7 @@ Every function states the contract of the op it stands in for (layouts are NHWC 
 import torch
 import torch.nn.functional as F
 
-ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3, 4
 NORM_BATCH, NORM_INSTANCE = 0, 1
 CONV_USE_TC = 0
 LAUNCHES = [0]
@@ -25,6 +25,8 @@ def _act(x, act):
         return torch.tanh(x)
     if act == ACT_SIGMOID:
         return torch.sigmoid(x)
+    if act == ACT_RELU:
+        return F.relu(x)
     return x
 
 
@@ -82,6 +84,10 @@ def cat_channels(*xs):
 
 def upsample2x(x):
     return _nhwc(F.interpolate(_nchw(x), scale_factor=2, mode='nearest'))
+
+
+def maxpool2(x):
+    return _nhwc(F.max_pool2d(_nchw(x), 2, 2))
 
 
 def avgpool3s2(x):

@@ -163,7 +163,7 @@ def test_bench_options_equal_the_reference_parser():
     import bench
     for name, wl in bench.WORKLOADS.items():
         mine = vars(bench.make_opt(name))
-        ref = vars(refenv.parse_opt(wl['kind'], wl['H'], wl['W'], wl['batch'], extra=wl.get('ref_extra', []), gpu=False))
+        ref = vars(refenv.parse_opt(wl['kind'], wl['H'], wl['W'], wl['batch'], extra=wl.get('ref_extra', []), gpu=False, vgg=bool(wl.get('vgg'))))
         for k, v in mine.items():
             if k in ref and k not in ('gpu_ids', 'for_face'):
                 assert ref[k] == v, (name, k, ref[k], v)

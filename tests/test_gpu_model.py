@@ -57,7 +57,7 @@ def test_face_box_and_crop_vs_oracle(openpose):
 
 
 CASES = [('pose', 128, 128, [], 0, 1e-3), ('pose', 256, 256, [], -1, 5e-3), ('pose', 128, 64, ['--remove_face_labels'], 0, 1e-3),
-         ('street', 64, 128, [], 0, 1e-3), ('face', 128, 128, [], 0, 1e-3)]
+         ('street', 64, 128, [], 0, 1e-3), ('face', 128, 128, [], 0, 1e-3), ('pose', 128, 128, ['VGG'], 0, 1e-3)]
 
 
 @needs_ref
@@ -66,7 +66,8 @@ def test_step_matches_reference_model_on_gpu(kind, H, W, extra, use_tc, tol):
     from fsv import ops, model
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    opt = refenv.parse_opt(kind, H, W, 2, extra=list(extra), gpu=True)
+    use_vgg = 'VGG' in extra
+    opt = refenv.parse_opt(kind, H, W, 2, extra=[e for e in extra if e != 'VGG'], gpu=True, vgg=use_vgg)
     ref, _, _ = refenv.create_model(opt)
     ref = ref.module
     old = ops.CONV_USE_TC
@@ -78,6 +79,8 @@ def test_step_matches_reference_model_on_gpu(kind, H, W, extra, use_tc, tol):
             if a is not None:
                 b.load_state_dict(a.state_dict())
                 b.train()
+        if use_vgg:
+            step.vgg_loss.vgg.load_state_dict(ref.lossCollector.criterionVGG.vgg.state_dict())
         batch = {k: v.cuda() for k, v in synth.make(kind, 2, H, W, seed=21).items()}
         dl = refenv.data_list(batch)
         d0 = ref(dl, mode='discriminator')

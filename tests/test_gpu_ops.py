@@ -569,3 +569,73 @@ def test_fused_feature_matching_halves_l1():
     assert rel_err(out, ref.detach().view(1)) < 1e-6
     (out * 2.5).sum().backward()
     assert grad_err(xg.grad, xr.grad, floor=1e-12) < 1e-5
+
+
+def test_maxpool2_and_relu_conv_vs_torch():
+    """fsv_maxpool2_fwd/bwd (MaxPool2d(2,2), odd sizes floor) and a conv with the fused ReLU epilogue (VGG19 feature stack)."""
+    from fsv import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 16, 11, 14, generator=g)
+    xr = x.double().requires_grad_(True)
+    yr = torch.nn.functional.max_pool2d(xr, 2, 2)
+    go = torch.randn(yr.shape, generator=g)
+    (yr * go.double()).sum().backward()
+    xg = x.permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)
+    yg = ops.maxpool2(xg)
+    assert torch.equal(yg.permute(0, 3, 1, 2).cpu(), yr.detach().float())
+    (yg * go.permute(0, 2, 3, 1).cuda()).sum().backward()
+    assert torch.equal(xg.grad.permute(0, 3, 1, 2).cpu(), xr.grad.float())
+    w = torch.randn(32, 16, 3, 3, generator=g) * 0.2
+    b = torch.randn(32, generator=g) * 0.1
+    x2 = x.double().requires_grad_(True)
+    y2 = torch.relu(torch.nn.functional.conv2d(x2, w.double(), b.double(), padding=1))
+    go2 = torch.randn(y2.shape, generator=g)
+    (y2 * go2.double()).sum().backward()
+    x3 = x.permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)
+    y3 = ops.conv2d(x3, w.permute(0, 2, 3, 1).contiguous().cuda(), b.cuda(), pad=1, act=ops.ACT_RELU, use_tc=0)
+    assert rel_err(y3.permute(0, 3, 1, 2), y2.detach()) < 1e-5
+    (y3 * go2.permute(0, 2, 3, 1).cuda()).sum().backward()
+    assert rel_err(x3.grad.permute(0, 3, 1, 2), x2.grad) < 1e-5
+
+
+@pytest.mark.parametrize('use_tc,tol', [(0, 1e-4), (-1, 5e-3)])
+def test_vgg19_feature_stack_vs_torchvision(use_tc, tol):
+    """fsv.networks.vgg.VGGActivations (conv + ReLU fused, tcgen05 convs from the second layer on) against torchvision's VGG19 features with
+    the same (seeded random) weights: the five activations the perceptual loss uses, and the loss gradient w.r.t. the input frame."""
+    import torchvision
+    from fsv import ops
+    from fsv.networks.vgg import VGGActivations, VGGLoss
+    torch.manual_seed(3)
+    ref = torchvision.models.vgg19(weights=None).features.eval()
+    mine = VGGActivations()
+    mine.load_state_dict({'features.' + k: v for k, v in ref.state_dict().items()})
+    mine.cuda()
+    x = torch.rand(2, 3, 64, 64) * 2 - 1
+    y = torch.rand(2, 3, 64, 64) * 2 - 1
+    res, h = [], x
+    for i, m in enumerate(ref):
+        h = m(h)
+        if i in (1, 6, 11, 20, 29):
+            res.append(h)
+    old = ops.CONV_USE_TC
+    ops.CONV_USE_TC = use_tc
+    try:
+        out = mine(x.cuda())
+        for a, b in zip(out, res):
+            assert rel_err(a, b) < tol
+        L = VGGLoss()
+        L.vgg = mine
+        xg = x.cuda().requires_grad_(True)
+        L(xg, y.cuda()).backward()
+    finally:
+        ops.CONV_USE_TC = old
+    xr = x.clone().requires_grad_(True)
+    fr, fy = [], []
+    h, hy = xr, y
+    for i, m in enumerate(ref):
+        h, hy = m(h), m(hy)
+        if i in (1, 6, 11, 20, 29):
+            fr.append(h)
+            fy.append(hy)
+    sum(wt * torch.nn.functional.l1_loss(a, b.detach()) for wt, a, b in zip([1 / 32, 1 / 16, 1 / 8, 1 / 4, 1.0], fr, fy)).backward()
+    assert grad_err(xg.grad, xr.grad, floor=1e-9) < (1e-3 if use_tc == 0 else 5e-2)
