@@ -545,8 +545,8 @@ def guard_param(p):
     (a module called twice in one pass, gradient accumulation over several backward calls, .grad bound to a flat bucket) gets an
     in-place add on the main stream -- which must then first wait for the side stream.  The common case (.grad is None: the
     engine just adopts the tensor) costs nothing."""
-    if getattr(p, '_fsv_guarded', False) or not WGRAD_SIDE_STREAM:
-        return p
+    if getattr(p, '_fsv_guarded', False) or not WGRAD_SIDE_STREAM or not p.requires_grad:
+        return p          # (a frozen parameter -- the VGG feature stack -- never receives a gradient)
 
     def hook(grad, p=p):
         if p.grad is not None and grad.is_cuda:

