@@ -31,9 +31,14 @@ def child(impl, size, K, frames):
         torch.backends.cudnn.benchmark = True
     G = networks.define_G(opt)
     G.init_temporal_network()
-    G.cuda().eval()
+    G.cuda()
     b = {k: v.cuda() for k, v in synth.make('face', 1, size, size, seed=3, K=K).items()}
     label, lref, iref = b['tgt_label'][:, 0], b['ref_label'], b['ref_image']
+    G.train()       # BatchNorm running statistics of a fresh network are (0, 1): populate them (both arms) so that eval-mode values are finite
+    with torch.no_grad():
+        for _ in range(6):
+            G(label, lref, iref, [label, b['tgt_image'][:, 0]])
+    G.eval()
 
     def run(n):
         prev = [None, None]

@@ -94,9 +94,14 @@ def test_graphed_generator_equals_eager_eval_forward():
     torch.manual_seed(0)
     G = networks.define_G(opt)
     G.init_temporal_network()
-    G.cuda().eval()
+    G.cuda()
     b = {k: v.cuda() for k, v in synth.make('pose', 1, 64, 64, seed=4).items()}
     label, lref, iref = b['tgt_label'][:, 0], b['ref_label'], b['ref_image']
+    G.train()                       # a freshly initialised network has BatchNorm running statistics (0, 1): in eval mode its activations overflow.
+    with torch.no_grad():           # A dozen training-mode forwards give it the statistics a checkpoint would carry.
+        for _ in range(12):
+            G(label, lref, iref, [label, b['tgt_image'][:, 0]])
+    G.eval()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s), torch.no_grad():
@@ -106,6 +111,7 @@ def test_graphed_generator_equals_eager_eval_forward():
         gg = GraphedGenerator(G, label, lref, iref, prev)
         g1 = gg(label, prev)
         torch.cuda.synchronize()
+        assert torch.isfinite(e1[0]).all() and float(e1[0].abs().max()) > 0
         assert float((g1[0] - e1[0]).abs().max()) < 1e-5
         prev2 = [label, e1[0].contiguous()]
         e2 = G(label, lref, iref, prev2, t=2)
