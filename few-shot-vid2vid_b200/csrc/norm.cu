@@ -281,68 +281,90 @@ extern "C" int fsv_norm_apply_fwd(const float* x, const float* mean, const float
 }
 
 // ---------------------------------------------------------------- apply backward
+// derivative of the activation that followed the norm.  With y == NULL (fsv_norm_apply_bwd2) the post-activation tensor is not read:
+// for the sign-type activations (LeakyReLU / ReLU) its sign is recomputed from the normalised input with the forward's own formula
+// (xhat * weight + bias), which removes one full-tensor read from each of the two backward passes.
+__device__ __forceinline__ float norm_act_grad(const float* __restrict__ y, long long i, float xh, float w, float b, int act) {
+    if (act == FSV_ACT_NONE) return 1.f;
+    if (y) return fsv_act_grad(y[i], act);
+    const float pre = xh * w + b;
+    return act == FSV_ACT_LRELU ? (pre > 0.f ? 1.f : FSV_LRELU_SLOPE) : (pre > 0.f ? 1.f : 0.f);
+}
 struct NormBwdF {   // (sum dy', sum dy'*xhat), dy' = dy*act'(y)
-    const float *x, *y, *dy, *mean, *rstd;
+    const float *x, *y, *dy, *mean, *rstd, *weight, *bias;
     int C, act, instance;
     long long HW;
     __device__ float2 operator()(long long row, int c) const {
         long long i = row * C + c;
         int s = instance ? (int)(row / HW) * C + c : c;
-        float g = dy[i] * fsv_act_grad(y[i], act);
         float xh = (x[i] - mean[s]) * rstd[s];
+        float g = dy[i] * norm_act_grad(y, i, xh, weight ? weight[c] : 1.f, bias ? bias[c] : 0.f, act);
         return make_float2(g, g * xh);
     }
 };
 __global__ void k_norm_apply_bwd(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
                                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ weight,
-                                 const double* __restrict__ A, const double* __restrict__ B, float* __restrict__ dx,
+                                 const float* __restrict__ bias, const double* __restrict__ A, const double* __restrict__ B, float* __restrict__ dx,
                                  long long total, int C, long long HW, int instance, int act, int batch_stats, float inv_cnt) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % C);
         int s = instance ? (int)(i / (HW * C)) * C + c : c;
         float r = rstd[s];
-        float g = dy[i] * fsv_act_grad(y[i], act);
         float w = weight ? weight[c] : 1.f;
+        float xh = (x[i] - mean[s]) * r;
+        float g = dy[i] * norm_act_grad(y, i, xh, w, bias ? bias[c] : 0.f, act);
         float v = g;
-        if (batch_stats) {
-            float xh = (x[i] - mean[s]) * r;
-            v = g - (float)A[s] * inv_cnt - xh * (float)B[s] * inv_cnt;
-        }
+        if (batch_stats) v = g - (float)A[s] * inv_cnt - xh * (float)B[s] * inv_cnt;
         dx[i] = r * w * v;
     }
 }
 // float4 variant (C % 4 == 0): the scalar kernel above spends its time on 64-bit index arithmetic, not on memory
 __global__ void k_norm_apply_bwd4(const float4* __restrict__ x, const float4* __restrict__ y, const float4* __restrict__ dy,
                                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ weight,
-                                  const double* __restrict__ A, const double* __restrict__ B, float4* __restrict__ dx,
+                                  const float* __restrict__ bias, const double* __restrict__ A, const double* __restrict__ B, float4* __restrict__ dx,
                                   long long total4, int C, long long HWC, int instance, int act, int batch_stats, float inv_cnt) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i * 4;
         const int c = (int)(e % C);
         const int s = instance ? (int)(e / HWC) * C + c : c;
         const float4 r = *reinterpret_cast<const float4*>(rstd + s);
-        const float4 d4 = dy[i], y4 = y[i];
-        float g[4] = {d4.x * fsv_act_grad(y4.x, act), d4.y * fsv_act_grad(y4.y, act), d4.z * fsv_act_grad(y4.z, act),
-                      d4.w * fsv_act_grad(y4.w, act)};
-        float w[4] = {1.f, 1.f, 1.f, 1.f};
+        const float4 d4 = dy[i];
+        float w[4] = {1.f, 1.f, 1.f, 1.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
         if (weight) {
             const float4 w4 = *reinterpret_cast<const float4*>(weight + c);
             w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
         }
+        if (bias) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + c);
+            bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w;
+        }
         const float rr[4] = {r.x, r.y, r.z, r.w};
-        float o[4];
-        if (batch_stats) {
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+        const bool need_x = batch_stats || (y == nullptr && act != FSV_ACT_NONE);
+        float xh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (need_x) {
             const float4 m = *reinterpret_cast<const float4*>(mean + s);
             const float4 x4 = x[i];
-            const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, mm[4] = {m.x, m.y, m.z, m.w};
+            xh[0] = (x4.x - m.x) * rr[0]; xh[1] = (x4.y - m.y) * rr[1]; xh[2] = (x4.z - m.z) * rr[2]; xh[3] = (x4.w - m.w) * rr[3];
+        }
+        float yv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (y != nullptr && act != FSV_ACT_NONE) {
+            const float4 y4 = y[i];
+            yv[0] = y4.x; yv[1] = y4.y; yv[2] = y4.z; yv[3] = y4.w;
+        }
+        float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float xh = (xv[j] - mm[j]) * rr[j];
-                o[j] = rr[j] * w[j] * (g[j] - (float)A[s + j] * inv_cnt - xh * (float)B[s + j] * inv_cnt);
+        for (int j = 0; j < 4; ++j) {
+            float ag = 1.f;
+            if (act != FSV_ACT_NONE) {
+                if (y != nullptr) ag = fsv_act_grad(yv[j], act);
+                else {
+                    const float pre = xh[j] * w[j] + bb[j];
+                    ag = act == FSV_ACT_LRELU ? (pre > 0.f ? 1.f : FSV_LRELU_SLOPE) : (pre > 0.f ? 1.f : 0.f);
+                }
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = rr[j] * w[j] * g[j];
+            const float g = dv[j] * ag;
+            o[j] = batch_stats ? rr[j] * w[j] * (g - (float)A[s + j] * inv_cnt - xh[j] * (float)B[s + j] * inv_cnt) : rr[j] * w[j] * g;
         }
         dx[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -359,17 +381,19 @@ __global__ void k_norm_param_grads(const double* __restrict__ A, const double* _
     dbias[c] = (float)a;
     dweight[c] = (float)b;
 }
-extern "C" int fsv_norm_apply_bwd(const float* x, const float* y, const float* dy, const float* mean, const float* rstd,
-                                  const float* weight, float* dx, float* dweight, float* dbias, double* scratch,
-                                  int N, int HW, int C, int mode, int act, int batch_stats, void* stream) {
+static int norm_apply_bwd_impl(const float* x, const float* y, const float* dy, const float* mean, const float* rstd,
+                               const float* weight, const float* bias, float* dx, float* dweight, float* dbias, double* scratch,
+                               int N, int HW, int C, int mode, int act, int batch_stats, void* stream) {
     FSV_REQUIRE(N > 0 && HW > 0 && C > 0 && scratch, "norm_apply_bwd: bad args");
+    FSV_REQUIRE(y != nullptr || act == FSV_ACT_NONE || act == FSV_ACT_LRELU || act == FSV_ACT_RELU,
+                "norm_apply_bwd: without y only the sign-type activations can be differentiated");
     cudaStream_t st = (cudaStream_t)stream;
     int inst = mode == FSV_NORM_INSTANCE;
     int groups = inst ? N : 1;
     long long rpg = inst ? HW : (long long)N * HW;
     double* A = scratch;
     double* B = scratch + (size_t)groups * C;
-    NormBwdF f{x, y, dy, mean, rstd, C, act, inst, (long long)HW};
+    NormBwdF f{x, y, dy, mean, rstd, weight, bias, C, act, inst, (long long)HW};
     StoreE e{A, B, C};
     int rc = launch_reduce2(f, e, groups, rpg, C, B + (size_t)groups * C, st, "norm_bwd_reduce");
     if (rc) return rc;
@@ -380,14 +404,26 @@ extern "C" int fsv_norm_apply_bwd(const float* x, const float* y, const float* d
     }
     long long total = (long long)N * HW * C;
     if (C % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0)
-        k_norm_apply_bwd4<<<ew_grid(total / 4), 256, 0, st>>>((const float4*)x, (const float4*)y, (const float4*)dy, mean, rstd, weight, A, B,
+        k_norm_apply_bwd4<<<ew_grid(total / 4), 256, 0, st>>>((const float4*)x, (const float4*)y, (const float4*)dy, mean, rstd, weight, bias, A, B,
                                                               (float4*)dx, total / 4, C, (long long)HW * C, inst, act, batch_stats,
                                                               (float)(1.0 / (double)rpg));
     else
-        k_norm_apply_bwd<<<ew_grid(total), 256, 0, st>>>(x, y, dy, mean, rstd, weight, A, B, dx, total, C, HW, inst, act, batch_stats,
+        k_norm_apply_bwd<<<ew_grid(total), 256, 0, st>>>(x, y, dy, mean, rstd, weight, bias, A, B, dx, total, C, HW, inst, act, batch_stats,
                                                           (float)(1.0 / (double)rpg));
     FSV_CHECK_LAUNCH("norm_apply_bwd");
     return FSV_OK;
+}
+
+extern "C" int fsv_norm_apply_bwd(const float* x, const float* y, const float* dy, const float* mean, const float* rstd,
+                                  const float* weight, float* dx, float* dweight, float* dbias, double* scratch,
+                                  int N, int HW, int C, int mode, int act, int batch_stats, void* stream) {
+    FSV_REQUIRE(y != nullptr, "norm_apply_bwd: y is required (fsv_norm_apply_bwd2 differentiates the activation without it)");
+    return norm_apply_bwd_impl(x, y, dy, mean, rstd, weight, nullptr, dx, dweight, dbias, scratch, N, HW, C, mode, act, batch_stats, stream);
+}
+extern "C" int fsv_norm_apply_bwd2(const float* x, const float* dy, const float* mean, const float* rstd, const float* weight,
+                                   const float* bias, float* dx, float* dweight, float* dbias, double* scratch,
+                                   int N, int HW, int C, int mode, int act, int batch_stats, void* stream) {
+    return norm_apply_bwd_impl(x, nullptr, dy, mean, rstd, weight, bias, dx, dweight, dbias, scratch, N, HW, C, mode, act, batch_stats, stream);
 }
 
 // ---------------------------------------------------------------- SPADE norm backward (x may be read through a x2 upsample)

@@ -84,6 +84,7 @@ SIGNATURES = {
     'fsv_norm_from_running': [c_vp, c_vp, c_int, c_float, c_vp, c_vp, c_vp],
     'fsv_norm_apply_fwd': [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     'fsv_norm_apply_bwd': [c_vp] * 10 + [c_int] * 6 + [c_vp],
+    'fsv_norm_apply_bwd2': [c_vp] * 10 + [c_int] * 6 + [c_vp],
     'fsv_spade_fwd': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp],
     'fsv_spade_fwd_tc_eligible': [_SD],
     'fsv_spade_fwd_tc': [_SD, c_vp, c_vp, c_vp, PtrArray, PtrArray, PtrArray, PtrArray, PtrArray, c_vp, c_vp],

@@ -93,7 +93,7 @@ def _off(t, off_floats):
 # branch stream uses lane 1.  FSV_BRANCH_STREAMS=0 keeps the forward on one stream.
 BRANCH_STREAMS = os.environ.get('FSV_BRANCH_STREAMS', '1') != '0'
 _BRANCH, _LANES = {}, {}
-_LANE_FNS = ('fsv_norm_stats', 'fsv_norm_stats_finalize', 'fsv_norm_apply_bwd', 'fsv_spade_norm_bwd')
+_LANE_FNS = ('fsv_norm_stats', 'fsv_norm_stats_finalize', 'fsv_norm_apply_bwd', 'fsv_norm_apply_bwd2', 'fsv_spade_norm_bwd')
 
 
 def aux_stream(index):
@@ -781,12 +781,14 @@ class NormActFn(torch.autograd.Function):
         _call(lib.fsv_norm_apply_fwd, ptr(x), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), ptr(y), n, h * w, c, mode,
               cfg.get('act', ACT_NONE), stream())
         ctx.cfg = cfg
-        ctx.save_for_backward(x, y, mean, rstd, weight)
+        # the backward recomputes a sign-type activation's derivative from x (fsv_norm_apply_bwd2): y is not kept for it
+        recompute = cfg.get('act', ACT_NONE) in (ACT_NONE, ACT_LRELU, ACT_RELU)
+        ctx.save_for_backward(x, None if recompute else y, mean, rstd, weight, bias)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, rstd, weight = ctx.saved_tensors
+        x, y, mean, rstd, weight, bias = ctx.saved_tensors
         cfg = ctx.cfg
         dy = _c(dy)
         n, h, w, c = x.shape
@@ -798,8 +800,12 @@ class NormActFn(torch.autograd.Function):
         dbs = torch.empty(c, device=x.device, dtype=torch.float32) if weight is not None else None
         rpg = h * w if mode == NORM_INSTANCE else n * h * w
         scratch = torch.empty(2 * groups * c + int(lib.fsv_norm_work_doubles(groups, c, rpg)), device=x.device, dtype=torch.float64)
-        _call(lib.fsv_norm_apply_bwd, ptr(x), ptr(y), ptr(dy), ptr(mean), ptr(rstd), ptr(weight), ptr(dx), ptr(dwt), ptr(dbs),
-              ptr(scratch), n, h * w, c, mode, cfg.get('act', ACT_NONE), batch_stats, stream())
+        if y is None:
+            _call(lib.fsv_norm_apply_bwd2, ptr(x), ptr(dy), ptr(mean), ptr(rstd), ptr(weight), ptr(bias), ptr(dx), ptr(dwt), ptr(dbs),
+                  ptr(scratch), n, h * w, c, mode, cfg.get('act', ACT_NONE), batch_stats, stream())
+        else:
+            _call(lib.fsv_norm_apply_bwd, ptr(x), ptr(y), ptr(dy), ptr(mean), ptr(rstd), ptr(weight), ptr(dx), ptr(dwt), ptr(dbs),
+                  ptr(scratch), n, h * w, c, mode, cfg.get('act', ACT_NONE), batch_stats, stream())
         return dx, dwt, dbs, None, None, None
 
 

@@ -165,6 +165,12 @@ int fsv_norm_apply_bwd(const float* x, const float* y, const float* dy, const fl
                        const float* weight, float* dx, float* dweight, float* dbias, double* scratch,
                        int N, int HW, int C, int mode, int act, int batch_stats, void* stream);
 
+/* Same backward WITHOUT the post-activation tensor: for act in {none, LeakyReLU, ReLU} the activation's derivative is recomputed from
+ * sign(xhat*weight + bias) (the forward's own expression), saving one full-tensor read in each of the two passes. */
+int fsv_norm_apply_bwd2(const float* x, const float* dy, const float* mean, const float* rstd, const float* weight,
+                        const float* bias, float* dx, float* dweight, float* dbias, double* scratch,
+                        int N, int HW, int C, int mode, int act, int batch_stats, void* stream);
+
 /* ------------------------------------------------------------------ fused SPADE (normalization.py:37-52 + architecture.py:96-97) */
 #define FSV_SPADE_MAX_MAPS 3
 typedef struct fsv_spade_desc {
