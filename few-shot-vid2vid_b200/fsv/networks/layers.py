@@ -20,6 +20,12 @@ from ..ops import ACT_NONE, ACT_LRELU, NORM_BATCH, NORM_INSTANCE
 
 # one grouped spectral-norm launch per network forward instead of one per module (see SpectralPlanner); False = per-module calls
 GROUP_SPECTRAL = os.environ.get('FSV_GROUP_SPECTRAL', '1') != '0'
+# Number of groups a large network's spectral weights are split into (contiguous chunks of the call order, balanced by size).  With
+# several chunks the grouped backward of a chunk runs as soon as that chunk's layers are done, so its weight gradients reach the
+# data-parallel all-reduce buckets earlier; measured at N=2 that bought nothing over one group (the buckets
+# fired on the side stream already overlap), so the default stays 1 (FSV_SPECTRAL_CHUNKS overrides).
+SPECTRAL_GROUP_CHUNKS = int(os.environ.get('FSV_SPECTRAL_CHUNKS', '1'))
+SPECTRAL_CHUNK_MIN_NUMEL = int(os.environ.get('FSV_SPECTRAL_CHUNK_MIN', '20000000'))      # smaller networks (the discriminators) stay in one group
 
 
 class SpectralPlanner:
@@ -57,12 +63,27 @@ class SpectralPlanner:
         if not mods:
             self.ready = {}
             return True
-        entries = [(m.weight_orig, m.weight_u, m.weight_v, want) for m, want in mods]
-        if plan['group'] is None or not plan['group'].matches(entries):
-            plan['group'] = ops.SpectralGroup(entries)
-        m0 = mods[0][0]
-        ws, wts = ops.spectral_group_weights(plan['group'], m0.training, m0.fsv_spectral_eps, [e[0] for e in entries])
-        self.ready = {id(m): (w, wt) for (m, _), w, wt in zip(mods, ws, wts)}
+        if plan.get('chunks') is None:
+            total = sum(m.weight_orig.numel() for m, _ in mods)
+            k = SPECTRAL_GROUP_CHUNKS if total > SPECTRAL_CHUNK_MIN_NUMEL else 1          # only the generator is worth splitting
+            chunks, cur, acc = [], [], 0
+            for m, want in mods:
+                cur.append((m, want))
+                acc += m.weight_orig.numel()
+                if len(chunks) < k - 1 and acc >= total * (len(chunks) + 1) / k:
+                    chunks.append(cur)
+                    cur = []
+            if cur:
+                chunks.append(cur)
+            plan['chunks'], plan['groups'] = chunks, [None] * len(chunks)
+        self.ready = {}
+        for ci, chunk in enumerate(plan['chunks']):
+            entries = [(m.weight_orig, m.weight_u, m.weight_v, want) for m, want in chunk]
+            if plan['groups'][ci] is None or not plan['groups'][ci].matches(entries):
+                plan['groups'][ci] = ops.SpectralGroup(entries)
+            m0 = chunk[0][0]
+            ws, wts = ops.spectral_group_weights(plan['groups'][ci], m0.training, m0.fsv_spectral_eps, [e[0] for e in entries])
+            self.ready.update({id(m): (w, wt) for (m, _), w, wt in zip(chunk, ws, wts)})
         return True
 
     def end(self):

@@ -51,15 +51,21 @@ class GradSync:
     ``arm`` matters because the generator's backward also runs through the discriminator: D's buckets must not fire then.
     Everything is capturable into a CUDA graph (no host-device synchronisation; NCCL collectives are graph-capturable)."""
 
-    def __init__(self, params, bucket_mb=32, group=None, overlap=None):
+    def __init__(self, params, bucket_mb=32, group=None, overlap=None, stream_fire=None):
         self.params = [p for p in params if p.requires_grad]
+        on_gpu = any(p.is_cuda for p in self.params)
         if overlap is None:
             # With the side-stream weight gradients (ops.WGRAD_SIDE_STREAM) the leaves must receive their gradients with .grad ==
             # None (adoption launches nothing; an in-place add on the compute stream would race the side stream), so the buckets are
-            # filled by ONE multi-tensor copy after backward instead of in place, and the all-reduces start then ("collect" mode).
+            # filled by multi-tensor copies instead of in place ("collect" mode).
             from . import ops
-            overlap = not (ops.WGRAD_SIDE_STREAM and any(p.is_cuda for p in self.params))
-        self.group, self.overlap = group, overlap
+            overlap = not (ops.WGRAD_SIDE_STREAM and on_gpu)
+        if stream_fire is None:
+            # collect mode, refined: a post-accumulate hook per parameter counts arrivals, and a bucket whose last gradient has landed
+            # is copied and all-reduced right away ON THE SIDE STREAM, i.e. concurrently with the rest of backward; only the buckets
+            # that complete at the very end of the pass are left for sync().  (FSV_SYNC_STREAM=0: everything after backward.)
+            stream_fire = (not overlap) and os.environ.get('FSV_SYNC_STREAM', '1') != '0'
+        self.group, self.overlap, self.stream_fire = group, overlap, stream_fire and not overlap
         limit = max(1, int(bucket_mb * (1 << 20) // 4))
         self.buckets, cur, size = [], [], 0
         for p in reversed(self.params):
@@ -88,7 +94,8 @@ class GradSync:
         self.count = [0] * len(self.buckets)
         self.fired = [False] * len(self.buckets)
         self.handles = []
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] if overlap else []
+        hook = self._on_grad if overlap else (self._on_grad_stream if self.stream_fire else None)
+        self._hooks = [p.register_post_accumulate_grad_hook(hook) for p in self.params] if hook is not None else []
         backend = dist.get_backend(group) if dist.is_initialized() else 'none'
         self.native_avg = backend == 'nccl'
 
@@ -133,8 +140,67 @@ class GradSync:
         if self.count[bi] == len(self.buckets[bi]) and not self.fired[bi]:
             self._fire(bi)
 
+    def _side(self, bucket):
+        """(side stream context, compute stream) for a bucket's copy + collective; plain context on CPU tensors."""
+        if not bucket[0].is_cuda:
+            return None, None
+        from . import ops
+        cur = torch.cuda.current_stream()
+        dev = torch.cuda.current_device()
+        side = ops._SIDE.get(dev)
+        if side is None:
+            side = ops._SIDE[dev] = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)            # gradients produced on the compute stream so far (the side-stream ones are ordered anyway)
+        return side, cur
+
+    def _fire_stream(self, bi):
+        """collect-mode bucket: copy the adopted gradients into the flat bucket and all-reduce it, both on the side stream."""
+        self.fired[bi] = True
+        bucket = self.buckets[bi]
+        side, cur = self._side(bucket)
+        ctx = torch.cuda.stream(side) if side is not None else _Null()
+        with ctx:
+            have = [p for p in bucket if p.grad is not None and p.grad is not self.views[p]]
+            if side is not None:
+                for p in have:
+                    p.grad.record_stream(side)
+            if have:
+                torch._foreach_copy_([self.views[p] for p in have], [p.grad for p in have])
+            for p in bucket:
+                if p.grad is None:
+                    self.views[p].zero_()
+            if self.world > 1:
+                op = dist.ReduceOp.AVG if self.native_avg else dist.ReduceOp.SUM
+                self.handles.append((bi, dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True)))
+
+    def _on_grad_stream(self, p):
+        if not self.armed:
+            return
+        bi = self.bucket_of[p]
+        self.count[bi] += 1
+        if self.count[bi] == len(self.buckets[bi]) and not self.fired[bi]:
+            self._fire_stream(bi)
+
     def __call__(self):
         """After backward(): launch the buckets that did not fill up, wait for all of them, finish the mean."""
+        if self.stream_fire:
+            if not self.armed:
+                self.arm()
+            for bi in range(len(self.buckets)):
+                if not self.fired[bi]:
+                    self._fire_stream(bi)
+            side = self._side(self.buckets[0])[0]
+            for bi, h in self.handles:
+                h.wait()                 # the compute stream waits for the collective (which waited for the side stream's copy)
+                if not self.native_avg:
+                    self.flat[bi].mul_(1.0 / self.world)
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)      # world == 1 / zero-fills: still ordered before the optimizer
+            for p in self.params:
+                p.grad = self.views[p]
+            self.armed = False
+            self.handles = []
+            return
         if not self.overlap:
             have = [p for p in self.params if p.grad is not None and p.grad is not self.views[p]]
             if have:
@@ -160,6 +226,14 @@ class GradSync:
                 self.flat[bi].mul_(1.0 / self.world)
         self.armed = False
         self.handles = []
+
+
+class _Null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 def broadcast_state(module, src=0, group=None):

@@ -51,12 +51,27 @@ CASES = [
     ('face', 32, 32, ['--n_shot', '2'], False, 2),
     ('face', 64, 64, ['VGG'], False, 1),            # perceptual loss on (VGG19 with seeded random weights on both sides)
     ('pose', 128, 128, ['VGG'], False, 1),          # ... including the face-region VGG term of loss_collector.py:82
+    ('face', 64, 64, ['CHUNKS'], False, 1),         # grouped spectral norm split into 3 groups (the data-parallel configuration)
 ]
 
 
 @pytest.mark.parametrize('kind,H,W,extra,temporal,K', CASES)
 def test_step_losses_match_reference_model(env, kind, H, W, extra, temporal, K):
     use_vgg = 'VGG' in extra
+    if 'CHUNKS' in extra:
+        from fsv.networks import layers
+        env_patch = pytest.MonkeyPatch()
+        env_patch.setattr(layers, 'SPECTRAL_GROUP_CHUNKS', 3)
+        env_patch.setattr(layers, 'SPECTRAL_CHUNK_MIN_NUMEL', 0)
+        try:
+            _run_case(env, kind, H, W, [], temporal, K, False, expect_chunks=3)
+        finally:
+            env_patch.undo()
+        return
+    _run_case(env, kind, H, W, extra, temporal, K, use_vgg)
+
+
+def _run_case(env, kind, H, W, extra, temporal, K, use_vgg, expect_chunks=None):
     opt = refenv.parse_opt(kind, H, W, 2, extra=TINY + [e for e in extra if e != 'VGG'], gpu=False, vgg=use_vgg)
     ref = _ref_model(opt, temporal)
     step = env.Vid2VidStep(opt)
@@ -84,6 +99,13 @@ def test_step_losses_match_reference_model(env, kind, H, W, extra, temporal, K):
         assert abs(float(a) - float(b)) < 2e-4 * max(1.0, abs(float(a))), ('G', n, [float(x) for x in g0], [float(x) for x in g1.values()])
     for a, b in zip(prev0, prev1):
         assert (a - b).abs().max() < 1e-4
+    if expect_chunks is not None:
+        g2, _, _ = step.generator_losses(batch)          # same call signature again: this one runs on the recorded (chunked) plan
+        g3, _, _ = ref(dl, mode='generator')
+        for (n, b), a in zip(g2.items(), g3):
+            assert abs(float(a) - float(b)) < 2e-4 * max(1.0, abs(float(a))), ('G#2', n, float(a), float(b))
+        plans = [pl for pl in step.netG.__dict__['_planner'].plans.values() if pl.get('chunks')]
+        assert plans and all(len(pl['chunks']) == expect_chunks for pl in plans), [len(pl['chunks']) for pl in plans]
     sum(v.mean() for v in g1.values()).backward()
     sum(v.mean() for v in g0).backward()
     for (n, p0), (_, p1) in zip(ref.netG.named_parameters(), step.netG.named_parameters()):

@@ -31,17 +31,18 @@ def _worker(rank, world, port, out):
     x = torch.randn(8, 6, generator=g)
     lo, hi = parallel.shard_batch(8, rank, world)
     unused = torch.nn.Parameter(torch.zeros(3))          # a parameter without grad on this rank
-    for overlap in (True, False):                         # in-place buckets fired from hooks / collect-after-backward
+    # in-place buckets fired from hooks / collect-after-backward / collect with buckets fired from hooks as they complete
+    for overlap, stream_fire in ((True, False), (False, False), (False, True)):
         for p in list(net.parameters()) + [unused]:
             p.grad = None
-        sync = parallel.GradSync(list(net.parameters()) + [unused], bucket_mb=5e-5, overlap=overlap)      # tiny buckets: several of them
+        sync = parallel.GradSync(list(net.parameters()) + [unused], bucket_mb=5e-5, overlap=overlap, stream_fire=stream_fire)      # tiny buckets: several of them
         assert len(sync.buckets) >= 3
         for it in range(2):                               # twice: zero / arm / backward / sync protocol, views stay bound
             sync.zero()
             sync.arm()
             loss = net(x[lo:hi]).square().mean()
             loss.backward()
-            assert any(sync.fired) == overlap             # overlap: buckets were launched from inside backward
+            assert any(sync.fired) == (overlap or stream_fire)       # buckets were launched from inside backward
             sync()
             assert all(p.grad is sync.views[p] for p in sync.params)
     ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
