@@ -21,6 +21,8 @@ def mark(msg):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('CHECK_DP_DUMP_S', '120')), exit=True)      # a hang prints every thread's stack and exits
     from fsv import model, parallel, trainer
     from fsv.networks import layers
     rank, world, local = parallel.init_from_env()
@@ -110,6 +112,10 @@ def main():
     if rank == 0:
         print(json.dumps(report))
     dist.barrier()
+    torch.cuda.synchronize()
+    del graphed, syncG, syncD, optG, optD          # the captured graph holds NCCL work: it must be gone before the communicator is torn down
+    import gc
+    gc.collect()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
