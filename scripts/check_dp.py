@@ -116,8 +116,9 @@ def main():
     del graphed, syncG, syncD, optG, optD          # the captured graph holds NCCL work: it must be gone before the communicator is torn down
     import gc
     gc.collect()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0 if ok else 1)          # (no destroy_process_group: a communicator that was captured into a CUDA graph may block in teardown)
 
 
 if __name__ == '__main__':
