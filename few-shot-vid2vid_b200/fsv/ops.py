@@ -768,6 +768,9 @@ def _stats(x, n, hw, c, mode, training, running_mean, running_var, eps, momentum
     return mean, rstd
 
 
+NORM_BWD_RECOMPUTE = os.environ.get('FSV_NORM_BWD2', '1') != '0'      # 0: keep y for the backward (fsv_norm_apply_bwd)
+
+
 class NormActFn(torch.autograd.Function):
     """y = act(norm(x) * weight + bias): BatchNorm (local statistics) or InstanceNorm, + activation."""
 
@@ -782,7 +785,7 @@ class NormActFn(torch.autograd.Function):
               cfg.get('act', ACT_NONE), stream())
         ctx.cfg = cfg
         # the backward recomputes a sign-type activation's derivative from x (fsv_norm_apply_bwd2): y is not kept for it
-        recompute = cfg.get('act', ACT_NONE) in (ACT_NONE, ACT_LRELU, ACT_RELU)
+        recompute = NORM_BWD_RECOMPUTE and cfg.get('act', ACT_NONE) in (ACT_NONE, ACT_LRELU, ACT_RELU)
         ctx.save_for_backward(x, None if recompute else y, mean, rstd, weight, bias)
         return y
 
