@@ -432,10 +432,18 @@ static int tc_env_stages() {
     }
     return v;
 }
-static int pick_stages(int stage_bytes, int num_k) {
+// FSV_TC_DEEP=1: a launch whose tiles do not even fill the SMs once (one CTA per SM whatever the ring costs) takes a 200 KB ring, i.e.
+// twice the bytes in flight per SM (off by default: in the multi-stream training graph the big CTA also keeps the other streams'
+// kernels off its SM).
+static int tc_env_deep() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FSV_TC_DEEP"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v;
+}
+static int pick_stages(int stage_bytes, int num_k, long long total_tiles) {
     int st = tc_env_stages();
     if (st <= 0) {
-        const int budget = 96 * 1024;                       // two CTAs per SM
+        const int budget = (tc_env_deep() && total_tiles <= fsv_sm_count()) ? 200 * 1024 : 96 * 1024;      // default: two CTAs per SM
         st = budget / stage_bytes;
         if (st < 3) st = 3;
     }
@@ -449,7 +457,8 @@ static int pick_stages(int stage_bytes, int num_k) {
 
 static int launch_tc(TcParams& p, int tiles_n, const float* bias, const float* residual, float* y, cudaStream_t st, const char* who) {
     const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 4;
-    p.stages = pick_stages(stage_bytes, p.ntaps * (p.Cin / TC_BK));
+    p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+    p.stages = pick_stages(stage_bytes, p.ntaps * (p.Cin / TC_BK), (long long)p.m_tiles * (p.Cout / p.BN));
     const int smem_bytes = p.stages * stage_bytes + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 1024;
     static unsigned long long configured = 0;
     if (fsv_first_on_device(&configured)) {
