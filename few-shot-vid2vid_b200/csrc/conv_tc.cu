@@ -42,6 +42,11 @@ struct __align__(64) TcParams {
     int stages;                 // smem ring depth (2..TC_MAX_STAGES)
     int m_tiles;                // pixel tiles (tiles_w * tiles_h * tiles_n), used by the persistent variant
     int OH, OW, os, oph, opw;   // output buffer dims and pixel stride/offset: pixel (ho,wo) of the GEMM lands at (ho*os+oph, wo*os+opw)
+    // persistent variant only: ncls > 1 = several output-parity classes of one layer (stride-2 dgrad, collapsed up2 forward) in ONE
+    // launch.  Class c owns taps[cls_t0[c] .. +cls_nt[c]) and writes at pixel offset (c >> 1, c & 1); the classes share the tile
+    // geometry, so tile index = (class, channel block, pixel tile).
+    int ncls;
+    int cls_t0[4], cls_nt[4];
 };
 
 // ------------------------------------------------------------------ kernel
@@ -198,9 +203,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_p(const __grid_constant__ Tc
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = p.Cin / TC_BK;
-    const int num_k = p.ntaps * kblocks;
     const int m_tiles = p.m_tiles;
-    const int total = m_tiles * (p.Cout / BN);
+    const int per_cls = m_tiles * (p.Cout / BN);
+    const int ncls = p.ncls > 1 ? p.ncls : 1;
+    const int total = per_cls * ncls;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STG; ++s) {
@@ -230,8 +236,11 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_p(const __grid_constant__ Tc
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                int mt = tile % m_tiles;
-                const int co0 = (tile / m_tiles) * BN;
+                const int cls = tile / per_cls, tcl = tile - cls * per_cls;
+                const int t0 = p.ncls > 1 ? p.cls_t0[cls] : 0;
+                const int num_k = (p.ncls > 1 ? p.cls_nt[cls] : p.ntaps) * kblocks;
+                int mt = tcl % m_tiles;
+                const int co0 = (tcl / m_tiles) * BN;
                 const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
                 const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
                 const int n0 = mt * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_p(const __grid_constant__ Tc
                     const uint32_t ph = (it / STG) & 1;
                     mbar_wait(smem_u32(&bars[STG + s]), ph ^ 1);
                     const int t = kb / kblocks, cb = kb - t * kblocks;
-                    const TcTap tap = p.taps[t];
+                    const TcTap tap = p.taps[t0 + t];
                     const uint32_t full = smem_u32(&bars[s]);
                     const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
                     mbar_expect_tx(full, (uint32_t)stage_bytes);
@@ -255,6 +264,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_p(const __grid_constant__ Tc
             uint32_t it = 0, i = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
                 const uint32_t buf = i & 1;
+                const int num_k = (p.ncls > 1 ? p.cls_nt[tile / per_cls] : p.ntaps) * kblocks;
                 mbar_wait(smem_u32(&acc_empty[buf]), ((i >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * accw;
@@ -280,8 +290,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_p(const __grid_constant__ Tc
         uint32_t i = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
             const uint32_t buf = i & 1;
-            int mt = tile % m_tiles;
-            const int co0 = (tile / m_tiles) * BN;
+            const int cls = tile / per_cls, tcl = tile - cls * per_cls;
+            const int oph = p.ncls > 1 ? (cls >> 1) : p.oph, opw = p.ncls > 1 ? (cls & 1) : p.opw;
+            int mt = tcl % m_tiles;
+            const int co0 = (tcl / m_tiles) * BN;
             const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
             const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
             const int n0 = mt * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc_p(const __grid_constant__ Tc
             const int tn = r2 / p.TH;
             const int n = n0 + tn, ho = h0 + th, wo = w0 + tw;
             const bool valid = (n < p.N) && (ho < p.Ho) && (wo < p.Wo);
-            const long long pix = ((long long)n * p.OH + (ho * p.os + p.oph)) * p.OW + (wo * p.os + p.opw);
+            const long long pix = ((long long)n * p.OH + (ho * p.os + oph)) * p.OW + (wo * p.os + opw);
             float* yrow = y + pix * p.y_ld + p.y_coff + co0;
             const float* rrow = residual ? residual + pix * p.res_ld + p.res_coff + co0 : nullptr;
             mbar_wait(smem_u32(&acc_full[buf]), (i >> 1) & 1);
@@ -455,25 +467,40 @@ static int pick_stages(int stage_bytes, int num_k, long long total_tiles) {
     return st;
 }
 
+static int tc_persist() {
+    static int persist = -1;
+    if (persist < 0) { const char* e = getenv("FSV_TC_PERSIST"); persist = (e && atoi(e) == 0) ? 0 : 1; }
+    return persist;
+}
+// the four output-parity classes of a stride-2 dgrad / collapsed up2 forward as ONE launch of the persistent kernel (each class alone
+// fills a quarter of the SMs on the low-resolution layers, and the four launches were serialised on one stream).  FSV_TC_MERGE=0: four launches.
+static int tc_merge_classes() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FSV_TC_MERGE"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v && tc_persist();
+}
+
 static int launch_tc(TcParams& p, int tiles_n, const float* bias, const float* residual, float* y, cudaStream_t st, const char* who) {
     const int stage_bytes = TC_A_BYTES + p.BN * TC_BK * 4;
+    const int ncls = p.ncls > 1 ? p.ncls : 1;
     p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-    p.stages = pick_stages(stage_bytes, p.ntaps * (p.Cin / TC_BK), (long long)p.m_tiles * (p.Cout / p.BN));
+    int max_taps = p.ntaps;
+    if (ncls > 1) { max_taps = 0; for (int c = 0; c < ncls; ++c) max_taps = p.cls_nt[c] > max_taps ? p.cls_nt[c] : max_taps; }
+    p.stages = pick_stages(stage_bytes, max_taps * (p.Cin / TC_BK), (long long)p.m_tiles * (p.Cout / p.BN) * ncls);
     const int smem_bytes = p.stages * stage_bytes + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 1024;
     static unsigned long long configured = 0;
     if (fsv_first_on_device(&configured)) {
         FSV_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     }
-    p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-    static int persist = -1;
-    if (persist < 0) { const char* e = getenv("FSV_TC_PERSIST"); persist = (e && atoi(e) == 0) ? 0 : 1; }
+    const int persist = tc_persist();
+    FSV_REQUIRE(persist || ncls == 1, "%s: merged parity classes need the persistent kernel", who);
     if (persist) {      // default since round 2 (passes tests/test_gpu_tc.py on the B200, -1.2 ms per pose512 step); FSV_TC_PERSIST=0 = one tile per CTA
         static unsigned long long configured_p = 0;
         if (fsv_first_on_device(&configured_p)) {
             FSV_CUDA(cudaFuncSetAttribute(k_conv_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         }
         const int smem_p = smem_bytes + 4 * 8;
-        const long long total = (long long)p.m_tiles * (p.Cout / p.BN);
+        const long long total = (long long)p.m_tiles * (p.Cout / p.BN) * ncls;
         const int per_sm = smem_p <= 110 * 1024 ? 2 : 1;
         long long gx = (long long)fsv_sm_count() * per_sm;
         if (gx > total) gx = total;
@@ -573,6 +600,46 @@ extern "C" int fsv_conv2d_dgrad_tc(const fsv_conv_desc* d, const float* dy, cons
     const int taps_all = d->kh * d->kw;
     const long long ld = d->y_ld;
     const float* dyb = dy + d->y_coff;
+    if (d->stride == 2 && d->H % 2 == 0 && d->W % 2 == 0 && tc_merge_classes()) {
+        // all four parity classes have H/2 x W/2 pixels: one launch, tile index = (class, channel block, pixel tile)
+        const int OHc = d->H / 2, OWc = d->W / 2;
+        TcParams p;
+        memset(&p, 0, sizeof(p));
+        int TW, TH, TN;
+        pick_tile(OHc, OWc, TW, TH, TN);
+        p.TW = TW; p.TH = TH; p.TN = TN;
+        p.tiles_w = fsv_cdiv(OWc, TW); p.tiles_h = fsv_cdiv(OHc, TH);
+        const int tiles_n = fsv_cdiv(d->N, TN);
+        p.Cin = d->Cout; p.Cout = d->Cin; p.N = d->N; p.Ho = OHc; p.Wo = OWc;
+        p.OH = d->H; p.OW = d->W; p.os = 2;
+        p.y_ld = d->x_ld; p.y_coff = d->x_coff; p.res_ld = d->x_ld; p.res_coff = 0; p.act = FSV_ACT_NONE; p.out_scale = 1.f;
+        const int BN = occupancy_bn(BN0, d->Cin, 4LL * p.tiles_w * p.tiles_h * tiles_n);
+        p.BN = BN;
+        p.ncls = 4;
+        int nt = 0;
+        for (int cls = 0; cls < 4; ++cls) {
+            const int ph = cls >> 1, pw = cls & 1;
+            p.cls_t0[cls] = nt;
+            for (int r = 0; r < d->kh; ++r)
+                for (int s = 0; s < d->kw; ++s) {
+                    const int th = ph + d->pad - r, tw = pw + d->pad - s;
+                    if ((th & 1) || (tw & 1)) continue;
+                    TcTap& t = p.taps[nt++];
+                    t.map = 0; t.wk = r * d->kw + s;
+                    t.dh = th / 2; t.dw = tw / 2;          // even (may be negative: exact division)
+                }
+            p.cls_nt[cls] = nt - p.cls_t0[cls];
+            FSV_REQUIRE(p.cls_nt[cls] > 0, "conv2d_dgrad_tc: kernel %dx%d stride %d leaves a parity class without taps", d->kh, d->kw, d->stride);
+        }
+        p.ntaps = nt;
+        int rc = encode_act_map(&p.amap[0], dyb, d->Cout, d->y_ld, d->Wo, d->Ho, d->N, ld, ld * d->Wo, ld * d->Wo * d->Ho, TW, TH, TN);
+        FSV_REQUIRE(rc == 0, "conv2d_dgrad_tc: cuTensorMapEncodeTiled(A) failed with %d", rc);
+        p.w_per_sample = d->w_nstride != 0;
+        rc = encode_weight_map(&p.bmap, wt, (long long)taps_all * d->Cout, d->Cin, BN, p.w_per_sample ? d->N : 1,
+                               (long long)taps_all * d->Cout * d->Cin);
+        FSV_REQUIRE(rc == 0, "conv2d_dgrad_tc: cuTensorMapEncodeTiled(B) failed with %d", rc);
+        return launch_tc(p, tiles_n, nullptr, nullptr, dx, (cudaStream_t)stream, "conv2d_dgrad_tc");
+    }
     const int nclass = d->stride == 1 ? 1 : 4;
     for (int cls = 0; cls < nclass; ++cls) {
         const int ph = d->stride == 1 ? 0 : cls / 2, pw = d->stride == 1 ? 0 : cls % 2;
@@ -642,6 +709,37 @@ extern "C" int fsv_conv2d_fwd_tc_up2(const fsv_conv_desc* d, const float* x, con
     const int Hs = d->H / 2, Ws = d->W / 2;
     const int BN0 = pick_bn(d->Cout);
     const long long ld = d->x_ld;
+    if (tc_merge_classes()) {
+        TcParams p;
+        memset(&p, 0, sizeof(p));
+        int TW, TH, TN;
+        pick_tile(Hs, Ws, TW, TH, TN);
+        p.TW = TW; p.TH = TH; p.TN = TN;
+        p.tiles_w = fsv_cdiv(Ws, TW); p.tiles_h = fsv_cdiv(Hs, TH);
+        const int tiles_n = fsv_cdiv(d->N, TN);
+        p.Cin = d->Cin; p.Cout = d->Cout; p.N = d->N; p.Ho = Hs; p.Wo = Ws;
+        p.OH = d->Ho; p.OW = d->Wo; p.os = 2;
+        p.y_ld = d->y_ld; p.y_coff = d->y_coff; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.act = d->act; p.out_scale = d->out_scale;
+        const int BN = occupancy_bn(BN0, d->Cout, 4LL * p.tiles_w * p.tiles_h * tiles_n);
+        p.BN = BN;
+        p.ncls = 4;
+        p.ntaps = 16;
+        for (int cls = 0; cls < 4; ++cls) {
+            const int ph = cls >> 1, pw = cls & 1;
+            p.cls_t0[cls] = 4 * cls;
+            p.cls_nt[cls] = 4;
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                    TcTap& t = p.taps[4 * cls + a * 2 + b];
+                    t.map = 0; t.dh = a + ph - 1; t.dw = b + pw - 1; t.wk = ((ph * 2 + pw) * 2 + a) * 2 + b;
+                }
+        }
+        int rc = encode_act_map(&p.amap[0], x + d->x_coff, d->Cin, d->x_ld, Ws, Hs, d->N, ld, ld * Ws, ld * Ws * Hs, TW, TH, TN);
+        FSV_REQUIRE(rc == 0, "conv2d_fwd_tc_up2: cuTensorMapEncodeTiled(A) failed with %d", rc);
+        rc = encode_weight_map(&p.bmap, w4, 16LL * d->Cin, d->Cout, BN);
+        FSV_REQUIRE(rc == 0, "conv2d_fwd_tc_up2: cuTensorMapEncodeTiled(B) failed with %d", rc);
+        return launch_tc(p, tiles_n, bias, residual, y, (cudaStream_t)stream, "conv2d_fwd_tc_up2");
+    }
     for (int cls = 0; cls < 4; ++cls) {
         const int ph = cls >> 1, pw = cls & 1;
         TcParams p;

@@ -104,12 +104,16 @@ DGRAD_CASES = [
     (2, 31, 31, 32, 32, 4, 2, 2),
     (2, 16, 16, 128, 256, 3, 2, 1),
     (2, 16, 16, 64, 64, 1, 1, 0),
+    (2, 16, 16, 32, 64, 4, 2, 2),            # even dims, stride 2: the four parity classes run as ONE launch (4 taps per class)
+    (2, 24, 16, 64, 64, 3, 2, 1),            # ... 3x3: 1 / 2 / 2 / 4 taps per class
+    (1, 64, 64, 32, 256, 3, 2, 1),
 ]
 
 
 @pytest.mark.parametrize('case', DGRAD_CASES)
 def test_conv_tc_dgrad(case):
-    """tcgen05 data gradient (stride 1: one launch; stride 2: four parity launches with strided output) vs float64."""
+    """tcgen05 data gradient (stride 1: one launch; stride 2: the four output-parity classes, written through the strided-output
+    epilogue -- one merged launch when H and W are even, four launches otherwise) vs float64."""
     from fsv import ops, _lib
     N, H, W, Cin, Cout, k, stride, pad = case
     x = rnd(N, Cin, H, W).requires_grad_(True)
