@@ -41,12 +41,19 @@ int fsv_sm_count();
 // true the first time it is called for (flag set, current device): per-DEVICE one-time setup (cudaFuncSetAttribute is per device)
 bool fsv_first_on_device(unsigned long long* flags);
 
-__device__ __forceinline__ float fsv_act(float v, int act) {
-    if (act == FSV_ACT_LRELU) return v > 0.f ? v : v * FSV_LRELU_SLOPE;
+// The transcendental activations live in ONE out-of-line copy per translation unit: inlined at every element of an unrolled epilogue
+// (64 x tanhf in the SPADE kernel) they made 60-110 KB kernels whose warps stalled on instruction fetch (ncu: stall_no_inst was the
+// top stall of k_spade_tc); the layers that use them (output head, flow mask) pay a call per element.
+static __device__ __noinline__ float fsv_act_slow(float v, int act) {
     if (act == FSV_ACT_TANH) return tanhf(v);
     if (act == FSV_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
-    if (act == FSV_ACT_RELU) return v > 0.f ? v : 0.f;
     return v;
+}
+__device__ __forceinline__ float fsv_act(float v, int act) {
+    if (act == FSV_ACT_LRELU) return v > 0.f ? v : v * FSV_LRELU_SLOPE;
+    if (act == FSV_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == FSV_ACT_NONE) return v;
+    return fsv_act_slow(v, act);
 }
 // derivative of act expressed through the post-activation value y (before out_scale)
 __device__ __forceinline__ float fsv_act_grad(float y, int act) {

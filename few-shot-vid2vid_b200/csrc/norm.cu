@@ -45,13 +45,15 @@ __global__ void __launch_bounds__(RED_TX * RED_TY) k_chan_reduce2(F f, E e, long
     float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f, sa2 = 0.f, sb2 = 0.f, sa3 = 0.f, sb3 = 0.f;
     if (c < C) {
         const long long base = g * rows_per_group;
+        const typename F::Ctx ctx = f.begin(g, c);          // per-(group, channel) constants, loaded once per thread
         long long r = r0 + ty;
         for (; r + 3 * RED_TY < r1; r += 4 * RED_TY) {
-            float2 v0 = f(base + r, c), v1 = f(base + r + RED_TY, c), v2 = f(base + r + 2 * RED_TY, c), v3 = f(base + r + 3 * RED_TY, c);
+            float2 v0 = f(ctx, base + r, c), v1 = f(ctx, base + r + RED_TY, c), v2 = f(ctx, base + r + 2 * RED_TY, c),
+                   v3 = f(ctx, base + r + 3 * RED_TY, c);
             sa0 += v0.x; sb0 += v0.y; sa1 += v1.x; sb1 += v1.y; sa2 += v2.x; sb2 += v2.y; sa3 += v3.x; sb3 += v3.y;
         }
         for (; r < r1; r += RED_TY) {
-            float2 v = f(base + r, c);
+            float2 v = f(ctx, base + r, c);
             sa0 += v.x; sb0 += v.y;
         }
     }
@@ -133,10 +135,23 @@ struct StoreE {   // totals -> a[g*C+c], b[g*C+c]
     }
 };
 
+struct StoreParamE {   // one group: totals -> a[c], b[c] and, as floats, the affine parameter gradients (dbias = a, dweight = b)
+    double *a, *b;
+    float *dweight, *dbias;
+    __device__ void operator()(int, int c, double ta, double tb) const {
+        a[c] = ta;
+        b[c] = tb;
+        dbias[c] = (float)ta;
+        dweight[c] = (float)tb;
+    }
+};
+
 struct StatsF {
     const float* x;
     int ld, coff;
-    __device__ float2 operator()(long long row, int c) const {
+    struct Ctx {};
+    __device__ Ctx begin(int, int) const { return Ctx(); }
+    __device__ float2 operator()(const Ctx&, long long row, int c) const {
         float v = x[row * ld + coff + c];
         return make_float2(v, v * v);
     }
@@ -294,11 +309,17 @@ struct NormBwdF {   // (sum dy', sum dy'*xhat), dy' = dy*act'(y)
     const float *x, *y, *dy, *mean, *rstd, *weight, *bias;
     int C, act, instance;
     long long HW;
-    __device__ float2 operator()(long long row, int c) const {
+    struct Ctx { float mean, rstd, w, b; };
+    __device__ Ctx begin(int g, int c) const {          // instance mode: group g IS the sample
+        const int s = instance ? g * C + c : c;
+        Ctx k;
+        k.mean = mean[s]; k.rstd = rstd[s]; k.w = weight ? weight[c] : 1.f; k.b = bias ? bias[c] : 0.f;
+        return k;
+    }
+    __device__ float2 operator()(const Ctx& k, long long row, int c) const {
         long long i = row * C + c;
-        int s = instance ? (int)(row / HW) * C + c : c;
-        float xh = (x[i] - mean[s]) * rstd[s];
-        float g = dy[i] * norm_act_grad(y, i, xh, weight ? weight[c] : 1.f, bias ? bias[c] : 0.f, act);
+        float xh = (x[i] - k.mean) * k.rstd;
+        float g = dy[i] * norm_act_grad(y, i, xh, k.w, k.b, act);
         return make_float2(g, g * xh);
     }
 };
@@ -394,11 +415,17 @@ static int norm_apply_bwd_impl(const float* x, const float* y, const float* dy, 
     double* A = scratch;
     double* B = scratch + (size_t)groups * C;
     NormBwdF f{x, y, dy, mean, rstd, weight, bias, C, act, inst, (long long)HW};
-    StoreE e{A, B, C};
-    int rc = launch_reduce2(f, e, groups, rpg, C, B + (size_t)groups * C, st, "norm_bwd_reduce");
+    if (weight) FSV_REQUIRE(dweight && dbias, "norm_apply_bwd: affine needs dweight/dbias");
+    int rc;
+    if (weight && groups == 1) {          // batch mode: the reduction's last block writes the parameter gradients itself
+        StoreParamE e{A, B, dweight, dbias};
+        rc = launch_reduce2(f, e, groups, rpg, C, B + (size_t)groups * C, st, "norm_bwd_reduce");
+    } else {
+        StoreE e{A, B, C};
+        rc = launch_reduce2(f, e, groups, rpg, C, B + (size_t)groups * C, st, "norm_bwd_reduce");
+    }
     if (rc) return rc;
-    if (weight) {
-        FSV_REQUIRE(dweight && dbias, "norm_apply_bwd: affine needs dweight/dbias");
+    if (weight && groups != 1) {
         k_norm_param_grads<<<fsv_cdiv(C, 256), 256, 0, st>>>(A, B, groups, C, dweight, dbias);
         FSV_CHECK_LAUNCH("norm_param_grads");
     }
@@ -430,15 +457,25 @@ extern "C" int fsv_norm_apply_bwd2(const float* x, const float* dy, const float*
 struct SpadeNormBwdF {   // rows are full-resolution pixels
     const float *x, *g, *mean, *rstd;
     int C, H, W, up, instance;
-    __device__ float2 operator()(long long row, int c) const {
-        int w = (int)(row % W);
-        long long q = row / W;
-        int h = (int)(q % H);
-        long long n = q / H;
-        int Hs = H / up, Ws = W / up;
-        int s = instance ? (int)n * C + c : c;
-        float xv = x[((n * Hs + h / up) * Ws + w / up) * C + c];
-        float xh = (xv - mean[s]) * rstd[s];
+    struct Ctx { float mean, rstd; };
+    __device__ Ctx begin(int grp, int c) const {
+        const int s = instance ? grp * C + c : c;
+        Ctx k;
+        k.mean = mean[s]; k.rstd = rstd[s];
+        return k;
+    }
+    __device__ float2 operator()(const Ctx& k, long long row, int c) const {
+        float xv;
+        if (up == 1) xv = x[row * C + c];            // same layout as g: no index arithmetic
+        else {
+            int w = (int)(row % W);
+            long long q = row / W;
+            int h = (int)(q % H);
+            long long n = q / H;
+            int Hs = H / up, Ws = W / up;
+            xv = x[((n * Hs + h / up) * Ws + w / up) * C + c];
+        }
+        float xh = (xv - k.mean) * k.rstd;
         float gv = g[row * C + c];
         return make_float2(gv, gv * xh);
     }
