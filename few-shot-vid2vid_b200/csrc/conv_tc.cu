@@ -377,10 +377,13 @@ static int pick_bn(int cout) {
 // A re-reads stay in L2).  FSV_TC_BN_OCC=0 disables.
 static int occupancy_bn(int bn, int cout, long long m_tiles) {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("FSV_TC_BN_OCC"); on = (e && atoi(e) == 0) ? 0 : 1; }
+    if (on < 0) { const char* e = getenv("FSV_TC_BN_OCC"); on = e ? atoi(e) : 1; }
     if (!on) return bn;
     const long long sms = fsv_sm_count();
-    while (bn >= 64 && 2 * m_tiles * (cout / bn) <= sms && cout % (bn / 2) == 0 && (bn / 2) % 16 == 0) bn /= 2;   // less than half the SMs busy
+    // level 1 (default): narrow while less than half the SMs would get a CTA; level 2 (experiment): while not every SM gets one
+    // (two narrower CTAs per SM keep twice the operand bytes in flight of one wide CTA)
+    const long long f = on >= 2 ? 1 : 2;
+    while (bn >= 64 && f * m_tiles * (cout / bn) <= sms && cout % (bn / 2) == 0 && (bn / 2) % 16 == 0) bn /= 2;
     return bn;
 }
 
