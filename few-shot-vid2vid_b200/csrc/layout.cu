@@ -219,6 +219,72 @@ extern "C" int fsv_up2_weights(const float* w, float* w4, int Cout, int Cin, voi
 }
 
 
+// Backward of y = conv3x3(nearest_up2(x)) at SOURCE resolution (the autograd of generator.py:484,537 runs the 3x3 data gradient at
+// the upsampled resolution and then sums 2x2 blocks).  Source pixel i feeds the upsampled rows 2i and 2i+1, and kernel row r of
+// upsampled row u reads dy row u + 1 - r, so dx[i] gathers dy rows 2i + k - 1, k = 0..3: a 4x4 / stride-2 / pad-1 convolution of dy
+// whose tap row k sums the 3x3 rows r with k in {2 - r, 3 - r}:   k=0 <- {2}, k=1 <- {1,2}, k=2 <- {0,1}, k=3 <- {0}
+// (same for columns).  16 taps at a quarter of the pixels = 4/9 of the MACs, no full-resolution dx and no 2x2 reduction pass.
+//   data gradient  : dx = conv4x4s2(dy, wf),  wf[ci][k][l][co] = sum_{r in R(k), s in R(l)} wt[ci][r][s][co]     (fsv_up2_dgrad_weights)
+//   weight gradient: dW16[ci][k][l][co] = sum_px x[px][ci] * dy[2 px + (k,l) - 1][co]  (the 4x4 / stride-2 weight gradient with the roles
+//                    of the two tensors exchanged), dW[co][r][s][ci] = sum_{k in {2-r,3-r}, l in {2-s,3-s}} dW16[ci][k][l][co]  (fsv_up2_wgrad_fold)
+__global__ void k_up2_dgrad_weights(const float* __restrict__ wt, float* __restrict__ wf, long long cin, int cout) {
+    const long long total = cin * 16 * cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % cout);
+        const long long t = i / cout;
+        const int l = (int)(t & 3), k = (int)((t >> 2) & 3);
+        const long long ci = t >> 4;
+        const int r0 = max(0, 2 - k), r1 = min(2, 3 - k);
+        const int s0 = max(0, 2 - l), s1 = min(2, 3 - l);
+        float acc = 0.f;
+        for (int r = r0; r <= r1; ++r)
+            for (int s = s0; s <= s1; ++s) acc += wt[((ci * 3 + r) * 3 + s) * cout + co];
+        wf[i] = acc;
+    }
+}
+extern "C" int fsv_up2_dgrad_weights(const float* wt, float* wf, int Cin, int Cout, void* stream) {
+    FSV_REQUIRE(wt && wf && Cout > 0 && Cin > 0, "up2_dgrad_weights: bad args");
+    k_up2_dgrad_weights<<<stream_grid((long long)Cin * 16 * Cout, 256), 256, 0, (cudaStream_t)stream>>>(wt, wf, Cin, Cout);
+    FSV_CHECK_LAUNCH("up2_dgrad_weights");
+    return FSV_OK;
+}
+
+// grid (co tiles, ci tiles, 9 taps); 32x32 tiles through shared memory so that both the (.., co) reads and the (.., ci) writes are coalesced
+__global__ void __launch_bounds__(256) k_up2_wgrad_fold(const float* __restrict__ dw16, float* __restrict__ dw, int cout, int cin, int accumulate) {
+    __shared__ float tile[32][33];
+    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+    const int r = blockIdx.z / 3, s = blockIdx.z - 3 * r;
+    for (int i = threadIdx.y; i < 32; i += 8) {         // i = ci within the tile, threadIdx.x = co
+        const int ci = ci0 + i, co = co0 + threadIdx.x;
+        float acc = 0.f;
+        if (ci < cin && co < cout) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+                    acc += dw16[(((long long)ci * 4 + (2 - r + a)) * 4 + (2 - s + b)) * cout + co];
+        }
+        tile[i][threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {         // i = co within the tile, threadIdx.x = ci
+        const int co = co0 + i, ci = ci0 + threadIdx.x;
+        if (ci < cin && co < cout) {
+            float* o = dw + (((long long)co * 3 + r) * 3 + s) * cin + ci;
+            *o = accumulate ? *o + tile[threadIdx.x][i] : tile[threadIdx.x][i];
+        }
+    }
+}
+extern "C" int fsv_up2_wgrad_fold(const float* dw16, float* dw, int Cout, int Cin, int accumulate, void* stream) {
+    FSV_REQUIRE(dw16 && dw && Cout > 0 && Cin > 0, "up2_wgrad_fold: bad args");
+    dim3 grid(fsv_cdiv(Cout, 32), fsv_cdiv(Cin, 32), 9);
+    FSV_REQUIRE(grid.y <= 65535, "up2_wgrad_fold: grid too large");
+    k_up2_wgrad_fold<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dw16, dw, Cout, Cin, accumulate);
+    FSV_CHECK_LAUNCH("up2_wgrad_fold");
+    return FSV_OK;
+}
+
+
 // MaxPool2d(kernel 2, stride 2) on NHWC (VGG19 feature stack of the perceptual loss, vgg.py:45-59).  One thread per output element.
 __global__ void k_maxpool2_fwd(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C) {
     const int Ho = H / 2, Wo = W / 2;

@@ -71,6 +71,8 @@ SIGNATURES = {
     'fsv_conv2d_fwd_tc_up2_eligible': [_CD],
     'fsv_up2_weights': [c_vp, c_vp, c_int, c_int, c_vp],
     'fsv_conv2d_fwd_tc_up2': [_CD, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'fsv_up2_dgrad_weights': [c_vp, c_vp, c_int, c_int, c_vp],
+    'fsv_up2_wgrad_fold': [c_vp, c_vp, c_int, c_int, c_int, c_vp],
     'fsv_conv2d_dgrad_tc_eligible': [_CD],
     'fsv_conv2d_dgrad_tc': [_CD, c_vp, c_vp, c_vp, c_vp],
     'fsv_conv2d_wgrad_tc_eligible': [_CD],

@@ -27,6 +27,8 @@ LAUNCHES = [0]
 # runs when the backward pass ends (before any optimizer can read .grad).  Everything is capturable into a CUDA graph (the side
 # stream becomes a parallel branch of the graph).  FSV_WGRAD_SIDE=0 keeps everything on one stream.
 WGRAD_SIDE_STREAM = os.environ.get('FSV_WGRAD_SIDE', '1') != '0'
+# backward of the upsample-collapsed convolutions at source resolution (4/9 of the MACs, no full-resolution dx); 0: 3x3 at the upsampled one
+UP2_BWD_SOURCE = os.environ.get('FSV_UP2_BWD', '0') != '0'      # off until measured on the B200
 _SIDE, _SIDE_DIRTY = {}, {}
 
 
@@ -439,7 +441,22 @@ class Conv2dFn(torch.autograd.Function):
         else:
             g = dy
         dx = dw = db = dres = None
-        if ctx.needs_input_grad[0]:
+        # backward of conv3x3(up2(x)) at source resolution: 4x4 / stride-2 convolutions of g (see csrc/layout.cu)
+        up2_src = (UP2_BWD_SOURCE and d.up == 2 and d.use_tc != 0 and cfg.get('w_off', 0) == 0 and d.w_nstride == 0
+                   and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.pad == 1 and d.in_act == ACT_NONE)
+        dx_done = False
+        if ctx.needs_input_grad[0] and up2_src:
+            df = _conv_desc(d.N, d.H, d.W, d.Cout, d.Cin, 4, 4, 2, 1, use_tc=d.use_tc)
+            if lib.fsv_conv2d_tc_eligible(ctypes.byref(df)):
+                wt = cfg.get('wt')
+                if wt is None or wt.numel() != wbase.numel():
+                    wt = wbase.reshape(d.Cout, 3, 3, d.Cin).permute(3, 1, 2, 0).contiguous()
+                wf = torch.empty((d.Cin, 16, d.Cout), device=dy.device, dtype=torch.float32)
+                _call(lib.fsv_up2_dgrad_weights, ptr(wt), ptr(wf), d.Cin, d.Cout, st)
+                dx = torch.empty_like(x)
+                _call(lib.fsv_conv2d_fwd, ctypes.byref(df), ptr(g), ptr(wf), None, None, ptr(dx), st)
+                dx_done = True
+        if ctx.needs_input_grad[0] and not dx_done:
             dfull = torch.empty((d.N, d.H, d.W, d.Cin), device=dy.device, dtype=torch.float32)
             done = False
             if d.use_tc != 0 and cfg.get('w_off', 0) == 0:
@@ -476,7 +493,16 @@ class Conv2dFn(torch.autograd.Function):
                 if need_b:
                     db = dw if ctx.same_base else torch.zeros(ctx.bshape, device=dy.device, dtype=torch.float32)
                 w_done = False
-                if need_w and shared and d.use_tc != 0 and lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(d)):
+                if need_w and shared and up2_src:
+                    # g in the role of x, x in the role of dy: dw16 (Cin, 4, 4, Cout), folded into dw (Cout, 3, 3, Cin)
+                    dg = _conv_desc(d.N, d.H, d.W, d.Cout, d.Cin, 4, 4, 2, 1, use_tc=d.use_tc)
+                    if lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(dg)):
+                        dw16 = torch.empty((d.Cin, 16, d.Cout), device=dy.device, dtype=torch.float32)
+                        ws = torch.empty(int(lib.fsv_conv2d_wgrad_tc_workspace(ctypes.byref(dg))) // 4 + 1, device=dy.device, dtype=torch.float32)
+                        _call(lib.fsv_conv2d_wgrad_tc, ctypes.byref(dg), ptr(g), ptr(x), ptr(dw16), ptr(ws), 0, sw)
+                        _call(lib.fsv_up2_wgrad_fold, ptr(dw16), ptr(dw), d.Cout, d.Cin, 0, sw)
+                        w_done = True
+                if not w_done and need_w and shared and d.use_tc != 0 and lib.fsv_conv2d_wgrad_tc_eligible(ctypes.byref(d)):
                     ws = torch.empty(int(lib.fsv_conv2d_wgrad_tc_workspace(ctypes.byref(d))) // 4 + 1, device=dy.device, dtype=torch.float32)
                     _call(lib.fsv_conv2d_wgrad_tc, ctypes.byref(d), ptr(x), ptr(g), ptr(dw), ptr(ws), 0, sw)
                     w_done = True

@@ -113,6 +113,13 @@ int fsv_conv2d_fwd_tc_up2_eligible(const fsv_conv_desc* d);
 int fsv_up2_weights(const float* w, float* w4, int Cout, int Cin, void* stream);
 int fsv_conv2d_fwd_tc_up2(const fsv_conv_desc* d, const float* x, const float* w4, const float* bias,
                           const float* residual, float* y, void* stream);
+/* Backward of y = conv3x3(nearest_up2(x)) at source resolution (autograd of generator.py:484,537; csrc/layout.cu).
+ * Data gradient: dx = conv 4x4 / stride 2 / pad 1 of dy (fsv_conv2d_fwd with that descriptor) with the folded weights
+ * wf (Cin, 4, 4, Cout) built here from wt (Cin, 3, 3, Cout), the weight with its channel axes swapped.
+ * Weight gradient: fsv_conv2d_wgrad_tc of that 4x4 / stride-2 descriptor with dy in the role of x and x in the role of dy
+ * gives dw16 (Cin, 4, 4, Cout); fsv_up2_wgrad_fold sums it into dw (Cout, 3, 3, Cin) (+= if accumulate). */
+int fsv_up2_dgrad_weights(const float* wt, float* wf, int Cin, int Cout, void* stream);
+int fsv_up2_wgrad_fold(const float* dw16, float* dw, int Cout, int Cin, int accumulate, void* stream);
 /* Data gradient on the tcgen05/TMA kernel.  wt is the weight with its channel axes swapped: wt[ci][r][s][co]
  * (Cin, kh, kw, Cout).  Stride 1: one launch; stride 2: one launch per output parity class with a strided-output
  * epilogue.  dx is fully overwritten.  FSV_ENOTSUP when fsv_conv2d_dgrad_tc_eligible() is 0. */

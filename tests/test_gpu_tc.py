@@ -268,6 +268,71 @@ def test_conv_tc_up2_forward_and_grads(N, Hs, Ws, Cin, Cout, act, has_r):
         assert grad_err(bg.grad, b.grad) < 1e-4
 
 
+@pytest.mark.parametrize('N,Hs,Ws,Cin,Cout', [(2, 16, 16, 64, 64), (2, 16, 32, 128, 32), (1, 32, 16, 32, 96), (2, 24, 20, 256, 64)])
+def test_conv_tc_up2_backward_at_source_resolution(N, Hs, Ws, Cin, Cout):
+    """Backward of conv3x3(nearest_up2(x)) as 4x4 / stride-2 convolutions at source resolution (folded weights, folded weight gradient:
+    fsv_up2_dgrad_weights / fsv_up2_wgrad_fold around the tcgen05 forward and weight-gradient kernels) vs float64 autograd of
+    Upsample -> Conv2d, and vs the same layer differentiated at the upsampled resolution (FSV_UP2_BWD=0)."""
+    from fsv import ops, _lib
+    x = rnd(N, Cin, Hs, Ws).requires_grad_(True)
+    w = rnd(Cout, Cin, 3, 3, scale=0.1).requires_grad_(True)
+    y = F.conv2d(O.up2(x), w, None, padding=1)
+    go = rnd(*y.shape)
+    (y * go).sum().backward()
+    dsrc = ops._conv_desc(N, 2 * Hs, 2 * Ws, Cout, Cin, 4, 4, 2, 1)
+    assert _lib.lib.fsv_conv2d_tc_eligible(dsrc) == 1 and _lib.lib.fsv_conv2d_wgrad_tc_eligible(dsrc) == 1
+    grads = {}
+    old = ops.UP2_BWD_SOURCE
+    try:
+        for mode in (True, False):
+            ops.UP2_BWD_SOURCE = mode
+            xg = to_nhwc(x.detach().float().cuda()).requires_grad_(True)
+            wg = w.detach().float().cuda().requires_grad_(True)
+            yg = ops.conv2d(xg, wg.permute(0, 2, 3, 1).contiguous(), None, pad=1, up=2, use_tc=-1)
+            n0 = ops.LAUNCHES[0]
+            (yg * to_nhwc(go.float().cuda())).sum().backward()
+            torch.cuda.synchronize()
+            grads[mode] = (xg.grad.permute(0, 3, 1, 2).clone(), wg.grad.clone(), ops.LAUNCHES[0] - n0)
+    finally:
+        ops.UP2_BWD_SOURCE = old
+    # source-resolution form: weight fold + conv, weight gradient + fold (+ the OHWI permute's own kernels are torch-side): 4 C-ABI calls
+    assert grads[True][2] == 4 and grads[False][2] >= 3
+    for mode in (True, False):
+        assert grad_err(grads[mode][0], x.grad) < TOL_TF32, mode
+        assert grad_err(grads[mode][1], w.grad) < TOL_TF32, mode
+
+
+@pytest.mark.parametrize('Cin,Cout', [(32, 32), (96, 40), (7, 5)])
+def test_up2_backward_weight_folds(Cin, Cout):
+    """fsv_up2_dgrad_weights / fsv_up2_wgrad_fold alone (exact fp32 sums) vs their index formulas."""
+    from fsv import ops, _lib
+    from fsv._lib import lib, ptr, stream
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    wt = torch.randn(Cin, 3, 3, Cout, generator=g)
+    ref = torch.zeros(Cin, 4, 4, Cout)
+    for k in range(4):
+        for l in range(4):
+            for r in range(max(0, 2 - k), min(2, 3 - k) + 1):
+                for s in range(max(0, 2 - l), min(2, 3 - l) + 1):
+                    ref[:, k, l, :] += wt[:, r, s, :]
+    wtg = wt.cuda()
+    wf = torch.empty(Cin, 4, 4, Cout, device='cuda')
+    ops._call(lib.fsv_up2_dgrad_weights, ptr(wtg), ptr(wf), Cin, Cout, stream())
+    assert (wf.cpu() - ref).abs().max() < 1e-5
+    dw16 = torch.randn(Cin, 4, 4, Cout, generator=g)
+    fold = torch.zeros(Cout, 3, 3, Cin)
+    for r in range(3):
+        for s in range(3):
+            for a in range(2):
+                for b in range(2):
+                    fold[:, r, s, :] += dw16[:, 2 - r + a, 2 - s + b, :].t()
+    base = torch.randn(Cout, 3, 3, Cin, generator=g)
+    for acc in (0, 1):
+        dw = base.clone().cuda()
+        ops._call(lib.fsv_up2_wgrad_fold, ptr(dw16.cuda()), ptr(dw), Cout, Cin, acc, stream())
+        assert (dw.cpu() - (fold + base * acc)).abs().max() < 1e-5
+
+
 @pytest.mark.parametrize('b,h,w,cin,cout', [(2, 32, 32, 64, 128), (1, 16, 32, 128, 96), (2, 8, 8, 32, 64)])
 def test_per_sample_matmul_tensor_core_path(b, h, w, cin, cout):
     """ops.per_sample_matmul (the K-shot attention GEMMs: per-sample 1x1 conv without bias) on the tcgen05 path -- forward through
