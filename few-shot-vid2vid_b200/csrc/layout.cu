@@ -3,6 +3,7 @@
 // All are pure streaming kernels (HBM-bound, no reuse): coalesced along the contiguous
 // dimension, grid-stride loops sized to a multiple of the SM count.
 #include "common.cuh"
+#include <stdlib.h>
 
 static inline int stream_grid(long long work_items, int threads) {
     long long blocks = (work_items + threads - 1) / threads;
@@ -36,10 +37,40 @@ __global__ void k_nhwc_to_nchw(const float* __restrict__ src, float* __restrict_
         }
     }
 }
+// Tiled form: a block moves 32 pixels x up to 32 channels through shared memory, so that the plane reads (32 consecutive pixels of one
+// channel) AND the pixel-major writes (the channels of one pixel, consecutive pixels back to back when the destination is dense) are both
+// contiguous.  The one-thread-per-pixel kernel above scatters every store instruction of a warp over 32 destination rows (round-2 timeline:
+// 0.46 ms for the discriminator's 20-channel 4 x 512 x 512 input, 0.37 TB/s).  grid (pixel tiles, N).
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc_tiled(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int ld, int coff) {
+    __shared__ float tile[32][33];                 // [channel][pixel]
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int p0 = blockIdx.x * 32;
+    const int np = min(32, HW - p0);
+    const float* s = src + (long long)blockIdx.y * C * HW + p0;
+    float* d = dst + ((long long)blockIdx.y * HW + p0) * ld + coff;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int nc = min(32, C - c0);
+        for (int c = ty; c < nc; c += 8)
+            if (tx < np) tile[c][tx] = s[(long long)(c0 + c) * HW + tx];
+        __syncthreads();
+        for (int i = tid; i < np * nc; i += 256) {
+            const int p = i / nc, c = i - p * nc;
+            d[(long long)p * ld + c0 + c] = tile[c][p];
+        }
+        __syncthreads();
+    }
+}
 extern "C" int fsv_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_ld, int dst_coff, void* stream) {
     FSV_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && dst_ld >= dst_coff + C, "nchw_to_nhwc: bad dims");
     long long HW = (long long)H * W;
-    k_nchw_to_nhwc<<<stream_grid(N * HW, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, N, C, HW, dst_ld, dst_coff);
+    static int tiled = -1;                          // FSV_PACK_TILED=0: the one-thread-per-pixel kernel
+    if (tiled < 0) { const char* e = getenv("FSV_PACK_TILED"); tiled = (e && atoi(e) == 0) ? 0 : 1; }
+    if (tiled && N <= 65535 && HW < (1LL << 31) - 32 && HW >= 1024) {
+        dim3 grid((unsigned)((HW + 31) / 32), N);
+        k_nchw_to_nhwc_tiled<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, C, (int)HW, dst_ld, dst_coff);
+    } else {
+        k_nchw_to_nhwc<<<stream_grid(N * HW, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, N, C, HW, dst_ld, dst_coff);
+    }
     FSV_CHECK_LAUNCH("nchw_to_nhwc");
     return FSV_OK;
 }

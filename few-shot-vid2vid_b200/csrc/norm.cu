@@ -9,6 +9,7 @@
 // Per-channel reductions walk NHWC rows with one warp per 32 consecutive channels
 // (128-byte coalesced rows), fp32 partials per thread, fp64 combine.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define RED_TX 32
 #define RED_TY 8
@@ -480,6 +481,30 @@ struct SpadeNormBwdF {   // rows are full-resolution pixels
         return make_float2(gv, gv * xh);
     }
 };
+// x2-upsampled input: the same two sums taken over the SOURCE pixels -- sum_hi g = sum_lo G, sum_hi g*xhat = sum_lo G*xhat with G = the
+// 2x2 block sum of g (xhat is constant over the block).  One pixel decode (32-bit) and one x load per four g loads; the per-element
+// form above spent most of its time in 64-bit divisions (round-2 timeline: 0.42 - 0.46 ms per 512x512x64 call, 11x the HBM time).
+struct SpadeNormBwdUp2F {   // rows are source-resolution pixels
+    const float *x, *g, *mean, *rstd;
+    int C, Hs, Ws, instance;
+    struct Ctx { float mean, rstd; };
+    __device__ Ctx begin(int grp, int c) const {
+        const int s = instance ? grp * C + c : c;
+        Ctx k;
+        k.mean = mean[s]; k.rstd = rstd[s];
+        return k;
+    }
+    __device__ float2 operator()(const Ctx& k, long long row, int c) const {
+        const unsigned r = (unsigned)row;
+        const unsigned ws = r % (unsigned)Ws, q = r / (unsigned)Ws;
+        const unsigned hs = q % (unsigned)Hs, n = q / (unsigned)Hs;
+        const long long wc = (long long)Ws * 2 * C;                                   // one upsampled image row
+        const float* gp = g + ((long long)(n * (unsigned)Hs + hs) * 2) * wc + (long long)ws * 2 * C + c;
+        const float gs = (gp[0] + gp[C]) + (gp[wc] + gp[wc + C]);
+        const float xh = (x[row * C + c] - k.mean) * k.rstd;
+        return make_float2(gs, gs * xh);
+    }
+};
 __global__ void k_spade_norm_bwd(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean,
                                  const float* __restrict__ rstd, const double* __restrict__ A, const double* __restrict__ B,
                                  float* __restrict__ dx, int N, int Hs, int Ws, int C, int up, int instance, int batch_stats, float inv_cnt) {
@@ -553,9 +578,17 @@ extern "C" int fsv_spade_norm_bwd(const float* x, const float* dxhat, const floa
     double* A = scratch;
     double* B = scratch + (size_t)groups * C;
     if (batch_stats) {
-        SpadeNormBwdF f{x, dxhat, mean, rstd, C, H, W, up, inst};
         StoreE e{A, B, C};
-        int rc = launch_reduce2(f, e, groups, rpg, C, B + (size_t)groups * C, st, "spade_norm_bwd_reduce");
+        int rc;
+        static int src_form = -1;       // FSV_SPADE_NORM_SRC=0: the per-upsampled-pixel form for up = 2 as well
+        if (src_form < 0) { const char* ev = getenv("FSV_SPADE_NORM_SRC"); src_form = (ev && atoi(ev) == 0) ? 0 : 1; }
+        if (up == 2 && src_form && (long long)N * H * W < (1LL << 31)) {
+            SpadeNormBwdUp2F f{x, dxhat, mean, rstd, C, H / 2, W / 2, inst};
+            rc = launch_reduce2(f, e, groups, rpg / 4, C, B + (size_t)groups * C, st, "spade_norm_bwd_reduce");
+        } else {
+            SpadeNormBwdF f{x, dxhat, mean, rstd, C, H, W, up, inst};
+            rc = launch_reduce2(f, e, groups, rpg, C, B + (size_t)groups * C, st, "spade_norm_bwd_reduce");
+        }
         if (rc) return rc;
     }
     long long total = (long long)N * (H / up) * (W / up) * C;

@@ -15,6 +15,7 @@
 //                    HBM speed); blocks own 16x8-pixel tiles so the 3x3 / 4x4 halo re-reads hit L1
 // Roofline: HBM; algorithmic bytes = 4*(|x| + |y|) (+ weights, negligible).
 #include "common.cuh"
+#include <stdlib.h>
 
 struct ThinP {
     int N, H, W, Cin, x_ld, x_coff, Cout, kh, kw, stride, pad, Ho, Wo, y_ld, y_coff, act, in_act;
@@ -608,13 +609,23 @@ __global__ void __launch_bounds__(128) k_thin_cin_dgrad(ThinP p, const float* __
 
 // ------------------------------------------------------------------ host side
 static bool thin_common_ok(const fsv_conv_desc* d) {
-    return d->up == 1 && d->w_nstride == 0 && d->b_nstride == 0 && d->kh * d->kw <= 16 && (long long)d->N * d->Ho * d->Wo >= 4096;
+    return d->up == 1 && d->w_nstride == 0 && d->b_nstride == 0 && d->kh * d->kw <= 16;
+}
+// Thin-output layers with few pixels but many input channels (the face discriminator's 512 -> 1 head on 10x10: 484 outputs of 8192
+// MACs each) are far worse off on the generic 64x64 SIMT tile than the large ones: 8 CTAs walk the whole reduction serially (0.5 - 0.75 ms
+// per call in the round-2 timeline).  FSV_THIN_OUT_MIN_PX lowers the pixel threshold of the thin-output kernels for them.
+static long long thin_out_min_px() {
+    static long long v = -1;
+    if (v < 0) { const char* e = getenv("FSV_THIN_OUT_MIN_PX"); v = e ? atoll(e) : 4096; if (v < 1) v = 1; }
+    return v;
 }
 extern "C" int fsv_conv2d_thin_kind(const fsv_conv_desc* d) {
     if (!d || !thin_common_ok(d)) return 0;
-    if (d->Cin <= 8 && d->Cout >= 16) return 1;                                         // thin input
+    const long long px = (long long)d->N * d->Ho * d->Wo;
+    if (d->Cin <= 8 && d->Cout >= 16 && px >= 4096) return 1;                                         // thin input
     if (d->Cout <= 4 && d->Cin >= 16 && d->Cin % 4 == 0 && d->x_ld % 4 == 0 && d->x_coff % 4 == 0 && d->N <= 65535 &&
-        (long long)d->Cout * d->kh * d->kw * d->Cin * 4 <= 40 * 1024) return 2;         // thin output
+        (long long)d->Cout * d->kh * d->kw * d->Cin * 4 <= 40 * 1024 &&
+        (px >= 4096 || (px >= thin_out_min_px() && d->Cin >= 64))) return 2;         // thin output
     return 0;
 }
 // tile: 16x8 pixels, shrunk (16x4, 8x4) while the grid would not fill the GPU twice over; always a multiple of the

@@ -15,6 +15,8 @@ Execution structure of a forward (all capturable into one CUDA graph): one group
 (layers.SpectralPlanner); the reference-encoder / hyper-network / label-embedding branch on a second stream concurrent with
 the flow / warp / image-embedding branch (ops.branch_fork / branch_join); then the SPADE main branch.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -330,6 +332,43 @@ class FewShotGenerator(BaseNetwork):
         atn_vis = attention.reshape(b, h * w, n, h * w).sum(3).permute(0, 2, 1).reshape(b, n, h, w)
         return out, attention, atn_vis[-1:, 0:1]
 
+    def attention_rows_per_chunk(self, b, h, w, n):
+        """Query rows per chunk of the memory-bounded attention, or None for the one-piece form.  The (b, h*w, n*h*w) attention matrix is
+        what runs the reference out of memory in the inference sweep (1024x1024 with K = 5: 86 GB); without autograd nothing needs it
+        whole, so it is formed a few query rows at a time.  Budget: ``attention_chunk_bytes`` (FSV_ATTN_CHUNK_MB, default 1024 MB)."""
+        if torch.is_grad_enabled():
+            return None
+        budget = getattr(self, 'attention_chunk_bytes', None)
+        if budget is None:
+            budget = int(os.environ.get('FSV_ATTN_CHUNK_MB', '1024')) << 20
+        if 4 * b * h * w * n * h * w <= budget:
+            return None
+        return max(1, min(h, budget // (4 * b * w * n * h * w)))
+
+    def attention_chunked(self, x, xl, label, label_ref, rows):
+        """generator.py:298-316,359-366 without the whole attention matrix (no-grad paths): per chunk of query rows the energies, their
+        softmax over the n*h*w reference positions, both merges (image and label features) and the running per-reference attention mass
+        the visualisation and the choice of the warped reference need.  Same kernels, same values as attention_module."""
+        bn, h, w, c = x.shape
+        n = self.n_shot
+        b = bn // n
+        key = self.attention_encode(label_ref, 'atn_key').reshape(b, n * h * w * c)
+        query = self.attention_encode(label, 'atn_query')
+        xt = x.reshape(b, n * h * w, c).transpose(1, 2).contiguous().reshape(b, c * n * h * w)
+        cl = xl.shape[3]
+        xlt = xl.reshape(b, n * h * w, cl).transpose(1, 2).contiguous().reshape(b, cl * n * h * w)
+        out_x = torch.empty((b, h, w, c), device=x.device, dtype=x.dtype)
+        out_l = torch.empty((b, h, w, cl), device=x.device, dtype=x.dtype)
+        vis = torch.empty((b, n, h, w), device=x.device, dtype=x.dtype)
+        for r0 in range(0, h, rows):
+            r1 = min(h, r0 + rows)
+            atn = ops.softmax_channels(ops.per_sample_matmul(query[:, r0:r1].contiguous(), key, n * h * w, c))   # (b, rows, w, n*h*w)
+            out_x[:, r0:r1] = ops.per_sample_matmul(atn, xt, c, n * h * w)
+            out_l[:, r0:r1] = ops.per_sample_matmul(atn, xlt, cl, n * h * w)
+            vis[:, :, r0:r1] = atn.reshape(b, (r1 - r0) * w, n, h * w).sum(3).permute(0, 2, 1).reshape(b, n, r1 - r0, w)
+        ref_idx = torch.argmax(vis.sum((2, 3)), dim=1)
+        return out_x, out_l, vis[-1:, 0:1], ref_idx
+
     def reference_encoding(self, img_ref, label_ref, need_weights, label=None, n=1):
         nd = self.n_downsample_G
         x = self.ref_img_first(img_ref)
@@ -338,7 +377,10 @@ class FewShotGenerator(BaseNetwork):
         for i in range(nd):
             x = getattr(self, 'ref_img_down_%d' % i)(x)
             xl = getattr(self, 'ref_label_down_%d' % i)(xl)
-            if n > 1 and i == self.n_downsample_A - 1:                               # generator.py:359-366
+            rows = self.attention_rows_per_chunk(x.shape[0] // n, x.shape[1], x.shape[2], n) if (n > 1 and i == self.n_downsample_A - 1) else None
+            if rows is not None:
+                x, xl, atn_vis, ref_idx = self.attention_chunked(x, xl, label, label_ref, rows)
+            elif n > 1 and i == self.n_downsample_A - 1:                             # generator.py:359-366
                 x, atn, atn_vis = self.attention_module(x, label, label_ref)
                 xl, _, _ = self.attention_module(xl, None, None, atn)
                 b, h, w = atn.shape[0], atn.shape[1], atn.shape[2]

@@ -28,19 +28,46 @@ LAUNCHES = [0]
 # stream becomes a parallel branch of the graph).  FSV_WGRAD_SIDE=0 keeps everything on one stream.
 WGRAD_SIDE_STREAM = os.environ.get('FSV_WGRAD_SIDE', '1') != '0'
 # backward of the upsample-collapsed convolutions at source resolution (4/9 of the MACs, no full-resolution dx); 0: 3x3 at the upsampled one
-UP2_BWD_SOURCE = os.environ.get('FSV_UP2_BWD', '0') != '0'      # off until measured on the B200
-_SIDE, _SIDE_DIRTY = {}, {}
+UP2_BWD_SOURCE = os.environ.get('FSV_UP2_BWD', '1') != '0'
+# FSV_SIDE_LANES > 1: weight gradients are dealt round-robin onto that many side streams.  The side stream is a FIFO of ~12 ms of
+# mostly small-grid kernels per iteration (a 512 -> 512 linear's weight gradient is 64 CTAs, a 64 -> 64 one a single CTA), and what is
+# still queued when the data-gradient chain ends drains serially (round-2 timeline: a 2.6 ms tail of one-at-a-time launches).  Lane 0
+# is the gathering lane: the grouped spectral backward and the gradient buckets run there after waiting for the lanes used so far.
+SIDE_LANES = max(1, int(os.environ.get('FSV_SIDE_LANES', '1')))
+_SIDE, _SIDE_DIRTY = {}, {}           # lane 0 per device; streams that forked work since the last join
+_SIDE_EXTRA, _SIDE_USED, _SIDE_RR = {}, {}, {}
 
 
-def side_fork(*tensors):
-    """-> the side stream, made to wait for everything enqueued on the current stream so far; ``tensors`` (allocated on the
-    current stream, about to be read on the side stream) are registered with the allocator so their memory is not reused early."""
-    dev = torch.cuda.current_device()
+def _side_lanes(dev):
     side = _SIDE.get(dev)
     if side is None:
         side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    extra = _SIDE_EXTRA.get(dev)
+    if extra is None or len(extra) != SIDE_LANES - 1:
+        extra = _SIDE_EXTRA[dev] = [torch.cuda.Stream(device=dev) for _ in range(SIDE_LANES - 1)]
+    return [side] + extra
+
+
+def side_fork(*tensors, gather=False):
+    """-> a side stream, made to wait for everything enqueued on the current stream so far; ``tensors`` (allocated on the
+    current stream, about to be read on the side stream) are registered with the allocator so their memory is not reused early.
+    ``gather``: lane 0, which additionally waits for every other lane used since the last join (consumers of side-stream results)."""
+    dev = torch.cuda.current_device()
+    lanes = _side_lanes(dev)
+    used = _SIDE_USED.setdefault(dev, set())
+    if gather or len(lanes) == 1:
+        li = 0
+    else:
+        li = _SIDE_RR.get(dev, 0) % len(lanes)
+        _SIDE_RR[dev] = li + 1
+    side = lanes[li]
     cur = torch.cuda.current_stream()
     side.wait_stream(cur)
+    if gather:
+        for j in sorted(used):
+            if j != 0:
+                side.wait_stream(lanes[j])
+    used.add(li)
     for t in tensors:
         if t is not None:
             t.record_stream(side)
@@ -52,8 +79,20 @@ def side_fork(*tensors):
     return side
 
 
+def side_gather_stream():
+    """Lane 0 after waiting for the current stream and for the other lanes in use (fsv.parallel: gradient buckets); the caller joins."""
+    dev = torch.cuda.current_device()
+    lanes = _side_lanes(dev)
+    used = _SIDE_USED.setdefault(dev, set())
+    lanes[0].wait_stream(torch.cuda.current_stream())
+    for j in sorted(used):
+        if j != 0:
+            lanes[0].wait_stream(lanes[j])
+    return lanes[0]
+
+
 def side_join():
-    """Every stream that forked weight-gradient work since the last join -- and the current stream -- waits for the side stream.
+    """Every stream that forked weight-gradient work since the last join -- and the current stream -- waits for the side streams.
     (Making the forking streams wait, not just whatever stream happens to be current in the engine callback, keeps the join correct
     when a backward pass is driven from a non-default auxiliary stream, e.g. the discriminator update of trainer.train_iteration.)"""
     if not _SIDE:
@@ -61,18 +100,26 @@ def side_join():
     dev = torch.cuda.current_device()
     owners = _SIDE_DIRTY.get(dev)
     if owners:
-        side = _SIDE[dev]
+        lanes = _side_lanes(dev)
+        used = sorted(_SIDE_USED.get(dev) or {0})
         cur = torch.cuda.current_stream()
         for o in owners:
-            o.wait_stream(side)
+            for j in used:
+                o.wait_stream(lanes[j])
         if all(o.cuda_stream != cur.cuda_stream for o in owners):
-            cur.wait_stream(side)
+            for j in used:
+                cur.wait_stream(lanes[j])
         _SIDE_DIRTY[dev] = []
+        _SIDE_USED[dev] = set()
+        _SIDE_RR[dev] = 0
 
 
 def on_side_stream():
     dev = torch.cuda.current_device()
-    return dev in _SIDE and torch.cuda.current_stream() == _SIDE[dev]
+    if dev not in _SIDE:
+        return False
+    cur = torch.cuda.current_stream()
+    return cur == _SIDE[dev] or any(cur == s for s in _SIDE_EXTRA.get(dev, ()))
 
 
 def _c(t):
@@ -557,7 +604,7 @@ class OhwiFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dw):
-        side = side_fork(dw) if (WGRAD_SIDE_STREAM and dw.is_cuda and not on_side_stream()) else None
+        side = side_fork(dw, gather=True) if (WGRAD_SIDE_STREAM and dw.is_cuda and not on_side_stream()) else None
         with torch.cuda.stream(side) if side is not None else _NullCtx():
             return dw.permute(0, 3, 1, 2).contiguous()
 
@@ -622,7 +669,7 @@ class SpectralWeightFn(torch.autograd.Function):
     def backward(ctx, dout, *unused):
         out, uvs = ctx.saved_tensors
         R, cin, taps, shape = ctx.dims
-        side = side_fork(out, uvs, dout) if (WGRAD_SIDE_STREAM and not on_side_stream()) else None   # dout usually comes from a side-stream wgrad
+        side = side_fork(out, uvs, dout, gather=True) if (WGRAD_SIDE_STREAM and not on_side_stream()) else None   # dout usually comes from a side-stream wgrad
         with torch.cuda.stream(side) if side is not None else _NullCtx():
             dout = _c(dout)
             dw = torch.empty(shape, device=dout.device, dtype=torch.float32)
@@ -720,7 +767,7 @@ class GroupSpectralFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         group, out = ctx.group, ctx.arena
-        side = side_fork(out, *grads) if (WGRAD_SIDE_STREAM and not on_side_stream()) else None
+        side = side_fork(out, *grads, gather=True) if (WGRAD_SIDE_STREAM and not on_side_stream()) else None
         with torch.cuda.stream(side) if side is not None else _NullCtx():
             st = stream()
             gs = [None if g is None else _c(g) for g in grads[:group.n]]

@@ -146,11 +146,7 @@ class GradSync:
             return None, None
         from . import ops
         cur = torch.cuda.current_stream()
-        dev = torch.cuda.current_device()
-        side = ops._SIDE.get(dev)
-        if side is None:
-            side = ops._SIDE[dev] = torch.cuda.Stream(device=dev)
-        side.wait_stream(cur)            # gradients produced on the compute stream so far (the side-stream ones are ordered anyway)
+        side = ops.side_gather_stream()  # waits for the compute stream and for the weight-gradient lanes in use
         return side, cur
 
     def _fire_stream(self, bi):

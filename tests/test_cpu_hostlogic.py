@@ -158,6 +158,28 @@ def test_generator_two_reference_images(nets):
             assert grad_err(params[k[5:]].grad, T(z[k])) < GTOL, k
 
 
+def test_generator_two_reference_images_chunked_attention(nets):
+    """No-grad K = 2 forward with the attention matrix formed a few query rows at a time (FewShotGenerator.attention_chunked: the
+    memory-bounded form the inference sweep needs at 1024x1024 / K = 5) against the one-piece form: frame, flow, warp, the attention
+    visualisation and the picked reference."""
+    z = load_npz('g_kshot_tiny.npz')
+    sd = state_from(z, 'sd.')
+    G = _build(nets, opt_from(z), sd)
+    label, lref, iref = T(z['label']), T(z['lref']), T(z['iref'])
+    outs = []
+    with torch.no_grad():
+        for budget in (1 << 40, 1):          # one piece; one query row per chunk
+            G.load_state_dict(sd)                # same statistics / power-iteration state for both runs
+            G.attention_chunk_bytes = budget
+            nd = G.n_downsample_A
+            rows = G.attention_rows_per_chunk(label.shape[0], label.shape[2] >> nd, label.shape[3] >> nd, G.n_shot)
+            assert (rows is None) == (budget > 1) and (budget > 1 or rows == 1)
+            outs.append(G(label, lref, iref))
+    a, b = outs
+    assert rel_err(b[0], a[0]) < 1e-5 and rel_err(b[1][0], a[1][0]) < 1e-5 and rel_err(b[4][0], a[4][0]) < 1e-5
+    assert rel_err(b[7], a[7]) < 1e-5 and torch.equal(a[8], b[8])
+
+
 def test_train_step_losses(nets, monkeypatch):
     """one D-step + G-step through fsv.trainer (the mirror of vid2vid_model.py:62-128 + loss_collector.py) on the
     emulated op layer: loss values, the generated frame and parameter gradients against the reference's LossCollector."""

@@ -74,6 +74,10 @@ CONV_CASES = [
     (2, 66, 70, 16, 4, 4, 2, 1, 1, 0, True, False),     # stride 2, 16 taps x 4 outputs (generic wgrad)
     (3, 40, 40, 48, 2, 3, 1, 1, 1, 0, False, True),     # Cin/4 = 12: not a power of two
     (2, 48, 48, 160, 1, 1, 1, 0, 1, 0, True, False),    # 1x1, Cin > 128 (two channel groups in the wgrad)
+    # few pixels, many input channels (face-discriminator heads; thin-output kernels when FSV_THIN_OUT_MIN_PX admits them)
+    (4, 10, 10, 512, 1, 4, 1, 2, 1, 0, True, False),
+    (4, 9, 9, 256, 1, 4, 1, 2, 1, 0, True, False),
+    (2, 7, 5, 64, 2, 3, 1, 1, 1, 0, True, False),
 ]
 
 
@@ -317,6 +321,21 @@ def test_layout_ops():
     (ref * go).sum().backward()
     (back * dev(go)).sum().backward()
     assert grad_err(xg.grad, x.grad) < 1e-5 and grad_err(zg.grad, z.grad) < 1e-5
+
+
+@pytest.mark.parametrize('N,C,H,W,ld,coff', [(2, 3, 40, 40, 3, 0), (4, 20, 33, 37, 32, 0), (1, 70, 32, 35, 96, 8), (3, 6, 64, 17, 15, 5)])
+def test_pack_nchw_to_nhwc_tiled(N, C, H, W, ld, coff):
+    """fsv_nchw_to_nhwc (shared-memory tiled form, H*W >= 1024) into a channel slice [coff, coff+C) of an ld-wide NHWC buffer: exact copy,
+    the rest of the buffer untouched."""
+    ops = _fsv()
+    from fsv._lib import lib, ptr, stream
+    x = torch.randn(N, C, H, W, generator=torch.Generator().manual_seed(C * 100 + W)).cuda()
+    y = torch.full((N, H, W, ld), -7.0, device='cuda')
+    ops._call(lib.fsv_nchw_to_nhwc, ptr(x), ptr(y), N, C, H, W, ld, coff, stream())
+    torch.cuda.synchronize()
+    ref = torch.full((N, H, W, ld), -7.0, device='cuda')
+    ref[..., coff:coff + C] = x.permute(0, 2, 3, 1)
+    assert torch.equal(y, ref)
 
 
 def test_cpu_tensor_is_rejected_loudly():

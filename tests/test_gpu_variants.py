@@ -97,3 +97,35 @@ def test_generator_two_reference_images_vs_reference_golden():
                 assert l2_err(params[k[5:]].grad, T(z[k])) < 1e-2, k
     finally:
         ops.CONV_USE_TC = old
+
+
+def test_generator_two_reference_images_chunked_attention_on_gpu():
+    """No-grad K = 2 forward with the attention matrix formed a few query rows at a time (memory-bounded form of the inference sweep)
+    against the one-piece form on the same kernels: frame, flow, warp, attention visualisation, picked reference."""
+    import torch
+    from fsv import networks, ops
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fsvtest import load_npz, state_from, opt_from, T, rel_err
+    z = load_npz('g_kshot_tiny.npz')
+    opt = opt_from(z)
+    opt.gpu_ids = [0]
+    old = ops.CONV_USE_TC
+    ops.CONV_USE_TC = 0
+    try:
+        G = networks.define_G(opt)
+        sd = state_from(z, 'sd.')
+        G.train()
+        label, lref, iref = T(z['label']).cuda(), T(z['lref']).cuda(), T(z['iref']).cuda()
+        outs = []
+        with torch.no_grad():
+            for budget in (1 << 40, 1, 3 * 4 * label.shape[0] * (label.shape[3] >> G.n_downsample_A) * G.n_shot *
+                           (label.shape[2] >> G.n_downsample_A) * (label.shape[3] >> G.n_downsample_A)):     # one piece; 1 row; 3 rows per chunk
+                G.load_state_dict(sd)
+                G.attention_chunk_bytes = budget
+                outs.append(G(label, lref, iref))
+        a = outs[0]
+        for b in outs[1:]:
+            assert rel_err(b[0], a[0]) < 1e-5 and rel_err(b[1][0], a[1][0]) < 1e-5 and rel_err(b[4][0], a[4][0]) < 1e-5
+            assert rel_err(b[7], a[7]) < 1e-5 and torch.equal(a[8], b[8])
+    finally:
+        ops.CONV_USE_TC = old
