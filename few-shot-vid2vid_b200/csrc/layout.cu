@@ -37,25 +37,28 @@ __global__ void k_nhwc_to_nchw(const float* __restrict__ src, float* __restrict_
         }
     }
 }
-// Tiled form: a block moves 32 pixels x up to 32 channels through shared memory, so that the plane reads (32 consecutive pixels of one
+// Tiled form: a block moves PK_PX pixels x up to 32 channels through shared memory, so that the plane reads (128 consecutive pixels of one
 // channel) AND the pixel-major writes (the channels of one pixel, consecutive pixels back to back when the destination is dense) are both
 // contiguous.  The one-thread-per-pixel kernel above scatters every store instruction of a warp over 32 destination rows (round-2 timeline:
 // 0.46 ms for the discriminator's 20-channel 4 x 512 x 512 input, 0.37 TB/s).  grid (pixel tiles, N).
+#define PK_PX 128
 __global__ void __launch_bounds__(256) k_nchw_to_nhwc_tiled(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int ld, int coff) {
-    __shared__ float tile[32][33];                 // [channel][pixel]
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-    const int p0 = blockIdx.x * 32;
-    const int np = min(32, HW - p0);
+    __shared__ float tile[32][PK_PX + 1];          // [channel][pixel]
+    const int tid = threadIdx.x;
+    const int p0 = blockIdx.x * PK_PX;
+    const int np = min(PK_PX, HW - p0);
     const float* s = src + (long long)blockIdx.y * C * HW + p0;
     float* d = dst + ((long long)blockIdx.y * HW + p0) * ld + coff;
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int nc = min(32, C - c0);
-        for (int c = ty; c < nc; c += 8)
-            if (tx < np) tile[c][tx] = s[(long long)(c0 + c) * HW + tx];
+        for (int i = tid; i < nc * PK_PX; i += 256) {
+            const int c = i / PK_PX, px = i - c * PK_PX;
+            if (px < np) tile[c][px] = s[(long long)(c0 + c) * HW + px];
+        }
         __syncthreads();
         for (int i = tid; i < np * nc; i += 256) {
-            const int p = i / nc, c = i - p * nc;
-            d[(long long)p * ld + c0 + c] = tile[c][p];
+            const int px = i / nc, c = i - px * nc;
+            d[(long long)px * ld + c0 + c] = tile[c][px];
         }
         __syncthreads();
     }
@@ -65,9 +68,9 @@ extern "C" int fsv_nchw_to_nhwc(const float* src, float* dst, int N, int C, int 
     long long HW = (long long)H * W;
     static int tiled = -1;                          // FSV_PACK_TILED=0: the one-thread-per-pixel kernel
     if (tiled < 0) { const char* e = getenv("FSV_PACK_TILED"); tiled = (e && atoi(e) == 0) ? 0 : 1; }
-    if (tiled && N <= 65535 && HW < (1LL << 31) - 32 && HW >= 1024) {
-        dim3 grid((unsigned)((HW + 31) / 32), N);
-        k_nchw_to_nhwc_tiled<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, C, (int)HW, dst_ld, dst_coff);
+    if (tiled && N <= 65535 && HW < (1LL << 31) - PK_PX && HW >= 1024) {
+        dim3 grid((unsigned)((HW + PK_PX - 1) / PK_PX), N);
+        k_nchw_to_nhwc_tiled<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, C, (int)HW, dst_ld, dst_coff);
     } else {
         k_nchw_to_nhwc<<<stream_grid(N * HW, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, N, C, HW, dst_ld, dst_coff);
     }
@@ -130,8 +133,25 @@ __global__ void k_up2_bwd(const float* __restrict__ dy, float* __restrict__ dx, 
         dx[i] = b[0] + b[C] + b[(long long)W * C] + b[(long long)W * C + C];
     }
 }
+// float4 / 32-bit-index form (C % 4 == 0, fewer than 2^31 output float4s): one thread per output float4; the generic kernel above spends
+// its time in three 64-bit divisions per element (round-2 timeline: 80 - 100 us for a 67 MB output, 5x the HBM time)
+__global__ void k_up2_fwd4(const float4* __restrict__ x, float4* __restrict__ y, unsigned total4, unsigned Hs, unsigned Ws, unsigned C4) {
+    const unsigned W = Ws * 2, H = Hs * 2;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        const unsigned c = i % C4, p = i / C4;
+        const unsigned w = p % W, q = p / W;
+        const unsigned h = q % H, n = q / H;
+        y[i] = x[((size_t)(n * Hs + (h >> 1)) * Ws + (w >> 1)) * C4 + c];
+    }
+}
 extern "C" int fsv_upsample2x_fwd(const float* x, float* y, int N, int Hs, int Ws, int C, void* stream) {
     FSV_REQUIRE(N > 0 && Hs > 0 && Ws > 0 && C > 0, "upsample2x: bad dims");
+    const long long total4 = (long long)N * Hs * Ws * C;           // = output elements / 4
+    if (C % 4 == 0 && total4 < (1LL << 31) - (1 << 22) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
+        k_up2_fwd4<<<stream_grid(total4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, (unsigned)total4, Hs, Ws, C / 4);
+        FSV_CHECK_LAUNCH("upsample2x_fwd");
+        return FSV_OK;
+    }
     k_up2_fwd<<<stream_grid((long long)N * Hs * Ws * 4 * C, 256), 256, 0, (cudaStream_t)stream>>>(x, y, N, Hs, Ws, C);
     FSV_CHECK_LAUNCH("upsample2x_fwd");
     return FSV_OK;

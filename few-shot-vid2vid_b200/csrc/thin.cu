@@ -32,7 +32,8 @@ static ThinP thin_p(const fsv_conv_desc* d) {
 }
 
 // ------------------------------------------------------------------ Cin <= 8 forward
-// grid.x = pixel blocks of 128, grid.y = 32-wide output-channel chunks
+// grid.x = pixel blocks of 128 * THIN_PPT, grid.y = 32-wide output-channel chunks
+#define THIN_PPT 4
 __global__ void __launch_bounds__(128) k_thin_cin_fwd(ThinP p, const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, const float* __restrict__ residual,
                                                       float* __restrict__ y) {
@@ -47,7 +48,9 @@ __global__ void __launch_bounds__(128) k_thin_cin_fwd(ThinP p, const float* __re
     }
     __syncthreads();
     const long long total = (long long)p.N * p.Ho * p.Wo;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // THIN_PPT pixels per thread, 128 apart: the weight staging above (taps*Cin*32 global loads per block) is amortised over 512 pixels
+    for (int it = 0; it < THIN_PPT; ++it) {
+    const long long pix = ((long long)blockIdx.x * THIN_PPT + it) * blockDim.x + threadIdx.x;
     if (pix >= total) return;
     const int wo = (int)(pix % p.Wo);
     const long long q = pix / p.Wo;
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(128) k_thin_cin_fwd(ThinP p, const float* __re
         else
             for (int j = 0; j < 4; ++j)
                 if (co0 + c4 * 4 + j < p.Cout) yp[c4 * 4 + j] = v[j];
+    }
     }
 }
 
@@ -613,10 +617,11 @@ static bool thin_common_ok(const fsv_conv_desc* d) {
 }
 // Thin-output layers with few pixels but many input channels (the face discriminator's 512 -> 1 head on 10x10: 484 outputs of 8192
 // MACs each) are far worse off on the generic 64x64 SIMT tile than the large ones: 8 CTAs walk the whole reduction serially (0.5 - 0.75 ms
-// per call in the round-2 timeline).  FSV_THIN_OUT_MIN_PX lowers the pixel threshold of the thin-output kernels for them.
+// per call in the round-2 timeline; -0.9 ms per pose512 step with the thin-output kernels).  FSV_THIN_OUT_MIN_PX = their pixel threshold
+// for layers with >= 64 input channels (default 64; 4096 restores the round-1 dispatch).
 static long long thin_out_min_px() {
     static long long v = -1;
-    if (v < 0) { const char* e = getenv("FSV_THIN_OUT_MIN_PX"); v = e ? atoll(e) : 4096; if (v < 1) v = 1; }
+    if (v < 0) { const char* e = getenv("FSV_THIN_OUT_MIN_PX"); v = e ? atoll(e) : 64; if (v < 1) v = 1; }
     return v;
 }
 extern "C" int fsv_conv2d_thin_kind(const fsv_conv_desc* d) {
@@ -661,7 +666,7 @@ extern "C" int fsv_conv2d_fwd_thin(const fsv_conv_desc* d, const float* x, const
     const long long total = (long long)d->N * d->Ho * d->Wo;
     const int taps = d->kh * d->kw;
     if (kind == 1) {
-        dim3 grid(fsv_cdiv(total, 128), fsv_cdiv(d->Cout, 32));
+        dim3 grid(fsv_cdiv(total, 128 * THIN_PPT), fsv_cdiv(d->Cout, 32));
         k_thin_cin_fwd<<<grid, 128, taps * d->Cin * 32 * sizeof(float), st>>>(p, x, w, bias, residual, y);
     } else {
         FSV_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w) & 15) == 0, "conv2d_fwd_thin: pointers must be 16-byte aligned");

@@ -33,7 +33,7 @@ UP2_BWD_SOURCE = os.environ.get('FSV_UP2_BWD', '1') != '0'
 # mostly small-grid kernels per iteration (a 512 -> 512 linear's weight gradient is 64 CTAs, a 64 -> 64 one a single CTA), and what is
 # still queued when the data-gradient chain ends drains serially (round-2 timeline: a 2.6 ms tail of one-at-a-time launches).  Lane 0
 # is the gathering lane: the grouped spectral backward and the gradient buckets run there after waiting for the lanes used so far.
-SIDE_LANES = max(1, int(os.environ.get('FSV_SIDE_LANES', '1')))
+SIDE_LANES = max(1, int(os.environ.get('FSV_SIDE_LANES', '3')))
 _SIDE, _SIDE_DIRTY = {}, {}           # lane 0 per device; streams that forked work since the last join
 _SIDE_EXTRA, _SIDE_USED, _SIDE_RR = {}, {}, {}
 
