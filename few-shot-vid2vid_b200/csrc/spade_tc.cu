@@ -272,6 +272,284 @@ __global__ void __launch_bounds__(192, MINB) k_spade_tc(const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------ persistent variant (FSV_SPADE_PERSIST)
+// The kernel above lives for ONE 128-pixel x SP_CB-channel tile: barrier init, TMEM allocation, one or two TMA round trips, a handful of
+// MMAs, the epilogue -- about 10 us per CTA for ~73 KB of HBM traffic, two CTAs per SM (round-2 timeline: 145 - 152 us for the
+// 512x512x64 layers = 2.0 TB/s).  Here one CTA per SM walks tiles (tile = blockIdx.x, + gridDim.x, ...) with the protocol of
+// conv_tc.cu's k_conv_tc_p: the operand ring runs continuously across tiles and the gamma/beta accumulators are double-buffered in
+// TMEM (2 x nmaps*2*SP_CB columns <= 512), so the TMA + MMA of tile i+1 overlap the epilogue of tile i.  Two epilogue groups of four
+// warps (one per TMEM buffer) alternate tiles, so one group's x / dout loads are in flight while the other computes and stores.
+//   full[s] / empty[s]  : TMA -> MMA ring, stage counter carried across tiles
+//   acc_full[b]         : tcgen05.commit after the last MMA of a tile -> epilogue group b
+//   acc_empty[b]        : one arrive per warp of group b after its last tcgen05.ld of the tile -> the MMA issuer may overwrite buffer b
+// Tile order: channel blocks of one pixel tile are consecutive tile indices, i.e. they run on neighbouring CTAs at the same time and the
+// map tile they share is fetched from HBM once.
+// NGRP epilogue groups: 2 for the forward (168 registers per thread fit 320 threads); the backward epilogue needs ~250 registers, so it runs
+// one group of four warps that alternates between the two accumulator buffers.
+template <int SP_CB, bool BWD, int NGRP>
+__global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_constant__ SpTcParams p, const float* __restrict__ x,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             float* __restrict__ out, const float* __restrict__ dout,
+                                                             float* __restrict__ dxhat, int stages, int m_tiles) {
+    constexpr int SP_STAGE_BYTES = SP_STAGE_BYTES_OF(SP_CB);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int STG = stages;
+    uint64_t* bars = (uint64_t*)(smem + STG * SP_STAGE_BYTES);      // full[STG], empty[STG], acc_full[2], acc_empty[2]
+    uint64_t* acc_full = bars + 2 * STG;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncb = p.C / SP_CB;
+    const int total = m_tiles * ncb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STG; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[STG + s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&acc_full[b]), 1);
+            mbar_init(smem_u32(&acc_empty[b]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    uint32_t accw = 32;
+    while (accw < (uint32_t)(p.nmaps * 2 * SP_CB)) accw <<= 1;
+    const uint32_t tmem_cols = 2 * accw;                             // host guarantees <= 512
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                int mt = tile / ncb;
+                const int c0 = (tile - mt * ncb) * SP_CB;
+                const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
+                const int n0 = mt * p.TN, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+                for (int i = 0; i < p.nmaps; ++i) {
+                    const int kbs = p.K[i] / TC_BK;
+                    const int wn = p.per_sample[i] ? n0 : 0;
+                    for (int kb = 0; kb < kbs; ++kb, ++it) {
+                        const int s = it % STG;
+                        const uint32_t ph = (it / STG) & 1;
+                        mbar_wait(smem_u32(&bars[STG + s]), ph ^ 1);
+                        const uint32_t full = smem_u32(&bars[s]);
+                        const uint32_t dst = smem_u32(smem + s * SP_STAGE_BYTES);
+                        mbar_expect_tx(full, (uint32_t)SP_STAGE_BYTES);
+                        tma_load_4d(dst, &p.mmap[i], full, kb * TC_BK, w0, h0, n0);
+                        tma_load_3d(dst + TC_A_BYTES, &p.gmap[i], full, kb * TC_BK, c0, wn);
+                        tma_load_3d(dst + TC_A_BYTES + SP_CB * TC_BK * 4, &p.bmap[i], full, kb * TC_BK, c0, wn);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, 2 * SP_CB);
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
+                const uint32_t buf = ti & 1;
+                mbar_wait(smem_u32(&acc_empty[buf]), ((ti >> 1) & 1) ^ 1);      // group `buf` has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * accw;
+                for (int i = 0; i < p.nmaps; ++i) {
+                    const int kbs = p.K[i] / TC_BK;
+                    for (int kb = 0; kb < kbs; ++kb, ++it) {
+                        const int s = it % STG;
+                        const uint32_t ph = (it / STG) & 1;
+                        mbar_wait(smem_u32(&bars[s]), ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + s * SP_STAGE_BYTES);
+                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k)
+                            tc_mma_tf32(d_tmem + (uint32_t)(i * 2 * SP_CB), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                        (kb | k) != 0);
+                        tc_commit(smem_u32(&bars[STG + s]));
+                    }
+                }
+                tc_commit(smem_u32(&acc_full[buf]));
+            }
+        }
+    } else {
+        const int grp = (warp - 2) >> 2;              // epilogue group = TMEM buffer
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int row = q * 32 + lane;
+        const int tw = row % p.TW, r2 = row / p.TW;
+        const int th = r2 % p.TH, tn = r2 / p.TH;
+        const int Hs = p.H / p.up, Ws = p.W / p.up;
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
+            const int buf = (int)(ti & 1);
+            if (NGRP == 2 && buf != grp) continue;
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * accw;
+            int mt = tile / ncb;
+            const int c0 = (tile - mt * ncb) * SP_CB;
+            const int tw_i = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th_i = mt % p.tiles_h; mt /= p.tiles_h;
+            const int n = mt * p.TN + tn, h = th_i * p.TH + th, w = tw_i * p.TW + tw;
+            const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+            const uint32_t par = (ti >> 1) & 1;
+            if constexpr (!BWD) {
+                float v[SP_CB];
+                if (valid) {
+                    const float4* xr = reinterpret_cast<const float4*>(x + (((long long)n * Hs + h / p.up) * Ws + w / p.up) * p.C + c0);
+                    const float* mp = mean + (p.instance ? n * p.C : 0) + c0;
+                    const float* rp = rstd + (p.instance ? n * p.C : 0) + c0;
+#pragma unroll
+                    for (int j = 0; j < SP_CB / 4; ++j) {
+                        float4 t = xr[j];
+                        float4 m = *reinterpret_cast<const float4*>(mp + 4 * j);
+                        float4 r = *reinterpret_cast<const float4*>(rp + 4 * j);
+                        v[4 * j + 0] = (t.x - m.x) * r.x; v[4 * j + 1] = (t.y - m.y) * r.y;
+                        v[4 * j + 2] = (t.z - m.z) * r.z; v[4 * j + 3] = (t.w - m.w) * r.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < SP_CB; ++j) v[j] = 0.f;
+                }
+                mbar_wait(smem_u32(&acc_full[buf]), par);
+                tc_fence_after();
+                for (int i = 0; i < p.nmaps; ++i) {
+                    const float* bgp = p.bg[i] ? p.bg[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 : nullptr;
+                    const float* bbp = p.bb[i] ? p.bb[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 : nullptr;
+#pragma unroll
+                    for (int c = 0; c < SP_CB; c += 32) {
+                        uint32_t g[32], b[32];
+                        const uint32_t taddr = tacc + (uint32_t)(i * 2 * SP_CB + c);
+                        tc_ld32(taddr, g);
+                        tc_ld32(taddr + SP_CB, b);
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float gv = __uint_as_float(g[j]) + (bgp ? bgp[c + j] : 0.f);
+                                float bv = __uint_as_float(b[j]) + (bbp ? bbp[c + j] : 0.f);
+                                v[c + j] = v[c + j] * (1.f + gv) + bv;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));      // accumulator drained: the MMAs of the next tile on this buffer may start
+                if (valid) {
+                    float4* orow = reinterpret_cast<float4*>(out + (((long long)n * p.H + h) * p.W + w) * p.C + c0);
+#pragma unroll
+                    for (int j = 0; j < SP_CB / 4; ++j)
+                        orow[j] = make_float4(fsv_act(v[4 * j], p.act), fsv_act(v[4 * j + 1], p.act), fsv_act(v[4 * j + 2], p.act),
+                                              fsv_act(v[4 * j + 3], p.act));
+                }
+            } else {
+                // backward epilogue: identical to k_spade_tc<.., true>, per 32-channel chunk; gamma is read twice (forward walk, reverse walk)
+                mbar_wait(smem_u32(&acc_full[buf]), par);
+                tc_fence_after();
+                const long long pix = ((long long)n * p.H + h) * p.W + w;
+#pragma unroll 1
+                for (int c = 0; c < SP_CB; c += 32) {
+                    float v[32], vprev[FSV_SPADE_MAX_MAPS][32];
+                    if (valid) {
+                        const float4* xr = reinterpret_cast<const float4*>(x + (((long long)n * Hs + h / p.up) * Ws + w / p.up) * p.C + c0 + c);
+                        const float* mp = mean + (p.instance ? n * p.C : 0) + c0 + c;
+                        const float* rp = rstd + (p.instance ? n * p.C : 0) + c0 + c;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 t = xr[j];
+                            float4 m = *reinterpret_cast<const float4*>(mp + 4 * j);
+                            float4 r = *reinterpret_cast<const float4*>(rp + 4 * j);
+                            v[4 * j + 0] = (t.x - m.x) * r.x; v[4 * j + 1] = (t.y - m.y) * r.y;
+                            v[4 * j + 2] = (t.z - m.z) * r.z; v[4 * j + 3] = (t.w - m.w) * r.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < FSV_SPADE_MAX_MAPS; ++i) {
+                        if (i < p.nmaps) {
+                            const float* bgp = p.bg[i] ? p.bg[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
+                            const float* bbp = p.bb[i] ? p.bb[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
+                            uint32_t g[32], b[32];
+                            const uint32_t taddr = tacc + (uint32_t)(i * 2 * SP_CB + c);
+                            tc_ld32(taddr, g);
+                            tc_ld32(taddr + SP_CB, b);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float gv = __uint_as_float(g[j]) + ((bgp && valid) ? bgp[j] : 0.f);
+                                float bv = __uint_as_float(b[j]) + ((bbp && valid) ? bbp[j] : 0.f);
+                                vprev[i][j] = v[j];
+                                v[j] = v[j] * (1.f + gv) + bv;
+                            }
+                        }
+                    }
+                    float gr[32];
+                    if (valid) {
+                        const float4* dr = reinterpret_cast<const float4*>(dout + pix * p.C + c0 + c);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 t = dr[j];
+                            gr[4 * j + 0] = t.x; gr[4 * j + 1] = t.y; gr[4 * j + 2] = t.z; gr[4 * j + 3] = t.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (p.act == FSV_ACT_LRELU) gr[j] *= (v[j] > 0.f ? 1.f : FSV_LRELU_SLOPE);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) gr[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int i = FSV_SPADE_MAX_MAPS - 1; i >= 0; --i) {
+                        if (i < p.nmaps) {
+                            const float* bgp = p.bg[i] ? p.bg[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
+                            uint32_t g[32];
+                            tc_ld32(tacc + (uint32_t)(i * 2 * SP_CB + c), g);
+                            if (valid) {
+                                float4* db = reinterpret_cast<float4*>(p.dbeta[i] + pix * p.dgb_ld[i] + c0 + c);
+                                float4* dg = reinterpret_cast<float4*>(p.dgamma[i] + pix * p.dgb_ld[i] + c0 + c);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    db[j] = make_float4(gr[4 * j], gr[4 * j + 1], gr[4 * j + 2], gr[4 * j + 3]);
+                                    dg[j] = make_float4(gr[4 * j] * vprev[i][4 * j], gr[4 * j + 1] * vprev[i][4 * j + 1],
+                                                        gr[4 * j + 2] * vprev[i][4 * j + 2], gr[4 * j + 3] * vprev[i][4 * j + 3]);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float gv = __uint_as_float(g[j]) + ((bgp && valid) ? bgp[j] : 0.f);
+                                gr[j] *= (1.f + gv);
+                            }
+                        }
+                    }
+                    if (valid) {
+                        float4* dxr = reinterpret_cast<float4*>(dxhat + pix * p.C + c0 + c);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dxr[j] = make_float4(gr[4 * j], gr[4 * j + 1], gr[4 * j + 2], gr[4 * j + 3]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
 // ------------------------------------------------------------------ host side
 static void sp_pick_tile(int H, int W, int& TW, int& TH, int& TN) {
     TW = 16; TH = 8; TN = 1;
@@ -367,6 +645,38 @@ static int spade_tc_launch(const fsv_spade_desc* d, const float* x, const float*
     }
     dim3 grid(p.tiles_w * p.tiles_h * tiles_n, d->C / CB);
     cudaStream_t st = (cudaStream_t)stream;
+    // persistent variant: FSV_SPADE_PERSIST bit 0 = forward, bit 1 = backward; needs both accumulator buffers in the 512 TMEM columns
+    static int persist = -1;
+    if (persist < 0) { const char* e = getenv("FSV_SPADE_PERSIST"); persist = e ? atoi(e) : 0; }
+    if ((persist & (bwd ? 2 : 1)) && d->nmaps * 2 * CB <= 256) {
+        const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+        const long long total = (long long)m_tiles * (d->C / CB);
+        int num_k = 0;
+        for (int i = 0; i < d->nmaps; ++i) num_k += d->K[i] / TC_BK;
+        int stages = (176 * 1024) / SP_STAGE_BYTES_OF(CB);          // one CTA per SM (it owns all of TMEM): a deep ring, several tiles ahead
+        if (stages > 8) stages = 8;
+        if (stages > 4 * num_k) stages = 4 * num_k;
+        if (stages < 2) stages = 2;
+        const int smem_p = stages * SP_STAGE_BYTES_OF(CB) + (2 * stages + 4) * 8 + 16 + 1024;
+        static unsigned long long configured_p = 0;
+        if (fsv_first_on_device(&configured_p)) {
+            FSV_CUDA(cudaFuncSetAttribute((k_spade_tc_p<64, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            FSV_CUDA(cudaFuncSetAttribute((k_spade_tc_p<32, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            FSV_CUDA(cudaFuncSetAttribute((k_spade_tc_p<64, true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            FSV_CUDA(cudaFuncSetAttribute((k_spade_tc_p<32, true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        }
+        long long gx = fsv_sm_count();
+        if (gx > total) gx = total;
+        if (!bwd) {
+            if (CB == 64) k_spade_tc_p<64, false, 2><<<(unsigned)gx, 320, smem_p, st>>>(p, x, mean, rstd, out, nullptr, nullptr, stages, m_tiles);
+            else k_spade_tc_p<32, false, 2><<<(unsigned)gx, 320, smem_p, st>>>(p, x, mean, rstd, out, nullptr, nullptr, stages, m_tiles);
+        } else {
+            if (CB == 64) k_spade_tc_p<64, true, 1><<<(unsigned)gx, 192, smem_p, st>>>(p, x, mean, rstd, nullptr, dout, dxhat, stages, m_tiles);
+            else k_spade_tc_p<32, true, 1><<<(unsigned)gx, 192, smem_p, st>>>(p, x, mean, rstd, nullptr, dout, dxhat, stages, m_tiles);
+        }
+        FSV_CHECK_LAUNCH(who);
+        return FSV_OK;
+    }
     if (!bwd) {
         if (CB == 64) k_spade_tc<64, false><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, out, nullptr, nullptr);
         else if (force_f == 32) k_spade_tc<32, false, 3><<<grid, 192, smem_bytes, st>>>(p, x, mean, rstd, out, nullptr, nullptr);   // 3 CTAs / SM
