@@ -647,7 +647,7 @@ static int spade_tc_launch(const fsv_spade_desc* d, const float* x, const float*
     cudaStream_t st = (cudaStream_t)stream;
     // persistent variant: FSV_SPADE_PERSIST bit 0 = forward, bit 1 = backward; needs both accumulator buffers in the 512 TMEM columns
     static int persist = -1;
-    if (persist < 0) { const char* e = getenv("FSV_SPADE_PERSIST"); persist = e ? atoi(e) : 0; }
+    if (persist < 0) { const char* e = getenv("FSV_SPADE_PERSIST"); persist = e ? atoi(e) : 3; }
     if ((persist & (bwd ? 2 : 1)) && d->nmaps * 2 * CB <= 256) {
         const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
         const long long total = (long long)m_tiles * (d->C / CB);
