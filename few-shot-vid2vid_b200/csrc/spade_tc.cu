@@ -292,10 +292,16 @@ __global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_
                                                              float* __restrict__ out, const float* __restrict__ dout,
                                                              float* __restrict__ dxhat, int stages, int m_tiles) {
     constexpr int SP_STAGE_BYTES = SP_STAGE_BYTES_OF(SP_CB);
+    constexpr int MAXM = SP_CB == 64 ? 2 : FSV_SPADE_MAX_MAPS;     // the host admits nmaps * 2 * SP_CB <= 256 only
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int STG = stages;
-    uint64_t* bars = (uint64_t*)(smem + STG * SP_STAGE_BYTES);      // full[STG], empty[STG], acc_full[2], acc_empty[2]
+    // forward: per epilogue warp a 32-row x SP_CB staging area through which the output tile is transposed, so that a store instruction
+    // writes whole pixels (SP_CB*4 contiguous bytes each) instead of 16 bytes of 32 different pixels (ncu, session 17: half of every
+    // written sector unused, 32 sectors per store request)
+    constexpr int SPP_STAGING = BWD ? 0 : NGRP * 4 * 32 * SP_CB * 4;
+    uint8_t* stage_base = smem + STG * SP_STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(stage_base + SPP_STAGING);         // full[STG], empty[STG], acc_full[2], acc_empty[2]
     uint64_t* acc_full = bars + 2 * STG;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
@@ -431,11 +437,16 @@ __global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_
                         tc_ld32(taddr, g);
                         tc_ld32(taddr + SP_CB, b);
                         if (valid) {
+                            // biases: per-channel constants, 16-byte loads (the scalar form issued 4 x 32 loads per map and chunk -- 3/4 of
+                            // this kernel's load instructions in the ncu capture of session 17)
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float gv = __uint_as_float(g[j]) + (bgp ? bgp[c + j] : 0.f);
-                                float bv = __uint_as_float(b[j]) + (bbp ? bbp[c + j] : 0.f);
-                                v[c + j] = v[c + j] * (1.f + gv) + bv;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 g4 = bgp ? *reinterpret_cast<const float4*>(bgp + c + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 b4 = bbp ? *reinterpret_cast<const float4*>(bbp + c + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                v[c + j + 0] = v[c + j + 0] * (1.f + (__uint_as_float(g[j + 0]) + g4.x)) + (__uint_as_float(b[j + 0]) + b4.x);
+                                v[c + j + 1] = v[c + j + 1] * (1.f + (__uint_as_float(g[j + 1]) + g4.y)) + (__uint_as_float(b[j + 1]) + b4.y);
+                                v[c + j + 2] = v[c + j + 2] * (1.f + (__uint_as_float(g[j + 2]) + g4.z)) + (__uint_as_float(b[j + 2]) + b4.z);
+                                v[c + j + 3] = v[c + j + 3] * (1.f + (__uint_as_float(g[j + 3]) + g4.w)) + (__uint_as_float(b[j + 3]) + b4.w);
                             }
                         }
                     }
@@ -443,12 +454,25 @@ __global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));      // accumulator drained: the MMAs of the next tile on this buffer may start
-                if (valid) {
-                    float4* orow = reinterpret_cast<float4*>(out + (((long long)n * p.H + h) * p.W + w) * p.C + c0);
+                {
+                    constexpr int LPR = SP_CB / 4;          // lanes per pixel row (float4 each)
+                    constexpr int RPI = 32 / LPR;           // pixel rows per store instruction
+                    float4* stg = reinterpret_cast<float4*>(stage_base) + (warp - 2) * (32 * LPR);
+                    const int sw = lane & 7;                // XOR swizzle of the 16-byte column: conflict-free writes and reads
 #pragma unroll
-                    for (int j = 0; j < SP_CB / 4; ++j)
-                        orow[j] = make_float4(fsv_act(v[4 * j], p.act), fsv_act(v[4 * j + 1], p.act), fsv_act(v[4 * j + 2], p.act),
-                                              fsv_act(v[4 * j + 3], p.act));
+                    for (int j = 0; j < LPR; ++j)
+                        stg[lane * LPR + (j ^ sw)] = make_float4(fsv_act(v[4 * j], p.act), fsv_act(v[4 * j + 1], p.act), fsv_act(v[4 * j + 2], p.act),
+                                                                 fsv_act(v[4 * j + 3], p.act));
+                    const long long pixoff = valid ? (((long long)n * p.H + h) * p.W + w) * p.C + c0 : -1;
+                    __syncwarp();
+#pragma unroll 4
+                    for (int it = 0; it < 32 / RPI; ++it) {
+                        const int rr = it * RPI + lane / LPR, c4 = lane % LPR;
+                        const long long off = __shfl_sync(0xffffffffu, pixoff, rr);
+                        const float4 t = stg[rr * LPR + (c4 ^ (rr & 7))];
+                        if (off >= 0) *reinterpret_cast<float4*>(out + off + c4 * 4) = t;
+                    }
+                    __syncwarp();
                 }
             } else {
                 // backward epilogue: identical to k_spade_tc<.., true>, per 32-channel chunk; gamma is read twice (forward walk, reverse walk)
@@ -457,7 +481,7 @@ __global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_
                 const long long pix = ((long long)n * p.H + h) * p.W + w;
 #pragma unroll 1
                 for (int c = 0; c < SP_CB; c += 32) {
-                    float v[32], vprev[FSV_SPADE_MAX_MAPS][32];
+                    float v[32], vprev[MAXM][32];
                     if (valid) {
                         const float4* xr = reinterpret_cast<const float4*>(x + (((long long)n * Hs + h / p.up) * Ws + w / p.up) * p.C + c0 + c);
                         const float* mp = mean + (p.instance ? n * p.C : 0) + c0 + c;
@@ -475,7 +499,7 @@ __global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_
                         for (int j = 0; j < 32; ++j) v[j] = 0.f;
                     }
 #pragma unroll
-                    for (int i = 0; i < FSV_SPADE_MAX_MAPS; ++i) {
+                    for (int i = 0; i < MAXM; ++i) {
                         if (i < p.nmaps) {
                             const float* bgp = p.bg[i] ? p.bg[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
                             const float* bbp = p.bb[i] ? p.bb[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
@@ -484,11 +508,13 @@ __global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_
                             tc_ld32(taddr, g);
                             tc_ld32(taddr + SP_CB, b);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float gv = __uint_as_float(g[j]) + ((bgp && valid) ? bgp[j] : 0.f);
-                                float bv = __uint_as_float(b[j]) + ((bbp && valid) ? bbp[j] : 0.f);
-                                vprev[i][j] = v[j];
-                                v[j] = v[j] * (1.f + gv) + bv;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 g4 = (bgp && valid) ? *reinterpret_cast<const float4*>(bgp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 b4 = (bbp && valid) ? *reinterpret_cast<const float4*>(bbp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                vprev[i][j + 0] = v[j + 0]; v[j + 0] = v[j + 0] * (1.f + (__uint_as_float(g[j + 0]) + g4.x)) + (__uint_as_float(b[j + 0]) + b4.x);
+                                vprev[i][j + 1] = v[j + 1]; v[j + 1] = v[j + 1] * (1.f + (__uint_as_float(g[j + 1]) + g4.y)) + (__uint_as_float(b[j + 1]) + b4.y);
+                                vprev[i][j + 2] = v[j + 2]; v[j + 2] = v[j + 2] * (1.f + (__uint_as_float(g[j + 2]) + g4.z)) + (__uint_as_float(b[j + 2]) + b4.z);
+                                vprev[i][j + 3] = v[j + 3]; v[j + 3] = v[j + 3] * (1.f + (__uint_as_float(g[j + 3]) + g4.w)) + (__uint_as_float(b[j + 3]) + b4.w);
                             }
                         }
                     }
@@ -508,7 +534,7 @@ __global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_
                         for (int j = 0; j < 32; ++j) gr[j] = 0.f;
                     }
 #pragma unroll
-                    for (int i = FSV_SPADE_MAX_MAPS - 1; i >= 0; --i) {
+                    for (int i = MAXM - 1; i >= 0; --i) {
                         if (i < p.nmaps) {
                             const float* bgp = p.bg[i] ? p.bg[i] + (long long)(p.per_sample[i] ? n : 0) * p.b_nstride[i] + c0 + c : nullptr;
                             uint32_t g[32];
@@ -524,9 +550,12 @@ __global__ void __launch_bounds__(64 + 128 * NGRP, 1) k_spade_tc_p(const __grid_
                                 }
                             }
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float gv = __uint_as_float(g[j]) + ((bgp && valid) ? bgp[j] : 0.f);
-                                gr[j] *= (1.f + gv);
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 g4 = (bgp && valid) ? *reinterpret_cast<const float4*>(bgp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                gr[j + 0] *= (1.f + (__uint_as_float(g[j + 0]) + g4.x));
+                                gr[j + 1] *= (1.f + (__uint_as_float(g[j + 1]) + g4.y));
+                                gr[j + 2] *= (1.f + (__uint_as_float(g[j + 2]) + g4.z));
+                                gr[j + 3] *= (1.f + (__uint_as_float(g[j + 3]) + g4.w));
                             }
                         }
                     }
@@ -648,16 +677,20 @@ static int spade_tc_launch(const fsv_spade_desc* d, const float* x, const float*
     // persistent variant: FSV_SPADE_PERSIST bit 0 = forward, bit 1 = backward; needs both accumulator buffers in the 512 TMEM columns
     static int persist = -1;
     if (persist < 0) { const char* e = getenv("FSV_SPADE_PERSIST"); persist = e ? atoi(e) : 3; }
-    if ((persist & (bwd ? 2 : 1)) && d->nmaps * 2 * CB <= 256) {
+    bool bias_al = true;            // the persistent kernels read the biases with 16-byte loads
+    for (int i = 0; i < d->nmaps; ++i)
+        bias_al = bias_al && (!bg[i] || (((uintptr_t)bg[i]) & 15) == 0) && (!bb[i] || (((uintptr_t)bb[i]) & 15) == 0);
+    if ((persist & (bwd ? 2 : 1)) && d->nmaps * 2 * CB <= 256 && bias_al) {
         const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
         const long long total = (long long)m_tiles * (d->C / CB);
         int num_k = 0;
         for (int i = 0; i < d->nmaps; ++i) num_k += d->K[i] / TC_BK;
-        int stages = (176 * 1024) / SP_STAGE_BYTES_OF(CB);          // one CTA per SM (it owns all of TMEM): a deep ring, several tiles ahead
+        const int staging = bwd ? 0 : 2 * 4 * 32 * CB * 4;          // forward: output transposition area of the eight epilogue warps
+        int stages = (176 * 1024 - staging) / SP_STAGE_BYTES_OF(CB);   // one CTA per SM (it owns all of TMEM): a deep ring, several tiles ahead
         if (stages > 8) stages = 8;
         if (stages > 4 * num_k) stages = 4 * num_k;
         if (stages < 2) stages = 2;
-        const int smem_p = stages * SP_STAGE_BYTES_OF(CB) + (2 * stages + 4) * 8 + 16 + 1024;
+        const int smem_p = stages * SP_STAGE_BYTES_OF(CB) + staging + (2 * stages + 4) * 8 + 16 + 1024;
         static unsigned long long configured_p = 0;
         if (fsv_first_on_device(&configured_p)) {
             FSV_CUDA(cudaFuncSetAttribute((k_spade_tc_p<64, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
