@@ -147,6 +147,24 @@ def load_peaks():
     return dict(hbm=6650.0, tflops=1400.0, src='fallback (B200_PROFILING.md)')
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernels from the committed ncu --set full capture of layers of known shape
+    (scripts/ncu_layers.py -> profiles/ncu_traffic_r2.json): {'conv': {...}, 'spade': {...}} or {}."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic_r2.json')
+    if not os.path.exists(path):
+        return {}
+    t = json.load(open(path))
+    out = {}
+    for l in t.get('launches', []):
+        if 'conv' not in out and l['kernel'].startswith('k_conv_tc_p') and l['grid'].replace(' ', '') == '(128,1,1)':
+            out['conv'] = {'dram_bytes_per_launch': l['dram'], 'algorithmic_bytes_per_launch': t['layers']['conv64']['fwd_bytes'], 'launch_us_under_ncu': l['us'],
+                           'layer': 'k_conv_tc_p forward ' + t['layers']['conv64']['shape']}
+        if 'spade' not in out and 'k_spade_tc_p<64, 0' in l['kernel']:
+            out['spade'] = {'dram_bytes_per_launch': l['dram'], 'algorithmic_bytes_per_launch': t['layers']['spade512']['fwd_bytes'], 'launch_us_under_ncu': l['us'],
+                            'layer': 'k_spade_tc_p forward ' + t['layers']['spade512']['shape']}
+    return out
+
+
 def host_threads():
     return min(os.cpu_count() or 1, 32)   # more threads than this slows the small per-layer CPU convs down
 
@@ -364,11 +382,14 @@ def run_fsv(args):
     conv_ms = sum(v[0] for k, v in prof.items() if k.startswith('fsv_conv2d'))
     total_ms = sum(v[0] for v in prof.values())
     ach = acc['conv_flops'] / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = ncu_traffic()
     roof = {'bound': 'tensor', 'kernel': 'fsv_conv2d_{fwd,dgrad,wgrad}* (all launches of one step)', 'achieved': ach, 'peak': peaks['tflops'],
-            'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
+            'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': traffic.get('conv', {}).get('dram_bytes_per_launch'),
+            'traffic_detail': traffic.get('conv'),
             'flops_executed_per_step': acc['conv_flops'], 'family_ms_per_step_eager': conv_ms,
-            'note': 'executed FLOPs summed from the launch descriptors (4/9 for upsample-collapsed convs; SPADE gamma/beta GEMMs excluded), '
-                    'time = CUDA events around each launch in an eager pass; traffic: aggregate over many shapes, per-launch dram bytes are in profiles/',
+            'note': 'executed FLOPs summed from the launch descriptors (4/9 for upsample-collapsed convs, forward and backward; SPADE gamma/beta GEMMs '
+                    'excluded), time = CUDA events around each launch in an eager pass; traffic = dram__bytes_read+write of ONE launch of the most '
+                    'frequent conv class from the committed ncu capture (profiles/ncu_layers_r2_summary.txt), see traffic_detail',
             'peak_source': peaks['src'] + ', dense bf16 sustained', 'share_of_step_kernel_time': conv_ms / total_ms if total_ms else None}
     if wl.get('flop'):
         roof['whole_step'] = {'achieved': value / world * wl['flop'] / 1e12, 'frac': value / world * wl['flop'] / 1e12 / peaks['tflops'],
@@ -378,7 +399,8 @@ def run_fsv(args):
     if sp_ms > 0:
         a = acc['spade_bytes'] / (sp_ms / 1e3) / 1e9
         roof_spade = {'bound': 'hbm', 'kernel': 'fsv_spade_fwd[_tc] (all launches of one step)', 'achieved': a, 'peak': peaks['hbm'],
-                      'unit': 'GB/s', 'frac': a / peaks['hbm'], 'traffic': None, 'peak_source': peaks['src']}
+                      'unit': 'GB/s', 'frac': a / peaks['hbm'], 'traffic': traffic.get('spade', {}).get('dram_bytes_per_launch'),
+                      'traffic_detail': traffic.get('spade'), 'peak_source': peaks['src']}
     line = base_line(args, wl, value, t_step * 1e3, 'fp32' if ops.CONV_USE_TC == 0 else 'tf32', batch,
                      {'global_batch': gbatch, 'parallelism': 'dp%d' % world, 'cuda_graph': bool(use_graph), 'cuda_graph_note': graph_note,
                       'l2': 'per-step working set (activations of %d %dx%d frames) is far larger than the 126 MB L2' % (batch, wl['H'], wl['W'])})

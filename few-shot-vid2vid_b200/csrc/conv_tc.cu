@@ -22,6 +22,7 @@
 // 1.05 MFLOP (32 FLOP/B) through L2, so this first version is L2-bandwidth bound below the TF32 peak
 // (DESIGN.md section 5).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 #define TC_MAX_TAPS 16
 #define TC_MAX_STAGES 8
@@ -47,6 +48,10 @@ struct __align__(64) TcParams {
     // geometry, so tile index = (class, channel block, pixel tile).
     int ncls;
     int cls_t0[4], cls_nt[4];
+    // bring-up experiment (FSV_TC_SHIFT_EXP, one-tile-per-CTA kernel only): the A box is loaded one pixel to the left and the UMMA descriptor
+    // starts one 128-byte row later -- does a start address that is not aligned to the 1024-byte swizzle pattern address the rows it should?
+    // 1: base_offset 0, 2: base_offset = (start >> 7) & 7.  Pixels with tw == TW-1 are wrong by construction.  See scripts/shift_exp.py.
+    int shift_exp;
 };
 
 // ------------------------------------------------------------------ kernel
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
                 const uint32_t full = smem_u32(&bars[s]);
                 const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
                 mbar_expect_tx(full, (uint32_t)stage_bytes);
-                tma_load_4d(a_dst, &p.amap[tap.map], full, cb * TC_BK, w0 + tap.dw, h0 + tap.dh, n0);
+                tma_load_4d(a_dst, &p.amap[tap.map], full, cb * TC_BK, w0 + tap.dw - (p.shift_exp ? 1 : 0), h0 + tap.dh, n0);
                 tma_load_3d(a_dst + TC_A_BYTES, &p.bmap, full, tap.wk * p.Cin + cb * TC_BK, co0, p.w_per_sample ? n0 : 0);
             }
         }
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcPa
                 mbar_wait(smem_u32(&bars[s]), ph);                           // operands landed
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                uint64_t adesc = make_kmajor_sw128_desc(a_addr + (p.shift_exp ? 128u : 0u));
+                if (p.shift_exp == 2) adesc |= (uint64_t)(((a_addr + 128u) >> 7) & 7u) << 49;
                 const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + TC_A_BYTES);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
@@ -510,6 +516,11 @@ static int launch_tc(TcParams& p, int tiles_n, const float* bias, const float* r
         k_conv_tc_p<<<(unsigned)gx, 192, smem_p, st>>>(p, bias, residual, y);
         FSV_CHECK_LAUNCH(who);
         return FSV_OK;
+    }
+    {
+        static int exp_mode = -1;
+        if (exp_mode < 0) { const char* e = getenv("FSV_TC_SHIFT_EXP"); exp_mode = e ? atoi(e) : 0; }
+        p.shift_exp = exp_mode;
     }
     dim3 grid(p.m_tiles, p.Cout / p.BN);
     k_conv_tc<<<grid, 192, smem_bytes, st>>>(p, bias, residual, y);

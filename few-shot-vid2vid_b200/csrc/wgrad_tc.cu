@@ -170,6 +170,10 @@ struct __align__(64) WgMnParams {
     long long dw_nstride;
     int stages;                         // smem ring depth (2..WG_MAX_STAGES)
     int lbo16, sbo16, kstep16, ltype;   // descriptor fields in 16-byte units (tunable while bringing the layout up)
+    // bring-up experiment (FSV_WG_SHIFT_EXP): the x box is loaded one pixel to the left and its descriptor starts one 128-byte K row later
+    // (1: base_offset 0, 2: (start >> 7) & 3, 3: (start >> 7) & 7); K row 31 of every block is then garbage -- scripts/shift_exp.py zeroes
+    // the dy pixels it meets.
+    int shift_exp;
 };
 
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, int lbo16, int sbo16, int ltype) {
@@ -245,10 +249,11 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ 
                 const uint32_t full = smem_u32(&bars[s]);
                 const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
                 mbar_expect_tx(full, (uint32_t)stage_bytes);
+                const int xs = p.shift_exp ? 1 : 0;
                 for (int j = 0; j < 4; ++j)
-                    tma_load_4d(a_dst + j * WGMN_BLOCK_BYTES, amap, full, m0 + 32 * j, w0 + a_dw, h0 + a_dh, nn0);
+                    tma_load_4d(a_dst + j * WGMN_BLOCK_BYTES, amap, full, m0 + 32 * j, w0 + a_dw - (p.role == 1 ? xs : 0), h0 + a_dh, nn0);
                 for (int j = 0; j < BN / 32; ++j)
-                    tma_load_4d(a_dst + a_bytes + j * WGMN_BLOCK_BYTES, bmap, full, n0 + 32 * j, w0 + b_dw, h0 + b_dh, nn0);
+                    tma_load_4d(a_dst + a_bytes + j * WGMN_BLOCK_BYTES, bmap, full, n0 + 32 * j, w0 + b_dw - (p.role == 0 ? xs : 0), h0 + b_dh, nn0);
             }
         }
     } else if (warp == 1) {
@@ -260,8 +265,13 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_tc_mn(const __grid_constant__ 
                 mbar_wait(smem_u32(&bars[s]), ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                const uint64_t adesc = make_mnmajor_desc(a_addr, p.lbo16, p.sbo16, p.ltype);
-                const uint64_t bdesc = make_mnmajor_desc(a_addr + a_bytes, p.lbo16, p.sbo16, p.ltype);
+                uint64_t adesc = make_mnmajor_desc(a_addr + ((p.shift_exp && p.role == 1) ? 128u : 0u), p.lbo16, p.sbo16, p.ltype);
+                uint64_t bdesc = make_mnmajor_desc(a_addr + a_bytes + ((p.shift_exp && p.role == 0) ? 128u : 0u), p.lbo16, p.sbo16, p.ltype);
+                if (p.shift_exp >= 2) {
+                    const uint32_t xa = (p.role == 1 ? a_addr : a_addr + a_bytes) + 128u;
+                    const uint64_t bo = (uint64_t)((xa >> 7) & (p.shift_exp == 2 ? 3u : 7u)) << 49;
+                    if (p.role == 1) adesc |= bo; else bdesc |= bo;
+                }
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k)     // 8 pixels = 8 rows of 128 B = +1024 B = +64 in (addr >> 4)
                     tc_mma_tf32(tmem_base, adesc + (uint64_t)(k * p.kstep16), bdesc + (uint64_t)(k * p.kstep16), idesc, (i | k) != 0);
@@ -501,6 +511,11 @@ static int wgrad_tc_mn(const fsv_conv_desc* d, const float* x, const float* dy, 
     p.sbo16 = 512 >> 4;                // 512 B between groups of 4 K rows
     p.kstep16 = 1024 >> 4;             // 8 pixels (one tf32 MMA K step) = 8 rows x 128 B
     p.ltype = 1;                       // SWIZZLE_128B_BASE32B
+    {
+        static int exp_mode = -1;
+        if (exp_mode < 0) { const char* e = getenv("FSV_WG_SHIFT_EXP"); exp_mode = e ? atoi(e) : 0; }
+        p.shift_exp = exp_mode;
+    }
     const int KB = p.nWB * p.nHB * p.nNB;
     const long long base = (long long)taps * p.mtiles * p.ntiles;
     // split-K: enough CTAs for ~1.5 waves; every extra split costs Cout*taps*Cin fp32 reductions into dW through L2
