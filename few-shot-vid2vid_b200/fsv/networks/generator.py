@@ -24,6 +24,9 @@ from .. import ops
 from ..ops import ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID
 from .layers import Conv2d, Linear, BatchNorm, ConvNormAct, SPADEResnetBlock, SpectralPlanner, spectral, init_weights
 
+# image / label reference encoders on separate streams (FSV_ENC_SPLIT; off until measured)
+ENC_SPLIT = os.environ.get('FSV_ENC_SPLIT', '0') != '0'
+
 
 class BaseNetwork(nn.Module):
     """base_network.py:76-124 surface used from outside the networks."""
@@ -371,6 +374,33 @@ class FewShotGenerator(BaseNetwork):
 
     def reference_encoding(self, img_ref, label_ref, need_weights, label=None, n=1):
         nd = self.n_downsample_G
+        if n == 1 and ENC_SPLIT and getattr(ops, 'BRANCH_STREAMS', False) and img_ref.is_cuda:
+            # the image and the label encoder (generator.py:341-372) are independent chains of small convolutions until their feature
+            # pyramids meet in the outer products: the label chain runs on a stream of its own (reduction lane 3)
+            s_lab = ops.branch_fork(label_ref, index=3)
+            with torch.cuda.stream(s_lab):
+                xl = self.ref_label_first(label_ref)
+                for i in range(nd):
+                    xl = getattr(self, 'ref_label_down_%d' % i)(xl)
+                enc_lab = [xl]
+                if need_weights:
+                    for i in reversed(range(nd)):
+                        enc_lab.append(getattr(self, 'ref_label_up_%d' % i)(enc_lab[-1]))
+            x = self.ref_img_first(img_ref)
+            for i in range(nd):
+                x = getattr(self, 'ref_img_down_%d' % i)(x)
+            encoded = None
+            if need_weights:
+                enc_img = [x]
+                for i in reversed(range(nd)):
+                    enc_img.append(getattr(self, 'ref_img_up_%d' % i)(enc_img[-1]))
+                ops.branch_join(s_lab, *enc_lab)
+                enc_img, enc_lab = enc_img[::-1], enc_lab[::-1]
+                used = set(min(nd, i + 1) for i in range(self.n_adaptive_layers)) if self.adap_spade else set()
+                encoded = [ops.softmax_outer(enc_img[j], enc_lab[j]) if j in used else None for j in range(nd + 1)]
+            else:
+                ops.branch_join(s_lab, xl)
+            return x, encoded
         x = self.ref_img_first(img_ref)
         xl = self.ref_label_first(label_ref)
         atn_vis = ref_idx = None
