@@ -24,8 +24,8 @@ from .. import ops
 from ..ops import ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID
 from .layers import Conv2d, Linear, BatchNorm, ConvNormAct, SPADEResnetBlock, SpectralPlanner, spectral, init_weights
 
-# image / label reference encoders on separate streams (FSV_ENC_SPLIT; off until measured)
-ENC_SPLIT = os.environ.get('FSV_ENC_SPLIT', '0') != '0'
+# image / label reference encoders on separate streams (FSV_ENC_SPLIT=0: one stream; -0.35 .. -0.75 ms per pose512 step, session 20)
+ENC_SPLIT = os.environ.get('FSV_ENC_SPLIT', '1') != '0'
 
 
 class BaseNetwork(nn.Module):
