@@ -18,7 +18,8 @@
 // Tickets of the last-block reductions, one bank per "reduction lane": kernels of one lane must be stream-ordered among themselves,
 // different lanes may run concurrently (the drop-in generator runs its reference-encoder / hyper-network branch on a second stream
 // next to the flow / warp branch; each stream selects its own lane with fsv_set_reduction_lane, a thread-local host setting).
-#define RED_LANES 4
+// Lanes: 0 main stream, 1 / 3 generator branch streams, 2 discriminator-update stream, 4 .. 7 weight-gradient lanes (fsv/ops.py).
+#define RED_LANES 8
 __device__ unsigned int g_red_ticket[RED_LANES][RED_MAX_TICKETS];
 static thread_local int t_red_lane = 0;
 extern "C" int fsv_set_reduction_lane(int lane) {
@@ -26,6 +27,7 @@ extern "C" int fsv_set_reduction_lane(int lane) {
     t_red_lane = lane;
     return FSV_OK;
 }
+int fsv_current_reduction_lane() { return t_red_lane; }       // spectral.cu keeps its per-weight tickets in the same lanes
 
 // Generic two-value per-(group, channel) reduction over the rows of an NHWC slice: f(row, c) -> float2.
 // grid (row blocks, 32-channel blocks, groups), block 32 x 8.  Every block leaves its fp64 partials in `part`; the last

@@ -17,9 +17,14 @@
 
 #define SN_THREADS 256
 
-__device__ unsigned int g_sn_ticket[4];
+// Tickets of the per-weight kernels, one bank per reduction lane (norm.cu: fsv_set_reduction_lane): per-weight calls run wherever the
+// module runs -- the generator's branch streams in a recording forward, the gathering weight-gradient lane in backward -- and two
+// streams sharing one counter corrupt it for the rest of the process (round-2 session 21: garbage sigma in every later call).
+#define SN_LANES 8
+int fsv_current_reduction_lane();
+__device__ unsigned int g_sn_ticket[SN_LANES][4];
 #define SN_MAXCHUNKS 4096
-__device__ unsigned int g_sn_colticket[SN_MAXCHUNKS];
+__device__ unsigned int g_sn_colticket[SN_LANES][SN_MAXCHUNKS];
 
 __device__ __forceinline__ float block_sum(float v, float* sh) {
     v = warp_sum(v);
@@ -80,8 +85,8 @@ __device__ __forceinline__ void sn_wtu_body(const float* __restrict__ W, const f
     if (threadIdx.x == 0) nrm_part[chunk] = nrm;
 }
 __global__ void __launch_bounds__(SN_THREADS) k_sn_wtu(const float* __restrict__ W, const float* __restrict__ u, int R, int K,
-                                                       int rows_per_split, float* part, float* __restrict__ nrm_part) {
-    sn_wtu_body(W, u, R, K, rows_per_split, part, nrm_part, blockIdx.x, blockIdx.y, gridDim.y, &g_sn_colticket[blockIdx.x]);
+                                                       int rows_per_split, float* part, float* __restrict__ nrm_part, int lane) {
+    sn_wtu_body(W, u, R, K, rows_per_split, part, nrm_part, blockIdx.x, blockIdx.y, gridDim.y, &g_sn_colticket[lane][blockIdx.x]);
 }
 
 // phase 2: v = t / max(|t|, eps) (training), s = W v (warp per row); last block: sigma, u
@@ -174,8 +179,8 @@ __device__ __forceinline__ void sn_wv_body(const float* __restrict__ W, const fl
 __global__ void __launch_bounds__(SN_THREADS) k_sn_wv(const float* __restrict__ W, const float* __restrict__ t, const float* __restrict__ nrm_part,
                                                       int nchunks, int R, int K, int power, float eps, float* s, float* u_buf,
                                                       float* __restrict__ u_save, float* __restrict__ v_buf, float* __restrict__ v_save,
-                                                      float* __restrict__ sigma) {
-    sn_wv_body(W, t, nrm_part, nchunks, R, K, power, eps, s, u_buf, u_save, v_buf, v_save, sigma, blockIdx.x, gridDim.x, &g_sn_ticket[1]);
+                                                      float* __restrict__ sigma, int lane) {
+    sn_wv_body(W, t, nrm_part, nchunks, R, K, power, eps, s, u_buf, u_save, v_buf, v_save, sigma, blockIdx.x, gridDim.x, &g_sn_ticket[lane][1]);
 }
 
 // phase 3: W_sn (R, taps, Cin) = W (R, Cin, taps) / sigma.  Block = (SN_CI input channels of one row): a coalesced
@@ -258,8 +263,8 @@ __device__ __forceinline__ void sn_dot_body(const float* __restrict__ a, const f
     if (threadIdx.x == 0) *c_out = t;
 }
 __global__ void __launch_bounds__(SN_THREADS) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, long long total,
-                                                       float* part, float* __restrict__ c_out) {
-    sn_dot_body(a, b, total, part, c_out, blockIdx.x, gridDim.x, &g_sn_ticket[2]);
+                                                       float* part, float* __restrict__ c_out, int lane) {
+    sn_dot_body(a, b, total, part, c_out, blockIdx.x, gridDim.x, &g_sn_ticket[lane][2]);
 }
 
 // backward phase 2: dW (R, Cin, taps) = (dW_sn (R, taps, Cin) - c u v^T) / sigma; same tiling as k_sn_scale, transposing back
@@ -460,13 +465,15 @@ extern "C" int fsv_spectral_fwd(const float* w_orig, float* u, float* v, int R, 
     float* v_save = uvs;            // uvs = [v (K) | u (R) | sigma]: v first keeps it 16-byte aligned for the float4 loads
     float* u_save = uvs + K;
     float* sigma = uvs + K + R;
+    const int lane = fsv_current_reduction_lane();
+    FSV_REQUIRE(lane >= 0 && lane < SN_LANES, "spectral_fwd: reduction lane %d out of range", lane);
     if (power) {
         dim3 g(nchunks, rs);
-        k_sn_wtu<<<g, SN_THREADS, 0, st>>>(w_orig, u, R, K, rps, part, nrm_part);
+        k_sn_wtu<<<g, SN_THREADS, 0, st>>>(w_orig, u, R, K, rps, part, nrm_part, lane);
         FSV_CHECK_LAUNCH("spectral_wtu");
     }
     k_sn_wv<<<fsv_cdiv(R, SN_THREADS / 32), SN_THREADS, 0, st>>>(w_orig, power ? part : v, nrm_part, nchunks, R, K, power, eps, s, u, u_save,
-                                                                 v, v_save, sigma);
+                                                                 v, v_save, sigma, lane);
     FSV_CHECK_LAUNCH("spectral_wv");
     if (wt_out) {
         const int RB = taps <= 9 ? 32 : 16;
@@ -496,7 +503,9 @@ extern "C" int fsv_spectral_bwd(const float* dw_ohwi, const float* w_sn_ohwi, co
     if (blocks > 4096) blocks = 4096;
     float* part = work;
     float* c = work + 4096;
-    k_sn_dot<<<blocks, SN_THREADS, 0, st>>>(dw_ohwi, w_sn_ohwi, total, part, c);
+    const int lane = fsv_current_reduction_lane();
+    FSV_REQUIRE(lane >= 0 && lane < SN_LANES, "spectral_bwd: reduction lane %d out of range", lane);
+    k_sn_dot<<<blocks, SN_THREADS, 0, st>>>(dw_ohwi, w_sn_ohwi, total, part, c, lane);
     FSV_CHECK_LAUNCH("spectral_dot");
     dim3 g2(fsv_cdiv(Cin, SN_CI), R);
     k_sn_bwd<<<g2, SN_CI, 0, st>>>(dw_ohwi, uvs + K, uvs, uvs + K + R, c, Cin, taps, dw_orig);

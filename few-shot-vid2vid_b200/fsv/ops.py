@@ -33,7 +33,7 @@ UP2_BWD_SOURCE = os.environ.get('FSV_UP2_BWD', '1') != '0'
 # mostly small-grid kernels per iteration (a 512 -> 512 linear's weight gradient is 64 CTAs, a 64 -> 64 one a single CTA), and what is
 # still queued when the data-gradient chain ends drains serially (round-2 timeline: a 2.6 ms tail of one-at-a-time launches).  Lane 0
 # is the gathering lane: the grouped spectral backward and the gradient buckets run there after waiting for the lanes used so far.
-SIDE_LANES = max(1, int(os.environ.get('FSV_SIDE_LANES', '3')))
+SIDE_LANES = min(4, max(1, int(os.environ.get('FSV_SIDE_LANES', '3'))))
 _SIDE, _SIDE_DIRTY = {}, {}           # lane 0 per device; streams that forked work since the last join
 _SIDE_EXTRA, _SIDE_USED, _SIDE_RR = {}, {}, {}
 
@@ -45,6 +45,8 @@ def _side_lanes(dev):
     extra = _SIDE_EXTRA.get(dev)
     if extra is None or len(extra) != SIDE_LANES - 1:
         extra = _SIDE_EXTRA[dev] = [torch.cuda.Stream(device=dev) for _ in range(SIDE_LANES - 1)]
+    for li, st in enumerate([side] + extra):
+        _LANES.setdefault(st.cuda_stream, 4 + li)      # reduction-ticket lanes 4 .. 7 (per-weight spectral backward runs on lane 0 of these)
     return [side] + extra
 
 
@@ -142,7 +144,8 @@ def _off(t, off_floats):
 # branch stream uses lane 1.  FSV_BRANCH_STREAMS=0 keeps the forward on one stream.
 BRANCH_STREAMS = os.environ.get('FSV_BRANCH_STREAMS', '1') != '0'
 _BRANCH, _LANES = {}, {}
-_LANE_FNS = ('fsv_norm_stats', 'fsv_norm_stats_finalize', 'fsv_norm_apply_bwd', 'fsv_norm_apply_bwd2', 'fsv_spade_norm_bwd')
+_LANE_FNS = ('fsv_norm_stats', 'fsv_norm_stats_finalize', 'fsv_norm_apply_bwd', 'fsv_norm_apply_bwd2', 'fsv_spade_norm_bwd', 'fsv_spectral_fwd',
+             'fsv_spectral_bwd')
 
 
 def aux_stream(index):
